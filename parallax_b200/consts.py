@@ -1,0 +1,69 @@
+"""Environment-variable protocol between launcher ("master") and workers.
+
+Parity: reference `parallax/parallax/core/python/common/consts.py:18-38` and
+`common/partitions.py:29-31`, `common/lib.py:59-62`.  The contract is kept
+(the same script is re-executed on every worker and an env var tells the
+process which role it plays) but workers are one process per GPU for *every*
+run option, rendezvousing through `torch.distributed` on 127.0.0.1 / the
+first host instead of mpirun + gRPC.
+"""
+import os
+import getpass
+
+# --- role selection ---------------------------------------------------------
+PARALLAX_RUN_OPTION = "PARALLAX_RUN_OPTION"
+PARALLAX_RUN_MASTER = "PARALLAX_RUN_MASTER"
+PARALLAX_RUN_MPI = "PARALLAX_RUN_MPI"
+PARALLAX_RUN_PS = "PARALLAX_RUN_PS"
+PARALLAX_RUN_HYBRID = "PARALLAX_RUN_HYBRID"
+
+# --- worker identity --------------------------------------------------------
+PARALLAX_WORKER_ID = "PARALLAX_WORKER_ID"
+PARALLAX_NUM_WORKERS = "PARALLAX_NUM_WORKERS"
+PARALLAX_RESOURCE_INFO = "PARALLAX_RESOURCE_INFO"
+PARALLAX_MACHINE_ID = "PARALLAX_MACHINE_ID"
+PARALLAX_HOSTNAME = "PARALLAX_HOSTNAME"
+PARALLAX_LOCAL_RANK = "PARALLAX_LOCAL_RANK"
+
+# --- partition search -------------------------------------------------------
+PARALLAX_MIN_PARTITIONS = "PARALLAX_MIN_PARTITIONS"
+PARALLAX_PARTITIONS = "PARALLAX_PARTITIONS"
+PARALLAX_SEARCH = "PARALLAX_SEARCH"
+PARALLAX_SEARCH_ADDR = "PARALLAX_SEARCH_ADDR"
+
+# --- misc -------------------------------------------------------------------
+PARALLAX_LOG_LEVEL = "PARALLAX_LOG_LEVEL"
+PARALLAX_FABRIC = "PARALLAX_FABRIC"            # "nvlink" | "host" (tests)
+PARALLAX_TIMELINE = "PARALLAX_TIMELINE"        # chrome-trace output path
+PARALLAX_STALL_CHECK_TIME_SECONDS = "PARALLAX_STALL_CHECK_TIME_SECONDS"
+PARALLAX_STALL_SHUTDOWN_TIME_SECONDS = "PARALLAX_STALL_SHUTDOWN_TIME_SECONDS"
+PARALLAX_FUSION_THRESHOLD = "PARALLAX_FUSION_THRESHOLD"
+PARALLAX_AUTOTUNE = "PARALLAX_AUTOTUNE"
+PARALLAX_AUTOTUNE_LOG = "PARALLAX_AUTOTUNE_LOG"
+PARALLAX_DEBUG_CONSISTENCY = "PARALLAX_DEBUG_CONSISTENCY"
+
+
+def _user():
+    try:
+        return getpass.getuser()
+    except Exception:  # pragma: no cover - containers without passwd entry
+        return str(os.getuid())
+
+
+REMOTE_PARALLAX_ROOT = os.path.join("/tmp", "parallax-%s" % _user())
+
+# Step window used to time a partition candidate
+# (reference `common/session_context.py:28-29`).
+NUM_ITERATIONS_FOR_WARMUP = 50
+NUM_ITERATIONS_FOR_TEST = 100
+
+RUN_OPTIONS = ("PS", "MPI", "HYBRID")
+# "AR" is accepted as a modern alias of the reference's "MPI" run option.
+RUN_OPTION_ALIASES = {"AR": "MPI", "ALLREDUCE": "MPI"}
+
+RUN_OPTION_TO_ENV = {
+    "MPI": PARALLAX_RUN_MPI,
+    "PS": PARALLAX_RUN_PS,
+    "HYBRID": PARALLAX_RUN_HYBRID,
+}
+ENV_TO_RUN_OPTION = {v: k for k, v in RUN_OPTION_TO_ENV.items()}

@@ -1,0 +1,199 @@
+"""Optimizer specifications with TensorFlow-1.x update semantics.
+
+The reference does not implement optimizers; it recognises TF's update ops in
+the user graph (`graph_transform_lib.py:56-75`: ApplyGradientDescent,
+ApplyMomentum, ApplyAdagrad, ApplyAdam, ApplyRMSProp … and, for sparse
+variables, SparseApplyAdagrad / Scatter*) and runs TF's kernels
+(`tensorflow/core/kernels/training_ops_gpu.cu.cc:28-283`, CPU sparse
+`training_ops.cc:1276-1382`).  Here an optimizer is a *spec* (kind +
+hyper-parameters); the math is executed by
+
+* the fused sm_100a kernels (`ops/csrc/kernels/dense_step.cu`,
+  `sparse_apply.cu`) on the NVLink fabric, or
+* the pure-torch fp32 functions in this file on the host fabric — which are
+  also the numerics oracle for the kernel tests.
+
+Update rules (g = aggregated gradient):
+
+* sgd      : w -= lr·g
+* momentum : a = μ·a + g ; w -= lr·a            (nesterov: w -= lr·(g + μ·a))
+* adagrad  : a += g² ; w -= lr·g / sqrt(a)       (a₀ = initial_accumulator_value)
+* adam     : m = β₁m+(1-β₁)g ; v = β₂v+(1-β₂)g² ;
+             w -= lr·sqrt(1-β₂ᵗ)/(1-β₁ᵗ) · m/(sqrt(v)+ε)
+* rmsprop  : ms = ρ·ms+(1-ρ)g² ; mom = μ·mom + lr·g/sqrt(ms+ε) ; w -= mom
+
+Sparse variants touch only the rows present in the aggregated gradient
+("lazy" Adam/momentum, exactly like TF's sparse apply ops).
+"""
+import math
+
+import torch
+
+KINDS = ("sgd", "momentum", "adagrad", "adam", "rmsprop")
+KIND_ID = {k: i for i, k in enumerate(KINDS)}
+# number of fp32 state slots per kind
+NUM_SLOTS = {"sgd": 0, "momentum": 1, "adagrad": 1, "adam": 2, "rmsprop": 2}
+SLOT_NAMES = {
+    "sgd": (), "momentum": ("momentum",), "adagrad": ("accumulator",),
+    "adam": ("m", "v"), "rmsprop": ("ms", "mom"),
+}
+
+# layout of the device-side hyper-parameter vector read by the kernels
+HP_LR, HP_A, HP_B, HP_EPS, HP_WD, HP_STEP, HP_GSCALE, HP_FLAGS = range(8)
+HP_SIZE = 8
+
+
+class Optimizer(object):
+    kind = None
+
+    def __init__(self, learning_rate, weight_decay=0.0, name=None):
+        self.learning_rate = learning_rate
+        self.weight_decay = float(weight_decay)
+        self.name = name or type(self).__name__
+
+    # -- hyper-parameters ----------------------------------------------------
+    def lr_at(self, step):
+        lr = self.learning_rate
+        return float(lr(step)) if callable(lr) else float(lr)
+
+    def slot_init(self):
+        """Initial value of each state slot."""
+        return tuple(0.0 for _ in range(NUM_SLOTS[self.kind]))
+
+    def hyper(self, step):
+        """Vector [lr, a, b, eps, wd, step, gscale, flags] for step `step`
+        (1-based count of the update being applied)."""
+        hp = [0.0] * HP_SIZE
+        hp[HP_LR] = self.lr_at(step)
+        hp[HP_WD] = self.weight_decay
+        hp[HP_STEP] = float(step)
+        hp[HP_GSCALE] = 1.0
+        self._fill(hp, step)
+        return hp
+
+    def _fill(self, hp, step):
+        pass
+
+    def describe(self):
+        d = {k: v for k, v in vars(self).items() if not callable(v)}
+        d["kind"] = self.kind
+        return d
+
+
+class GradientDescent(Optimizer):
+    kind = "sgd"
+
+
+class Momentum(Optimizer):
+    kind = "momentum"
+
+    def __init__(self, learning_rate, momentum=0.9, use_nesterov=False, **kw):
+        super().__init__(learning_rate, **kw)
+        self.momentum = float(momentum)
+        self.use_nesterov = bool(use_nesterov)
+
+    def _fill(self, hp, step):
+        hp[HP_A] = self.momentum
+        hp[HP_FLAGS] = 1.0 if self.use_nesterov else 0.0
+
+
+class Adagrad(Optimizer):
+    kind = "adagrad"
+
+    def __init__(self, learning_rate, initial_accumulator_value=0.1, **kw):
+        super().__init__(learning_rate, **kw)
+        self.initial_accumulator_value = float(initial_accumulator_value)
+
+    def slot_init(self):
+        return (self.initial_accumulator_value,)
+
+
+class Adam(Optimizer):
+    kind = "adam"
+
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999,
+                 epsilon=1e-8, **kw):
+        super().__init__(learning_rate, **kw)
+        self.beta1, self.beta2, self.epsilon = \
+            float(beta1), float(beta2), float(epsilon)
+
+    def _fill(self, hp, step):
+        hp[HP_A], hp[HP_B], hp[HP_EPS] = self.beta1, self.beta2, self.epsilon
+        # bias-corrected step size, folded on the host (TF does the same in
+        # `_prepare`/`_finish`)
+        t = max(int(step), 1)
+        hp[HP_LR] = self.lr_at(step) * math.sqrt(1.0 - self.beta2 ** t) / \
+            (1.0 - self.beta1 ** t)
+
+
+class RMSProp(Optimizer):
+    kind = "rmsprop"
+
+    def __init__(self, learning_rate, decay=0.9, momentum=0.0,
+                 epsilon=1e-10, **kw):
+        super().__init__(learning_rate, **kw)
+        self.decay, self.momentum, self.epsilon = \
+            float(decay), float(momentum), float(epsilon)
+
+    def _fill(self, hp, step):
+        hp[HP_A], hp[HP_B], hp[HP_EPS] = self.decay, self.momentum, self.epsilon
+
+
+# TF-style aliases
+GradientDescentOptimizer = GradientDescent
+MomentumOptimizer = Momentum
+AdagradOptimizer = Adagrad
+AdamOptimizer = Adam
+RMSPropOptimizer = RMSProp
+
+
+# ---------------------------------------------------------------------------
+# fp32 torch reference math (host fabric + test oracle)
+# ---------------------------------------------------------------------------
+def apply_dense_(kind, w, g, slots, hp):
+    """In-place update of fp32 tensor `w` with gradient `g` (already
+    aggregated); `slots` is a tuple of fp32 state tensors shaped like `w`."""
+    lr, a, b, eps, wd = hp[HP_LR], hp[HP_A], hp[HP_B], hp[HP_EPS], hp[HP_WD]
+    g = g.to(torch.float32) * hp[HP_GSCALE]
+    if wd != 0.0:
+        g = g + wd * w
+    if kind == "sgd":
+        w.add_(g, alpha=-lr)
+    elif kind == "momentum":
+        (acc,) = slots
+        acc.mul_(a).add_(g)
+        if hp[HP_FLAGS] >= 0.5:
+            w.add_(g + a * acc, alpha=-lr)
+        else:
+            w.add_(acc, alpha=-lr)
+    elif kind == "adagrad":
+        (acc,) = slots
+        acc.addcmul_(g, g)
+        w.addcdiv_(g, acc.sqrt(), value=-lr)
+    elif kind == "adam":
+        m, v = slots
+        m.mul_(a).add_(g, alpha=1.0 - a)
+        v.mul_(b).addcmul_(g, g, value=1.0 - b)
+        w.addcdiv_(m, v.sqrt().add_(eps), value=-lr)
+    elif kind == "rmsprop":
+        ms, mom = slots
+        ms.mul_(a).addcmul_(g, g, value=1.0 - a)
+        mom.mul_(b).add_(g / (ms + eps).sqrt(), alpha=lr)
+        w.sub_(mom)
+    else:  # pragma: no cover
+        raise ValueError(kind)
+    return w
+
+
+def apply_sparse_rows_(kind, w, rows, g, slots, hp):
+    """Row-sparse update: `rows` (int64, unique) index dim 0 of `w`/`slots`;
+    `g` is [len(rows), D] — the *summed* gradient of each row."""
+    if rows.numel() == 0:
+        return w
+    w_r = w.index_select(0, rows)
+    s_r = tuple(s.index_select(0, rows) for s in slots)
+    apply_dense_(kind, w_r, g, s_r, hp)
+    w.index_copy_(0, rows, w_r)
+    for s, sr in zip(slots, s_r):
+        s.index_copy_(0, rows, sr)
+    return w
