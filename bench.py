@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Headline benchmark: LM1B words/sec (default) or ResNet-50 images/sec.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+        --master-addr 127.0.0.1 --master-port 29500 bench.py --gpus 8 ...
+
+Config = the reference's: LM1B vocab 793 470, emb 512, LSTM
+2048→512, 20 steps, batch 128/GPU, sampled softmax 8192, Adagrad, HYBRID sync;
+synthetic ids (`lm1b_distributed_driver.py:81-84`), random-init weights.
+words/s = steps × batch × num_steps × N / time (`:101-102`).
+
+Timing: W warm-up steps, then exactly K steps bracketed by barrier +
+cuda.synchronize, CUDA events on the launching stream, MAX over ranks.  The
+embedding / softmax tables (1.6 GB each, + Adagrad slots) are ≫ the 126 MB L2
+and every step touches fresh random rows, so no explicit L2 flush is needed
+("inputs larger than L2").  `e2e` times the same K steps through the public
+API (`sess.run`) with per-step H2D of the batch from pinned memory and a D2H
+read of the loss.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BASELINE_LM1B_WPS = 277000.0     # Parallax-HYBRID, 48× TITAN Xp
+BASELINE_RESNET_IPS = 7550.0     # Parallax-HYBRID, 48× TITAN Xp
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="parallax_b200",
+                    choices=["parallax_b200", "reference", "nccl"])
+    ap.add_argument("--model", default="lm1b", choices=["lm1b", "resnet50"])
+    ap.add_argument("--run-option", default="HYBRID")
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--small", action="store_true",
+                    help="tiny config for plumbing checks (NOT a valid number)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.lines, self.gpu = None, [], gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def reference_arm(args):
+    """Reference arm: the UNMODIFIED reference from baseline/_ref through its
+    own public API.  Its pure-python `parallax` package installs offline
+    (pip --no-deps from a /tmp copy) but importing it needs the
+    snuspl TensorFlow r1.11 fork + Horovod 0.16.3 + mpirun, none of which exist
+    for CUDA 12.9 / sm_100 or in /opt/wheelhouse — so the arm reports
+    `unavailable` with the actual import error."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    env = dict(os.environ, PYTHONPATH=ref_dir)
+    why = "baseline/_ref is empty (reference not installed)"
+    if os.path.isdir(os.path.join(ref_dir, "parallax")):
+        r = subprocess.run([sys.executable, "-c", "import parallax"], env=env,
+                           cwd="/tmp", capture_output=True, text=True)
+        if r.returncode == 0:
+            why = ("reference imports, but its runtime (TF1.11 fork kernels built for "
+                   "compute_35/70, Horovod, mpirun) cannot run on sm_100")
+        else:
+            last = (r.stderr.strip().splitlines() or ["import failed"])[-1]
+            why = ("reference `import parallax` fails: %s; it requires the snuspl "
+                   "TensorFlow r1.11 fork + Horovod 0.16.3 + mpirun (not in "
+                   "/opt/wheelhouse, no sm_100 build)" % last)
+    print(json.dumps({"impl": "reference", "unavailable": why}))
+    return 0
+
+
+def build_lm1b(args, parallax, torch):
+    from parallax_b200.models.lm1b import LM1B, lm1b_graph
+    if args.small:
+        kw = dict(vocab_size=50000, emb_size=128, state_size=512, projected_size=128,
+                  num_sampled=1024, num_steps=8, num_shards=8)
+        batch = args.batch or 32
+    else:
+        kw = dict(vocab_size=793470, emb_size=512, state_size=2048, projected_size=512,
+                  num_sampled=8192, num_steps=20, num_shards=32)
+        batch = args.batch or 128
+    model = LM1B(lazy=True, **kw)
+    graph = lm1b_graph(model, batch_size=batch)
+    T, V = kw["num_steps"], kw["vocab_size"]
+
+    def make_batch(gen):
+        x = torch.randint(0, V, (batch, T), generator=gen, dtype=torch.int64)
+        y = torch.randint(0, V, (batch, T), generator=gen, dtype=torch.int64)
+        return {"x": x, "y": y}
+    desc = {"model": "lm1b(vocab=%d,emb=%d,lstm=%d->%d,steps=%d,sampled=%d)" % (
+        V, kw["emb_size"], kw["state_size"], kw["projected_size"], T, kw["num_sampled"]),
+        "per_gpu_batch": batch, "seq_len": T, "optimizer": "adagrad(0.2)",
+        "items_per_step": batch * T}
+    return graph, make_batch, desc, "lm1b_words_per_sec", "words/s", BASELINE_LM1B_WPS
+
+
+def build_resnet(args, parallax, torch):
+    from parallax_b200.models.resnet import resnet50, resnet_graph
+    batch = args.batch or (8 if args.small else 64)
+    model = resnet50(num_classes=1000)
+    graph = resnet_graph(model)
+    hw = 64 if args.small else 224
+
+    def make_batch(gen):
+        return {"images": torch.randn(batch, 3, hw, hw, generator=gen),
+                "labels": torch.randint(0, 1000, (batch,), generator=gen)}
+    desc = {"model": "resnet50_v1", "per_gpu_batch": batch, "seq_len": hw,
+            "optimizer": "momentum(0.9)", "items_per_step": batch}
+    return graph, make_batch, desc, "resnet50_images_per_sec", "images/s", BASELINE_RESNET_IPS
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+    import torch
+    import torch.distributed as dist
+    if args.impl == "nccl":
+        from baseline.nccl_reference import main as nccl_main
+        return nccl_main(args)
+    import parallax_b200 as parallax
+    from parallax_b200.parallel import nvops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun for --gpus > 1"
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device", "metric": "lm1b_words_per_sec"}))
+        return 1
+    torch.manual_seed(1234 + rank)
+    builder = build_lm1b if args.model == "lm1b" else build_resnet
+    graph, make_batch, desc, metric, unit, baseline = builder(args, parallax, torch)
+    sc = {"compute_dtype": args.dtype, "cuda_graph": not args.no_graph}
+    cfg = parallax.Config(run_option=args.run_option, search_partitions=False,
+                          sess_config=sc)
+    sess, nw, wid, _ = parallax.parallel_run(graph, "localhost:0", sync=True,
+                                             parallax_config=cfg)
+    eng = sess.engine
+    dev = eng.comm.device
+    gen = torch.Generator().manual_seed(99 + rank)
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    # ---- device-timed arm: inputs resident on the device -------------------
+    batches = [{k: v.to(dev) for k, v in make_batch(gen).items()} for _ in range(4)]
+    for i in range(Wm):
+        eng.train_step(batches[i % 4])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    l0 = nvops.launches["n"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(K):
+        out = eng.train_step(batches[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    launches = nvops.launches["n"] - l0
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    loss_val = float(out["loss"])
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # ---- end-to-end arm: public API, pinned H2D in, loss D2H out -------------
+    e2e = None
+    if not args.no_e2e:
+        host_batches = [{k: v.pin_memory() for k, v in make_batch(gen).items()}
+                        for _ in range(4)]
+        h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+        for i in range(3):
+            sess.run(["loss", "train_op"], {k: [v] for k, v in host_batches[i % 4].items()})
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(K):
+            loss, _ = sess.run(["loss", "train_op"],
+                               {k: [v] for k, v in host_batches[i % 4].items()})
+        s1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t2 = torch.tensor([s0.elapsed_time(s1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms2 = float(t2.item())
+        e2e = {"value": desc["items_per_step"] * world * K / (ms2 / 1e3), "unit": unit,
+               "ms_per_step": ms2 / K, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "last_loss": float(loss[0])}
+    clocks = sampler.stop() if rank == 0 else None
+
+    value = desc["items_per_step"] * world * K / (ms / 1e3)
+    if rank == 0:
+        rec = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world,
+            "steps": K, "warmup": Wm, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": value / baseline, "dtype": args.dtype,
+            "data": "synthetic (random ids / images, random-init weights)",
+            "impl": "parallax_b200",
+            "config": {"model": desc["model"],
+                       "global_batch": desc["per_gpu_batch"] * world,
+                       "seq_len": desc["seq_len"],
+                       "parallelism": "dp%d/%s/sync" % (world, eng.run_option.lower()),
+                       "optimizer": desc["optimizer"],
+                       "l2": "inputs larger than L2 (tables >> 126 MB, fresh random rows each step)"
+                       if args.model == "lm1b" else "activations+weights >> L2 per step",
+                       "cuda_graph": bool(getattr(eng, "graph_captured", False)),
+                       "valid": not args.small},
+            "baseline": {"value": baseline,
+                         "what": "Parallax-HYBRID on 48x TITAN Xp (BASELINE.md)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "loss": loss_val,
+        }
+        print(json.dumps(rec))
+    sess.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,155 @@
+"""LM1B language model (the reference's headline sparse workload).
+
+Parity: `parallax/parallax/examples/lm1b/language_model.py:18-110` (model) and
+`language_model_graph.py:24-81` (training graph):
+
+* vocab 793 470, embedding 512, one LSTM layer with 2048 cells projected to
+  512, 20 unrolled steps, dropout keep 0.9 on inputs and outputs, batch 128
+  per GPU;
+* `emb` and `softmax_w` are partitioned variables
+  (`parallax.get_partitioner(num_variable_shards)`, default 32); with
+  `softmax_b` they are *sparse* (their gradients are IndexedSlices);
+* LSTM math: ``i, j, f, o = split(xw_plus_b(cat(x, h), W, B))``,
+  ``c = σ(f + 1)·c + σ(i)·tanh(j)``, ``h = (σ(o)·tanh(c)) @ W_P``;
+* loss: `tf.nn.sampled_softmax_loss` with 8192 log-uniform negatives shared by
+  the batch (accidental hits removed), mean over batch×steps, scaled by
+  ``num_steps`` before differentiation;
+* Adagrad(lr 0.2, initial accumulator 1.0); embedding grads × batch_size; LSTM
+  grads clipped to global norm 10; EMA(0.999) over the LSTM variables.
+
+Differences: negatives are drawn with replacement on the device (no host
+round-trip for TF's rejection loop), expected counts adjusted accordingly;
+the input half of the LSTM matmul for all time steps is hoisted into one GEMM.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import nn as pnn
+from .. import optim
+from ..graph import (Graph, ClipByGlobalNorm, ScaleGradients,
+                     ExponentialMovingAverage)
+from ..partitions import get_partitioner
+
+
+def log_uniform_sample(num_sampled, range_max, device, generator=None):
+    """ids ~ P(k) = log((k+2)/(k+1)) / log(range_max+1), with replacement."""
+    u = torch.rand(num_sampled, device=device, generator=generator)
+    ids = (torch.exp(u * math.log(range_max + 1.0)) - 1.0).to(torch.int64)
+    return ids.clamp_(0, range_max - 1)
+
+
+def log_uniform_logq(ids, num_sampled, range_max):
+    """log of the expected count of each id among `num_sampled` draws."""
+    idf = ids.to(torch.float32)
+    p = (torch.log(idf + 2.0) - torch.log(idf + 1.0)) / math.log(range_max + 1.0)
+    return torch.log(p * num_sampled)
+
+
+class LM1B(nn.Module):
+    def __init__(self, vocab_size=793470, emb_size=512, state_size=2048,
+                 projected_size=512, num_sampled=8192, num_steps=20,
+                 num_shards=32, keep_prob=0.9, lazy=False):
+        super().__init__()
+        self.vocab_size, self.emb_size = vocab_size, emb_size
+        self.state_size, self.projected_size = state_size, projected_size
+        self.num_sampled, self.num_steps = num_sampled, num_steps
+        self.keep_prob = keep_prob
+        part = get_partitioner(num_shards)
+        self.emb = pnn.Embedding(vocab_size, emb_size, partitioner=part, lazy=lazy)
+        self.softmax_w = pnn.Embedding(vocab_size, projected_size,
+                                       partitioner=part, lazy=lazy, seed=4321)
+        self.softmax_b = pnn.Embedding(vocab_size, 1, partitioner=part, lazy=lazy,
+                                       init_scale=0.0, seed=99)
+        k = emb_size + projected_size
+        self.W = nn.Parameter(torch.empty(k, 4 * state_size).uniform_(
+            -math.sqrt(3.0 / k), math.sqrt(3.0 / k)))
+        self.B = nn.Parameter(torch.zeros(4 * state_size))
+        self.W_P = nn.Parameter(torch.empty(state_size, projected_size).uniform_(
+            -math.sqrt(3.0 / state_size), math.sqrt(3.0 / state_size)))
+
+    def lstm(self, x, c, h):
+        """x: [B, T, E] -> outputs [B*T, P] (time-major inside), final c, h."""
+        Bsz, T, E = x.shape
+        S = self.state_size
+        Wx, Wh = self.W[:E], self.W[E:]
+        # hoisted input GEMM for all steps: [T*B, E] @ [E, 4S] + B
+        xw = torch.addmm(self.B, x.transpose(0, 1).reshape(T * Bsz, E), Wx)
+        xw = xw.view(T, Bsz, 4 * S)
+        outs = []
+        for t in range(T):
+            gates = torch.addmm(xw[t], h, Wh)
+            i, j, f, o = gates.split(S, dim=1)
+            c = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+            m = torch.sigmoid(o) * torch.tanh(c)
+            h = m @ self.W_P
+            out = h
+            if self.training and self.keep_prob < 1.0:
+                out = F.dropout(out, 1.0 - self.keep_prob)
+            outs.append(out)
+        # [B, T, P] order to match labels y.reshape(-1)
+        return torch.stack(outs, dim=1).reshape(Bsz * T, -1), c, h
+
+    def forward(self, x, y, w=None, initial_state_c=None, initial_state_h=None):
+        Bsz, T = x.shape
+        dev = self.W.device
+        dt = self.W.dtype
+        e = self.emb(x)
+        if e.dtype != dt:
+            e = e.to(dt)
+        if self.training and self.keep_prob < 1.0:
+            e = F.dropout(e, 1.0 - self.keep_prob)
+        c = initial_state_c if initial_state_c is not None else \
+            torch.zeros(Bsz, self.state_size, device=dev, dtype=dt)
+        h = initial_state_h if initial_state_h is not None else \
+            torch.zeros(Bsz, self.projected_size, device=dev, dtype=dt)
+        c, h = c.to(dt), h.to(dt)
+        inputs, c, h = self.lstm(e, c, h)
+        targets = y.reshape(-1)
+        if self.training and self.num_sampled > 0:
+            loss = self.sampled_softmax_loss(inputs, targets)
+        else:
+            loss = self.full_softmax_loss(inputs, targets)
+        if w is not None:
+            loss = loss * w.reshape(-1).to(loss.dtype)
+        return {"loss": loss.mean(), "final_state_c": c.detach(),
+                "final_state_h": h.detach()}
+
+    def sampled_softmax_loss(self, inputs, targets):
+        N, S, V = targets.numel(), self.num_sampled, self.vocab_size
+        sampled = log_uniform_sample(S, V, inputs.device)
+        ids = torch.cat([targets.to(torch.int64), sampled])
+        w_all = self.softmax_w(ids)                 # [N+S, P]
+        b_all = self.softmax_b(ids).squeeze(-1)     # [N+S]
+        if w_all.dtype != inputs.dtype:
+            w_all = w_all.to(inputs.dtype)
+        true_w, samp_w = w_all[:N], w_all[N:]
+        logq = log_uniform_logq(ids, S, V)
+        true_logits = (inputs * true_w).sum(-1).float() + b_all[:N].float() - logq[:N]
+        samp_logits = (inputs @ samp_w.t()).float() + (b_all[N:].float() - logq[N:])
+        hits = targets.unsqueeze(1) == sampled.unsqueeze(0)
+        samp_logits = samp_logits.masked_fill(hits, -1e30)
+        lse = torch.logsumexp(torch.cat([true_logits.unsqueeze(1), samp_logits], 1), 1)
+        return lse - true_logits
+
+    def full_softmax_loss(self, inputs, targets):
+        ids = torch.arange(self.vocab_size, device=inputs.device)
+        w = self.softmax_w(ids).to(inputs.dtype)
+        b = self.softmax_b(ids).squeeze(-1).float()
+        logits = (inputs @ w.t()).float() + b
+        return F.cross_entropy(logits, targets, reduction="none")
+
+
+def lm1b_graph(model, batch_size=128, learning_rate=0.2, max_grad_norm=10.0):
+    """The training graph of `language_model_graph.py:24-81`."""
+    lstm_vars = ["W", "B", "W_P"]
+    return Graph(
+        model,
+        optimizer=optim.Adagrad(learning_rate, initial_accumulator_value=1.0),
+        loss="loss", loss_scale=float(model.num_steps),
+        grad_rules=[ScaleGradients(float(batch_size), params=["emb.weight"]),
+                    ClipByGlobalNorm(max_grad_norm, params=lstm_vars)],
+        ema=ExponentialMovingAverage(0.999, params=lstm_vars),
+        name="lm1b")

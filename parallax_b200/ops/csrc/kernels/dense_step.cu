@@ -1,0 +1,300 @@
+// Fused dense step: reduce-scatter (pull) → fp32 optimizer on the owned slice
+// → all-gather of the *updated parameters* (push), in ONE kernel.
+//
+// What it replaces in the reference:
+//   AR / HYBRID dense : ncclAllReduce on the fusion buffer + `tf.div` +
+//     one Apply<Optimizer> Eigen kernel per variable on every replica
+//     (horovod/common/ops/nccl_operations.cc:60-109,
+//      horovod/tensorflow/__init__.py:76-81,
+//      tensorflow/core/kernels/training_ops_gpu.cu.cc:28-283)
+//   PS dense (sync)   : ConditionalAccumulator.take_grad(num_workers) on the PS
+//     CPU, chief applies, token queues, mirror-variable refresh
+//     (graph_transform_lib.py:330-582, :584-704)
+// Both are the same data movement on an NVSwitch box: the rank that owns
+// slice r is that slice's "parameter server".  Owning the slice also means
+// only 1/W of the fp32 master weights and optimizer slots live on each GPU.
+//
+// MODE 0 FUSED        : barrier, reduce, update, push params, barrier
+// MODE 1 REDUCE_ONLY  : barrier, reduce → fp32 scratch + Σg² (for global-norm
+//                       clipping the norm must be known before any update)
+// MODE 2 UPDATE_PUSH  : scratch·clip → update, push params, barrier
+// World 1 degenerates to a fused multi-tensor optimizer (also used as the
+// local update after a plain all-reduce in "replicated" AR mode).
+#include "common.cuh"
+#include "launch.h"
+
+enum { PX_SGD = 0, PX_MOMENTUM = 1, PX_ADAGRAD = 2, PX_ADAM = 3, PX_RMSPROP = 4 };
+enum { HP_LR = 0, HP_A, HP_B, HP_EPS, HP_WD, HP_STEP, HP_GSCALE, HP_FLAGS };
+
+struct DenseStepArgs {
+  PeerPtrs grads;    // rotated, element type T
+  PeerPtrs params;   // rotated, element type T
+  float* master;     // [slice] fp32 master weights of the owned slice
+  float* slot0;      // [slice] or null
+  float* slot1;      // [slice] or null
+  float* ema;        // [slice] or null
+  float* red;        // [slice] fp32 scratch (modes 1/2) or null
+  const float* hp;   // device hyper-parameters (8 floats)
+  const float* clip; // device scalar multiplier or null
+  float* sumsq;      // device scalar accumulator or null
+  size_t n;          // bucket elements, multiple of W * VN
+  float avg;         // 1/num_workers (or 1)
+  float ema_decay;
+  int rank, ch_start, ch_end, kind, mode;
+};
+
+__device__ __forceinline__ void px_update(int kind, float lr, float a, float b, float eps,
+                                          float wd, float nesterov, float g, float& w, float& s0,
+                                          float& s1) {
+  if (wd != 0.f) g = fmaf(wd, w, g);
+  switch (kind) {
+    case PX_SGD: w = fmaf(-lr, g, w); break;
+    case PX_MOMENTUM:
+      s0 = fmaf(a, s0, g);
+      w = nesterov != 0.f ? fmaf(-lr, fmaf(a, s0, g), w) : fmaf(-lr, s0, w);
+      break;
+    case PX_ADAGRAD:
+      s0 = fmaf(g, g, s0);
+      w = fmaf(-lr * g, rsqrtf(s0), w);
+      break;
+    case PX_ADAM:
+      s0 = fmaf(a, s0, (1.f - a) * g);
+      s1 = fmaf(b, s1, (1.f - b) * g * g);
+      w -= lr * s0 / (sqrtf(s1) + eps);
+      break;
+    case PX_RMSPROP:
+      s0 = fmaf(a, s0, (1.f - a) * g * g);
+      s1 = fmaf(b, s1, lr * g * rsqrtf(s0 + eps));
+      w -= s1;
+      break;
+  }
+}
+
+template <int VN>
+__device__ __forceinline__ void ld_f32(const float* p, float* f) {
+#pragma unroll
+  for (int i = 0; i < VN / 4; ++i) {
+    const uint4 v = ld_v4(p + 4 * i);
+    f[4 * i] = __uint_as_float(v.x); f[4 * i + 1] = __uint_as_float(v.y);
+    f[4 * i + 2] = __uint_as_float(v.z); f[4 * i + 3] = __uint_as_float(v.w);
+  }
+}
+template <int VN>
+__device__ __forceinline__ void st_f32(float* p, const float* f) {
+#pragma unroll
+  for (int i = 0; i < VN / 4; ++i)
+    st_v4(p + 4 * i, make_uint4(__float_as_uint(f[4 * i]), __float_as_uint(f[4 * i + 1]),
+                                __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3])));
+}
+
+template <typename T, int W>
+__global__ void __launch_bounds__(512)
+px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr) {
+  constexpr int VN = Vec16<T>::N;
+  const int mode = a.mode, kind = a.kind;
+  if (W > 1 && mode != 2) px_block_barrier(pads, epoch_ctr, a.ch_start, a.rank, W);
+  const size_t slice = a.n / W;
+  const size_t nvec = slice / VN;
+  const size_t base = (size_t)a.rank * slice;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const float lr = a.hp[HP_LR], ha = a.hp[HP_A], hb = a.hp[HP_B], eps = a.hp[HP_EPS],
+              wd = a.hp[HP_WD], nesterov = a.hp[HP_FLAGS];
+  float gmul = a.avg * a.hp[HP_GSCALE];
+  if (mode == 2) gmul = 1.f;                       // already applied in REDUCE
+  if (mode != 1 && a.clip != nullptr) gmul *= *a.clip;
+  float ss = 0.f;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const size_t e = v * VN;                        // element offset inside the slice
+    float g[VN];
+    if (mode == 2) {
+      ld_f32<VN>(a.red + e, g);
+    } else {
+      uint4 in[W];
+#pragma unroll
+      for (int p = 0; p < W; ++p)
+        in[p] = ld_v4_stream(reinterpret_cast<const T*>(a.grads.p[p]) + base + e);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) g[i] = 0.f;
+#pragma unroll
+      for (int p = 0; p < W; ++p) {
+        float f[VN];
+        Vec16<T>::unpack(in[p], f);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) g[i] += f[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VN; ++i) g[i] *= gmul;
+    if (mode == 1) {
+#pragma unroll
+      for (int i = 0; i < VN; ++i) ss += g[i] * g[i];
+      st_f32<VN>(a.red + e, g);
+      continue;
+    }
+    float w[VN], s0[VN], s1[VN];
+    ld_f32<VN>(a.master + e, w);
+    if (a.slot0) ld_f32<VN>(a.slot0 + e, s0);
+    if (a.slot1) ld_f32<VN>(a.slot1 + e, s1);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) px_update(kind, lr, ha, hb, eps, wd, nesterov, g[i], w[i], s0[i], s1[i]);
+    st_f32<VN>(a.master + e, w);
+    if (a.slot0) st_f32<VN>(a.slot0 + e, s0);
+    if (a.slot1) st_f32<VN>(a.slot1 + e, s1);
+    if (a.ema) {
+      float m[VN];
+      ld_f32<VN>(a.ema + e, m);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) m[i] -= (1.f - a.ema_decay) * (m[i] - w[i]);
+      st_f32<VN>(a.ema + e, m);
+    }
+    const uint4 out = Vec16<T>::pack(w);
+#pragma unroll
+    for (int p = 0; p < W; ++p)
+      st_v4_stream(reinterpret_cast<T*>(a.params.p[p]) + base + e, out);
+  }
+  if (mode == 1 && a.sumsq != nullptr) block_atomic_sum(ss, a.sumsq);
+  if (W > 1 && mode != 1) px_block_barrier(pads, epoch_ctr, a.ch_end, a.rank, W);
+}
+
+// scale = max_norm / max(sqrt(total), max_norm)  (tf.clip_by_global_norm);
+// also exports the norm and zeroes the accumulator for the next step.
+__global__ void px_clip_scale_kernel(const float* sumsq, float max_norm, float* scale_out,
+                                     float* norm_out, float* zero_after) {
+  const float norm = sqrtf(*sumsq);
+  *scale_out = max_norm / fmaxf(norm, max_norm);
+  if (norm_out) *norm_out = norm;
+  if (zero_after) *zero_after = 0.f;
+}
+
+// Asynchronous PS dense apply (Hogwild): this rank's gradient is applied,
+// un-averaged, straight onto every owner's master slice over NVLink, and the
+// refreshed values are pulled back into the local parameter mirror.
+// Reference: sync=False ⇒ no accumulators, update ops race on the PS
+// variables (ps/between_graph_parallel.py:137-146).
+template <typename T, int W>
+__global__ void __launch_bounds__(512)
+px_dense_async_kernel(const T* __restrict__ my_grads, T* __restrict__ my_params,
+                      PeerPtrs master, PeerPtrs slot0, PeerPtrs slot1, const float* hp,
+                      const float* clip, size_t n, int kind, int rank) {
+  constexpr int VN = Vec16<T>::N;
+  const size_t slice = n / W;
+  const size_t nvec = n / VN;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const float lr = hp[HP_LR], ha = hp[HP_A], hb = hp[HP_B], eps = hp[HP_EPS], wd = hp[HP_WD],
+              nesterov = hp[HP_FLAGS];
+  float gmul = hp[HP_GSCALE];
+  if (clip != nullptr) gmul *= *clip;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const size_t e = v * VN;
+    const int owner = (int)(e / slice);
+    const size_t le = e - (size_t)owner * slice;
+    float *pm = nullptr, *p0 = nullptr, *p1 = nullptr;
+#pragma unroll
+    for (int p = 0; p < W; ++p)     // master/slots arrive in NATURAL rank order
+      if (p == owner) {
+        pm = reinterpret_cast<float*>(master.p[p]) + le;
+        p0 = slot0.p[p] ? reinterpret_cast<float*>(slot0.p[p]) + le : nullptr;
+        p1 = slot1.p[p] ? reinterpret_cast<float*>(slot1.p[p]) + le : nullptr;
+      }
+    float g[VN], w[VN], s0[VN], s1[VN];
+    Vec16<T>::unpack(ld_v4(my_grads + e), g);
+    ld_f32<VN>(pm, w);
+    if (p0) ld_f32<VN>(p0, s0);
+    if (p1) ld_f32<VN>(p1, s1);
+#pragma unroll
+    for (int i = 0; i < VN; ++i)
+      px_update(kind, lr, ha, hb, eps, wd, nesterov, g[i] * gmul, w[i], s0[i], s1[i]);
+    st_f32<VN>(pm, w);
+    if (p0) st_f32<VN>(p0, s0);
+    if (p1) st_f32<VN>(p1, s1);
+    st_v4(my_params + e, Vec16<T>::pack(w));
+  }
+}
+
+// Σx² of a local buffer (used for clipping in the async path)
+template <typename T>
+__global__ void __launch_bounds__(512)
+px_sumsq_kernel(const T* __restrict__ x, size_t n, float mul, float* out) {
+  constexpr int VN = Vec16<T>::N;
+  const size_t nvec = n / VN;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float ss = 0.f;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    float f[VN];
+    Vec16<T>::unpack(ld_v4(x + v * VN), f);
+#pragma unroll
+    for (int i = 0; i < VN; ++i) ss += f[i] * f[i] * mul * mul;
+  }
+  block_atomic_sum(ss, out);
+}
+
+extern "C" {
+
+// dtype 0 fp32 / 1 bf16.  grads/params: `world` pointers in natural order.
+int px_dense_step(const void* const* grads, const void* const* params, float* master,
+                  float* slot0, float* slot1, float* ema, float* red, const float* hp,
+                  const float* clip, float* sumsq, size_t n, float avg, float ema_decay,
+                  int kind, int mode, int dtype, void* pads_dev, void* epoch_ctr, int ch_start,
+                  int ch_end, int rank, int world, int max_blocks, cudaStream_t stream) {
+  if (world < 1 || world > 8) return -3;
+  const int vn = dtype == 0 ? 4 : 8;
+  if (n % ((size_t)world * vn) != 0) return -1;
+  DenseStepArgs a;
+  a.grads = px_rotate(grads, rank, world);
+  a.params = px_rotate(params, rank, world);
+  a.master = master; a.slot0 = slot0; a.slot1 = slot1; a.ema = ema; a.red = red;
+  a.hp = hp; a.clip = clip; a.sumsq = sumsq; a.n = n; a.avg = avg; a.ema_decay = ema_decay;
+  a.rank = rank; a.ch_start = ch_start; a.ch_end = ch_end; a.kind = kind; a.mode = mode;
+  const int threads = 512;
+  int blocks = px_clamp_blocks(n / world / vn, threads, world == 1 ? 0x7fffffff : max_blocks);
+  if (world == 1) {
+    size_t b = (n / vn + threads - 1) / threads;
+    blocks = (int)(b < 1 ? 1 : (b > 148 * 4 ? 148 * 4 : b));
+  }
+#define LAUNCH(T, W)                                                                  \
+  px_dense_step_kernel<T, W><<<blocks, threads, 0, stream>>>(a, (uint32_t* const*)pads_dev, \
+                                                            (uint32_t*)epoch_ctr)
+  if (dtype == 0) { PX_DISPATCH_WORLD(world, LAUNCH, float); }
+  else { PX_DISPATCH_WORLD(world, LAUNCH, __nv_bfloat16); }
+#undef LAUNCH
+  return (int)cudaGetLastError();
+}
+
+int px_clip_scale(const float* sumsq, float max_norm, float* scale_out, float* norm_out,
+                  float* zero_after, cudaStream_t stream) {
+  px_clip_scale_kernel<<<1, 1, 0, stream>>>(sumsq, max_norm, scale_out, norm_out, zero_after);
+  return (int)cudaGetLastError();
+}
+
+int px_dense_async(const void* my_grads, void* my_params, const void* const* master,
+                   const void* const* slot0, const void* const* slot1, const float* hp,
+                   const float* clip, size_t n, int kind, int dtype, int rank, int world,
+                   int max_blocks, cudaStream_t stream) {
+  if (world < 1 || world > 8) return -3;
+  const int vn = dtype == 0 ? 4 : 8;
+  if (n % ((size_t)world * vn) != 0) return -1;
+  PeerPtrs M{}, S0{}, S1{};
+  for (int i = 0; i < world; ++i) {
+    M.p[i] = const_cast<void*>(master[i]);
+    S0.p[i] = slot0 ? const_cast<void*>(slot0[i]) : nullptr;
+    S1.p[i] = slot1 ? const_cast<void*>(slot1[i]) : nullptr;
+  }
+  const int blocks = px_clamp_blocks(n / vn, 512, max_blocks);
+#define LAUNCH(T, W)                                                                   \
+  px_dense_async_kernel<T, W><<<blocks, 512, 0, stream>>>(                             \
+      (const T*)my_grads, (T*)my_params, M, S0, S1, hp, clip, n, kind, rank)
+  if (dtype == 0) { PX_DISPATCH_WORLD(world, LAUNCH, float); }
+  else { PX_DISPATCH_WORLD(world, LAUNCH, __nv_bfloat16); }
+#undef LAUNCH
+  return (int)cudaGetLastError();
+}
+
+int px_sumsq(const void* x, size_t n, int dtype, float mul, float* out, cudaStream_t stream) {
+  const int vn = dtype == 0 ? 4 : 8;
+  const int blocks = px_clamp_blocks(n / vn, 512 * 4, 148 * 2);
+  if (dtype == 0) px_sumsq_kernel<float><<<blocks, 512, 0, stream>>>((const float*)x, n, mul, out);
+  else px_sumsq_kernel<__nv_bfloat16><<<blocks, 512, 0, stream>>>((const __nv_bfloat16*)x, n, mul, out);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -42,7 +42,7 @@ class _LookupFn(torch.autograd.Function):
         flat = ids.reshape(-1)
         rows, token = table.lookup(flat)
         ctx.token = token
-        return rows.view(*ids.shape, table.D)
+        return rows.reshape(*ids.shape, table.D)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -67,7 +67,7 @@ class ShardedEmbedding(tnn.Module):
         if torch.is_grad_enabled():
             return _LookupFn.apply(self._anchor, ids, self.table)
         rows, _ = self.table.lookup(ids.reshape(-1), record=False)
-        return rows.view(*ids.shape, self.table.D)
+        return rows.reshape(*ids.shape, self.table.D)
 
     def extra_repr(self):
         return "V=%d, D=%d, P=%d, replicated=%s" % (
@@ -196,16 +196,34 @@ class TrainEngine(object):
             out = {self.graph.loss: out}
         return out
 
+    def _table_order(self):
+        return [self.tables[k] for k in sorted(self.tables)]
+
     def train_step(self, feeds):
+        """One synchronous (or async-PS) training step.  The order in which
+        peer-synchronising work is issued is static: dense buckets (from
+        autograd hooks, in bucket order) then sparse tables in name order."""
         t0 = time.perf_counter()
+        step = self.global_step + 1
+        if self.dense is not None and hasattr(self.dense, "begin_step"):
+            self.dense.begin_step(step)
+        for t in self._table_order():
+            if hasattr(t, "begin_step"):
+                t.begin_step(step)
         out = self.forward(feeds)
         loss = out[self.graph.loss]
-        (loss * self.graph.loss_scale).backward()
-        self.global_step += 1
-        for t in self.tables.values():
-            t.finish_step(self.global_step)
+        if self.graph.loss_scale != 1.0:
+            (loss * self.graph.loss_scale).backward()
+        else:
+            loss.backward()
+        self.global_step = step
         if self.dense is not None:
-            self.dense.finish_step(self.global_step)
+            self.dense.finish_step(step)
+        for t in self._table_order():
+            t.finish_step(step)
+        if self.backend == "nvlink":
+            torch.cuda.current_stream(self.comm.device).wait_stream(
+                self.fabric.comm_stream)
         out = {k: (v.detach() if torch.is_tensor(v) else v)
                for k, v in out.items()}
         self.step_times.append(time.perf_counter() - t0)
@@ -269,3 +287,7 @@ class TrainEngine(object):
         for t in self.tables.values():
             if hasattr(t, "close"):
                 t.close()
+        fab = getattr(self, "fabric", None)
+        if fab is not None:
+            fab.close()
+            self.fabric = None

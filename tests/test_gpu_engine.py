@@ -1,0 +1,73 @@
+"""End-to-end engine on the NVLink fabric (1 GPU) vs the host-fabric oracle."""
+import numpy as np
+import pytest
+import torch
+
+import parallax_b200 as parallax
+from parallax_b200 import optim
+from parallax_b200.models.simple import MLPWithEmbedding
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(fabric, run_option, opt, steps, compute_dtype=None, sync=True,
+         dense_update="sharded", clip=None):
+    model = MLPWithEmbedding(64, partitioner=parallax.get_partitioner(3))
+    rules = [parallax.ClipByGlobalNorm(clip, params=["fc1.*", "fc2.*"])] if clip else []
+    graph = parallax.Graph(model, optimizer=opt, grad_rules=rules,
+                           ema=parallax.ExponentialMovingAverage(0.9, ["fc2.*"]))
+    sc = {"fabric": fabric, "dense_update": dense_update}
+    if compute_dtype:
+        sc["compute_dtype"] = compute_dtype
+    cfg = parallax.Config(run_option=run_option, sess_config=sc)
+    sess, *_ = parallax.parallel_run(graph, "localhost:0", sync=sync,
+                                     parallax_config=cfg)
+    g = torch.Generator().manual_seed(0)
+    losses = []
+    for s in range(steps):
+        ids = torch.randint(0, 64, (8, 3), generator=g)
+        ids[:, 0] = 5
+        labels = torch.randint(0, 4, (8,), generator=g)
+        loss, _ = sess.run(["loss", "train_op"], {"ids": [ids], "labels": [labels]})
+        losses.append(loss[0])
+    sd = sess.engine.state_dict()
+    sess.close()
+    return losses, sd
+
+
+@pytest.mark.parametrize("run_option", ["HYBRID", "MPI", "PS"])
+@pytest.mark.parametrize("opt_name", ["sgd", "adagrad", "adam"])
+def test_engine_matches_host_oracle(run_option, opt_name):
+    mk = lambda: {"sgd": optim.GradientDescent(0.3), "adagrad": optim.Adagrad(0.2, 1.0),
+                  "adam": optim.Adam(0.01)}[opt_name]
+    l_ref, sd_ref = _run("host", run_option, mk(), 5, clip=0.5)
+    l_nv, sd_nv = _run("nvlink", run_option, mk(), 5, clip=0.5)
+    np.testing.assert_allclose(l_nv, l_ref, rtol=1e-4, atol=1e-5)
+    for n, w in sd_ref["dense"]["master"].items():
+        torch.testing.assert_close(sd_nv["dense"]["master"][n], w, rtol=1e-4, atol=1e-5)
+    for n, w in sd_ref["dense"]["ema"].items():
+        torch.testing.assert_close(sd_nv["dense"]["ema"][n], w, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(sd_nv["sparse"]["emb.weight"]["weight"],
+                               sd_ref["sparse"]["emb.weight"]["weight"],
+                               rtol=1e-4, atol=1e-5)
+
+
+def test_engine_replicated_update_and_async():
+    l_ref, sd_ref = _run("host", "MPI", optim.Momentum(0.1, 0.9), 4)
+    l_nv, sd_nv = _run("nvlink", "MPI", optim.Momentum(0.1, 0.9), 4,
+                       dense_update="replicated")
+    np.testing.assert_allclose(l_nv, l_ref, rtol=1e-4, atol=1e-5)
+    l_ref, sd_ref = _run("host", "PS", optim.Adagrad(0.2, 1.0), 4, sync=False)
+    l_nv, sd_nv = _run("nvlink", "PS", optim.Adagrad(0.2, 1.0), 4, sync=False)
+    np.testing.assert_allclose(l_nv, l_ref, rtol=1e-4, atol=1e-5)
+
+
+def test_engine_bf16_trains():
+    losses, _ = _run("nvlink", "HYBRID", optim.Adagrad(0.2, 1.0), 12,
+                     compute_dtype="bf16")
+    assert losses[-1] < losses[0]
+
+
+def test_smoke_entry():
+    import __graft_entry__ as ge
+    ge.smoke()

@@ -1,0 +1,185 @@
+"""Sparse-path kernels (lookup / dedup / push / claim / apply / async) vs a
+plain PyTorch fp32 reference, on a world simulated inside one GPU."""
+import pytest
+import torch
+
+import parallax_b200 as parallax
+from parallax_b200 import optim
+
+pytestmark = pytest.mark.gpu
+
+
+def _tables(world, V, D, P, opt, run_option="HYBRID", sync=True, average=False,
+            local_agg=True, out_dtype=torch.float32, strategy="mod", cap=None):
+    from tests.gpu_utils import make_world
+    from parallax_b200.parallel import modes
+    from parallax_b200.parallel.nvlink_backend import NVSparseTable
+    from parallax_b200.graph import Graph
+    fabs = make_world(world)
+    route = modes.route_for(run_option, sync)
+    cfg = parallax.Config(run_option=run_option, average_sparse=average)
+    cfg.communication_config = parallax.CommunicationConfig(
+        parallax.PSConfig(local_aggregation=local_agg))
+    g = torch.Generator().manual_seed(7)
+    W0 = torch.randn(V, D, generator=g)
+    graph = Graph(torch.nn.Linear(1, 1), optimizer=opt)
+    tabs = [NVSparseTable("emb.weight", W0, P, strategy, opt, f, route, graph, cfg,
+                          out_dtype=out_dtype,
+                          options={"sparse_capacity": {"emb.weight": cap or 4096},
+                                   "sparse_blocks": 4})
+            for f in fabs]
+    return fabs, tabs, W0
+
+
+def _full(tabs, V, D):
+    out = torch.zeros(V, D)
+    L = tabs[0].layout
+    owners = [0] if L.replicated else range(len(tabs))
+    for o in owners:
+        g, l = L.global_ids_of_owner(o)
+        out[g] = tabs[o].table[:, :D].cpu()[l]
+    return out
+
+
+@pytest.mark.parametrize("world,P,strategy", [(1, 1, "mod"), (2, 5, "mod"),
+                                              (4, 8, "div"), (8, 32, "mod")])
+@pytest.mark.parametrize("D", [4, 64, 130])
+def test_lookup_matches_index_select(world, P, strategy, D):
+    V = 1000
+    fabs, tabs, W0 = _tables(world, V, D, P, optim.GradientDescent(0.1),
+                             strategy=strategy)
+    torch.cuda.synchronize()
+    for r, t in enumerate(tabs):
+        ids = torch.randint(0, V, (257,), device="cuda")
+        rows, pend = t.lookup(ids)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(rows.cpu(), W0[ids.cpu()])
+        assert torch.equal(pend.cpu().long(), ids.cpu())
+    for f in fabs:
+        f.close()
+
+
+@pytest.mark.parametrize("world,run_option", [(1, "HYBRID"), (2, "HYBRID"),
+                                              (4, "PS"), (4, "MPI"), (8, "HYBRID")])
+@pytest.mark.parametrize("kind", ["sgd", "adagrad", "adam"])
+@pytest.mark.parametrize("local_agg", [True, False])
+def test_push_claim_apply(world, run_option, kind, local_agg):
+    V, D, P = 503, 36, 8
+    opt = {"sgd": optim.GradientDescent(0.5), "adagrad": optim.Adagrad(0.2, 1.0),
+           "adam": optim.Adam(0.05)}[kind]
+    fabs, tabs, W0 = _tables(world, V, D, P, opt, run_option=run_option,
+                             average=(kind == "adam"), local_agg=local_agg)
+    ref_w = W0.clone()
+    ref_slots = tuple(torch.full_like(W0, v) for v in opt.slot_init())
+    gen = torch.Generator().manual_seed(11)
+    n = 300
+    for t in tabs:
+        t._ensure_capacity(n)
+    for t in tabs:
+        t.warm(n)
+    torch.cuda.synchronize()
+    for step in (1, 2, 3):
+        all_ids, all_g = [], []
+        toks = []
+        for r, t in enumerate(tabs):
+            ids = torch.randint(0, V, (n,), generator=gen)
+            ids[:40] = ids[0]                     # duplicates inside a rank
+            ids[40:60] = 17                       # and across ranks
+            gr = torch.randn(n, D, generator=gen)
+            rows, pend = t.lookup(ids.cuda())
+            toks.append(pend)
+            all_ids.append(ids)
+            all_g.append(gr)
+        torch.cuda.synchronize()
+        # lookups observe the previous step's update
+        for r, t in enumerate(tabs):
+            rows, _ = t.lookup(all_ids[r].cuda(), record=False)
+            torch.cuda.synchronize()
+            torch.testing.assert_close(rows.cpu(), ref_w[all_ids[r]], rtol=1e-4, atol=1e-5)
+        for r, t in enumerate(tabs):
+            t.add_pending(toks[r], all_g[r].cuda())
+            t.begin_step(step)
+        torch.cuda.synchronize()
+        for r, t in enumerate(tabs):
+            t.finish_step(step)
+        torch.cuda.synchronize()
+        ids_c, g_c = torch.cat(all_ids), torch.cat(all_g)
+        u, inv = torch.unique(ids_c, return_inverse=True)
+        gsum = torch.zeros(u.numel(), D).index_add_(0, inv, g_c)
+        if kind == "adam":
+            gsum /= world
+        optim.apply_sparse_rows_(kind, ref_w, u, gsum, ref_slots, opt.hyper(step))
+        if run_option == "MPI":
+            for t in tabs:        # every replica applied the same update
+                torch.testing.assert_close(t.table[:, :D].cpu(), ref_w, rtol=2e-4, atol=2e-5)
+        else:
+            torch.testing.assert_close(_full(tabs, V, D), ref_w, rtol=2e-4, atol=2e-5)
+    for f in fabs:
+        f.close()
+
+
+def test_large_n_uses_global_hash_and_bf16_grads():
+    V, D, P, world = 20011, 32, 4, 2
+    opt = optim.Adagrad(0.1, 1.0)
+    fabs, tabs, W0 = _tables(world, V, D, P, opt, out_dtype=torch.bfloat16,
+                             cap=40000)
+    n = 20000                                   # > SMEM_MAX_N -> global hash path
+    for t in tabs:
+        t._ensure_capacity(n)
+        assert not t.use_smem
+    for t in tabs:
+        t.warm(n)
+    gen = torch.Generator().manual_seed(3)
+    all_ids, all_g, toks = [], [], []
+    for r, t in enumerate(tabs):
+        ids = torch.randint(0, V, (n,), generator=gen)
+        gr = torch.randn(n, D, generator=gen).bfloat16()
+        rows, pend = t.lookup(ids.cuda())
+        assert rows.dtype == torch.bfloat16
+        toks.append(pend)
+        all_ids.append(ids)
+        all_g.append(gr)
+    torch.cuda.synchronize()
+    for r, t in enumerate(tabs):
+        t.add_pending(toks[r], all_g[r].cuda())
+        t.begin_step(1)
+    torch.cuda.synchronize()
+    for t in tabs:
+        t.finish_step(1)
+    torch.cuda.synchronize()
+    ids_c, g_c = torch.cat(all_ids), torch.cat(all_g).float()
+    u, inv = torch.unique(ids_c, return_inverse=True)
+    gsum = torch.zeros(u.numel(), D).index_add_(0, inv, g_c)
+    ref_w = W0.clone()
+    optim.apply_sparse_rows_("adagrad", ref_w, u, gsum,
+                             (torch.full_like(W0, 1.0),), opt.hyper(1))
+    torch.testing.assert_close(_full(tabs, V, D), ref_w, rtol=1e-3, atol=1e-4)
+    for f in fabs:
+        f.close()
+
+
+def test_async_apply_single_writer_matches_reference():
+    """Hogwild path, exercised without races (one rank pushes at a time)."""
+    V, D, P, world = 301, 16, 4, 2
+    opt = optim.Adagrad(0.3, 1.0)
+    fabs, tabs, W0 = _tables(world, V, D, P, opt, run_option="PS", sync=False)
+    ref_w, ref_acc = W0.clone(), torch.full_like(W0, 1.0)
+    gen = torch.Generator().manual_seed(5)
+    for t in tabs:
+        t.warm(64)
+    for step in (1, 2):
+        for r, t in enumerate(tabs):
+            ids = torch.randint(0, V, (64,), generator=gen)
+            gr = torch.randn(64, D, generator=gen)
+            rows, pend = t.lookup(ids.cuda())
+            t.add_pending(pend, gr.cuda())
+            t.begin_step(step)
+            t.finish_step(step)
+            torch.cuda.synchronize()
+            u, inv = torch.unique(ids, return_inverse=True)
+            gsum = torch.zeros(u.numel(), D).index_add_(0, inv, gr)
+            optim.apply_sparse_rows_("adagrad", ref_w, u, gsum, (ref_acc,),
+                                     opt.hyper(step))
+    torch.testing.assert_close(_full(tabs, V, D), ref_w, rtol=2e-4, atol=2e-5)
+    for f in fabs:
+        f.close()
