@@ -188,9 +188,13 @@ class TrainEngine(object):
 
     # ------------------------------------------------------------------- run
     def _prepare_feeds(self, feeds):
-        return feeds
+        dev = self.comm.device if self.backend != "host" else torch.device("cpu")
+        return {k: (v.to(dev, non_blocking=True)
+                    if torch.is_tensor(v) and v.device != dev else v)
+                for k, v in feeds.items()}
 
     def forward(self, feeds):
+        feeds = self._prepare_feeds(feeds)
         out = self.model(**feeds)
         if not isinstance(out, dict):
             out = {self.graph.loss: out}
@@ -199,24 +203,23 @@ class TrainEngine(object):
     def _table_order(self):
         return [self.tables[k] for k in sorted(self.tables)]
 
-    def train_step(self, feeds):
-        """One synchronous (or async-PS) training step.  The order in which
-        peer-synchronising work is issued is static: dense buckets (from
-        autograd hooks, in bucket order) then sparse tables in name order."""
-        t0 = time.perf_counter()
-        step = self.global_step + 1
+    def _begin_step(self, step):
         if self.dense is not None and hasattr(self.dense, "begin_step"):
             self.dense.begin_step(step)
         for t in self._table_order():
             if hasattr(t, "begin_step"):
                 t.begin_step(step)
+
+    def _step_body(self, feeds, step):
+        """forward + backward + aggregation + update.  The order in which
+        peer-synchronising work is issued is static: dense buckets (from
+        autograd hooks, in bucket order) then sparse tables in name order."""
         out = self.forward(feeds)
         loss = out[self.graph.loss]
         if self.graph.loss_scale != 1.0:
             (loss * self.graph.loss_scale).backward()
         else:
             loss.backward()
-        self.global_step = step
         if self.dense is not None:
             self.dense.finish_step(step)
         for t in self._table_order():
@@ -224,10 +227,65 @@ class TrainEngine(object):
         if self.backend == "nvlink":
             torch.cuda.current_stream(self.comm.device).wait_stream(
                 self.fabric.comm_stream)
-        out = {k: (v.detach() if torch.is_tensor(v) else v)
-               for k, v in out.items()}
+        return {k: (v.detach() if torch.is_tensor(v) else v)
+                for k, v in out.items()}
+
+    def train_step(self, feeds):
+        """One synchronous (or async-PS) training step.
+
+        On the NVLink fabric with ``sess_config['cuda_graph']`` the whole step
+        (forward, backward, every bucket/table kernel on the comm stream) is
+        captured once into a CUDA graph after a few eager warm-up steps and
+        replayed afterwards: the step is launch-bound otherwise (an unrolled
+        20-step LSTM is ~1.5k tiny kernels).  All cross-rank state the kernels
+        need (barrier epochs, step counters, hyper-parameters) lives in device
+        memory, so a replay is exactly a re-execution."""
+        t0 = time.perf_counter()
+        step = self.global_step + 1
+        self._begin_step(step)
+        if self._use_graph():
+            out = self._graph_step(feeds, step)
+        else:
+            out = self._step_body(feeds, step)
+        self.global_step = step
         self.step_times.append(time.perf_counter() - t0)
         return out
+
+    # ------------------------------------------------------------ CUDA graph
+    def _use_graph(self):
+        if self.backend != "nvlink" or not self.config.sess_option("cuda_graph", False):
+            return False
+        return self.global_step >= int(self.config.sess_option("graph_warmup", 3))
+
+    @staticmethod
+    def _feed_sig(feeds):
+        return tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(feeds.items()))
+
+    def _graph_step(self, feeds, step):
+        sig = self._feed_sig(feeds)
+        st = getattr(self, "_graph_state", None)
+        if st is None or st["sig"] != sig:
+            if st is not None:
+                parallax_log.warning("feed signature changed; re-capturing the step graph")
+            dev = self.comm.device
+            static = {k: torch.empty_like(v, device=dev) for k, v in feeds.items()}
+            for k, v in feeds.items():
+                static[k].copy_(v, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            if self.comm.distributed:
+                self.comm.barrier()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                out = self._step_body(static, step)
+            st = {"sig": sig, "graph": g, "in": static, "out": out}
+            self._graph_state = st
+            self.graph_captured = True
+            parallax_log.info("captured the training step into a CUDA graph")
+        else:
+            for k, v in feeds.items():
+                st["in"][k].copy_(v, non_blocking=True)
+        st["graph"].replay()
+        return st["out"]
 
     def eval_step(self, feeds):
         with torch.no_grad():

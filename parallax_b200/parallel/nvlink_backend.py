@@ -598,8 +598,9 @@ class NVSparseTable(object):
         self.stats["steps"] += 1
         cur = torch.cuda.current_stream(self.device)
         cs.wait_stream(cur)
-        pend_ids.record_stream(cs)
-        grads.record_stream(cs)
+        if not torch.cuda.is_current_stream_capturing():
+            pend_ids.record_stream(cs)
+            grads.record_stream(cs)
         nvops.sparse_dedup(pend_ids, n, self.hbits, self.keys, self.slot_u,
                            self.uniq_id, self.uniq_k, self.uniq_head, self.next,
                            self.ctl, self.geom, self.local_aggregation,

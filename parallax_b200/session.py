@@ -74,14 +74,13 @@ class ParallaxSession(object):
         return feeds
 
     def _to_device(self, v):
-        dev = self.engine.comm.device if self.engine.backend != "host" \
-            else torch.device("cpu")
+        """Feeds stay where the user put them (typically pinned host memory);
+        the engine issues the H2D copy itself — straight into the captured
+        graph's static input buffers when the step is graph-replayed."""
         if isinstance(v, np.ndarray):
             v = torch.from_numpy(v)
         elif not torch.is_tensor(v):
             v = torch.as_tensor(v)
-        if v.device != dev:
-            v = v.to(dev, non_blocking=True)
         return v
 
     # -------------------------------------------------------------------- run

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# simulated multi-rank worlds put up to 8 spinning kernels on 8 streams of one
+# GPU: give every stream its own hardware queue (must precede CUDA init).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -11,12 +11,12 @@ pytestmark = pytest.mark.gpu
 
 
 def _run(fabric, run_option, opt, steps, compute_dtype=None, sync=True,
-         dense_update="sharded", clip=None):
+         dense_update="sharded", clip=None, same_batch=False, graph=False):
     model = MLPWithEmbedding(64, partitioner=parallax.get_partitioner(3))
     rules = [parallax.ClipByGlobalNorm(clip, params=["fc1.*", "fc2.*"])] if clip else []
     graph = parallax.Graph(model, optimizer=opt, grad_rules=rules,
                            ema=parallax.ExponentialMovingAverage(0.9, ["fc2.*"]))
-    sc = {"fabric": fabric, "dense_update": dense_update}
+    sc = {"fabric": fabric, "dense_update": dense_update, "cuda_graph": graph}
     if compute_dtype:
         sc["compute_dtype"] = compute_dtype
     cfg = parallax.Config(run_option=run_option, sess_config=sc)
@@ -25,6 +25,8 @@ def _run(fabric, run_option, opt, steps, compute_dtype=None, sync=True,
     g = torch.Generator().manual_seed(0)
     losses = []
     for s in range(steps):
+        if same_batch:
+            g = torch.Generator().manual_seed(0)
         ids = torch.randint(0, 64, (8, 3), generator=g)
         ids[:, 0] = 5
         labels = torch.randint(0, 4, (8,), generator=g)
@@ -64,8 +66,21 @@ def test_engine_replicated_update_and_async():
 
 def test_engine_bf16_trains():
     losses, _ = _run("nvlink", "HYBRID", optim.Adagrad(0.2, 1.0), 12,
-                     compute_dtype="bf16")
+                     compute_dtype="bf16", same_batch=True)
     assert losses[-1] < losses[0]
+
+
+def test_engine_cuda_graph_matches_eager():
+    """The captured+replayed step must produce the same trajectory as eager."""
+    l_e, sd_e = _run("nvlink", "HYBRID", optim.Adagrad(0.2, 1.0), 8, clip=0.5)
+    l_g, sd_g = _run("nvlink", "HYBRID", optim.Adagrad(0.2, 1.0), 8, clip=0.5,
+                     graph=True)
+    np.testing.assert_allclose(l_g, l_e, rtol=1e-5, atol=1e-6)
+    for n, w in sd_e["dense"]["master"].items():
+        torch.testing.assert_close(sd_g["dense"]["master"][n], w, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(sd_g["sparse"]["emb.weight"]["weight"],
+                               sd_e["sparse"]["emb.weight"]["weight"],
+                               rtol=1e-5, atol=1e-6)
 
 
 def test_smoke_entry():
