@@ -1,0 +1,439 @@
+"""Horovod-style collective API over the NVLink fabric.
+
+Parity: `horovod/tensorflow/__init__.py:36-82` (`allreduce` — dense mean/sum;
+``IndexedSlices`` ⇒ allgather of values + indices), `:85-138` (broadcast of
+variables), `horovod/torch/mpi_ops.py:86-422` (handle API: `*_async`, `poll`,
+`synchronize`), `horovod/common/operations.cc:1625-1803` (init/rank/size,
+name-keyed enqueue, DUPLICATE_NAME_ERROR `:1713-1716`), fusion buffer
+(`fusion_buffer_manager.{h,cc}`, 64 MiB default `operations.cc:1030`).
+
+Design: there is no background negotiation thread.  Every rank calls the same
+ops in the same order (torch programs are rank-symmetric); an op is one or
+two kernels on the caller's stream:
+
+* ≤ `oneshot_bytes`  : staged one-shot all-reduce (one barrier, latency-bound)
+* larger              : copy into the symmetric workspace (the "fusion
+  buffer") → two-shot in-place reduce-scatter/all-gather kernel → copy out,
+  chunked by the workspace size.  Tensors allocated with `symmetric_empty`
+  skip both copies.
+The 1/size scaling and dtype handling are inside the kernel epilogue (Horovod
+runs a separate `div` kernel, `horovod/torch/mpi_ops_v2.cc:66-71`).
+
+Cross-rank validation (Horovod's coordinator errors, `operations.cc:213-415`)
+is done the first time a *name* is seen: shape/dtype/op digests are exchanged
+once and cached (`registry` — the analogue of the response cache,
+`response_cache.{h,cc}`); later calls with the same name skip the exchange.
+"""
+import ctypes
+import threading
+
+import torch
+import torch.distributed as dist
+
+from .log import parallax_log
+from .parallel.fabric import Comm
+
+_state = None
+
+
+class HorovodInternalError(RuntimeError):
+    pass
+
+
+class _State(object):
+    def __init__(self, comm, workspace_bytes, oneshot_bytes):
+        self.comm = comm
+        self.cuda = comm.is_cuda
+        self.fabric = None
+        self.handles = {}
+        self.next_handle = 1
+        self.inflight_names = set()
+        self.registry = {}
+        self.lock = threading.Lock()
+        self.timeline = None
+        if self.cuda:
+            from .parallel.nvlink_backend import NVFabric
+            self.fabric = NVFabric(comm)
+            heap = self.fabric.heap
+            self.ws_bytes = int(workspace_bytes)
+            self.ws = heap.alloc(self.ws_bytes, "fusion_workspace")
+            self.oneshot_bytes = int(oneshot_bytes)
+            self.stage = heap.alloc(2 * self.oneshot_bytes, "oneshot_stage")
+            self.user_bufs = {}
+
+
+def init(comm=None, workspace_bytes=64 << 20, oneshot_bytes=256 << 10):
+    """Initialise (idempotent).  `comm` defaults to the torchrun environment."""
+    global _state
+    if _state is not None:
+        return
+    comm = comm or Comm.from_env()
+    _state = _State(comm, workspace_bytes, oneshot_bytes)
+
+
+def shutdown():
+    global _state
+    if _state is None:
+        return
+    if _state.fabric is not None:
+        _state.fabric.close()
+    _state = None
+
+
+def _st():
+    if _state is None:
+        raise ValueError("parallax collectives have not been initialised; "
+                         "call init() first")
+    return _state
+
+
+def is_initialized():
+    return _state is not None
+
+
+def rank():
+    return _st().comm.rank
+
+
+def size():
+    return _st().comm.world
+
+
+def local_rank():
+    return _st().comm.local_rank
+
+
+def local_size():
+    import os
+    return int(os.environ.get("LOCAL_WORLD_SIZE", _st().comm.world))
+
+
+# ---------------------------------------------------------------------------
+def _validate(name, kind, tensor, extra=()):
+    """First use of `name`: exchange (kind, dtype, shape[1:] or shape) and
+    raise on every rank if they differ — Horovod's mismatch errors."""
+    st = _st()
+    if name is None or not st.comm.distributed:
+        return
+    shape = tuple(tensor.shape[1:]) if kind == "allgather" else tuple(tensor.shape)
+    sig = (kind, str(tensor.dtype), shape, tensor.device.type) + tuple(extra)
+    if st.registry.get(name) == sig:
+        return                                  # cache hit: no negotiation
+    sigs = st.comm.all_gather_object(sig)
+    if len(set(sigs)) != 1:
+        st.registry.pop(name, None)
+        raise HorovodInternalError(
+            "Mismatched %s for tensor %r across ranks: %s" % (kind, name, sigs))
+    st.registry[name] = sig
+
+
+def _vn(dtype):
+    return 16 // torch.empty((), dtype=dtype).element_size()
+
+
+def symmetric_empty(numel, dtype=torch.float32):
+    """A tensor in symmetric memory (collective call: every rank must allocate
+    the same sequence).  `allreduce_` on it is zero-copy."""
+    st = _st()
+    es = torch.empty((), dtype=dtype).element_size()
+    q = st.comm.world * _vn(dtype)
+    n = (int(numel) + q - 1) // q * q
+    buf = st.fabric.heap.alloc(n * es, "user")
+    t = buf.tensor(dtype, n)[:numel]
+    st.user_bufs[t.data_ptr()] = (buf, n)
+    return t
+
+
+def _allreduce_cuda(x, out, scale):
+    from .parallel import nvops
+    from .parallel.symmetric import CH_USER
+    st = _st()
+    heap, W = st.fabric.heap, st.comm.world
+    dt = x.dtype
+    if dt not in nvops.DT:
+        y = torch.empty_like(x, dtype=torch.float32)
+        _allreduce_cuda(x.float(), y, scale)
+        out.copy_(y.to(dt))
+        return out
+    es = x.element_size()
+    n = x.numel()
+    if n == 0:
+        return out
+    flat, oflat = x.reshape(-1), out.reshape(-1)
+    ub = st.user_bufs.get(x.data_ptr())
+    if ub is not None and out.data_ptr() == x.data_ptr():
+        buf, npad = ub
+        nvops.allreduce_twoshot(heap, buf.c_ptrs(), npad, dt, scale, CH_USER,
+                                max_blocks=st.fabric.max_blocks)
+        return out
+    if n * es <= st.oneshot_bytes and flat.data_ptr() % 16 == 0:
+        # storage may be shorter than the 16 B-padded length: stage a copy then
+        if (n * es) % 16 != 0:
+            pad = torch.zeros((n * es + 15) // 16 * 16 // es, dtype=dt, device=x.device)
+            pad[:n] = flat
+            dst = torch.empty_like(pad)
+            nvops.allreduce_oneshot(heap, pad, dst, st.stage, n, dt, scale,
+                                    CH_USER[0])
+            oflat.copy_(dst[:n])
+        else:
+            nvops.allreduce_oneshot(heap, flat, oflat, st.stage, n, dt, scale,
+                                    CH_USER[0])
+        return out
+    ws = st.ws.tensor(dt)
+    q = W * _vn(dt)
+    chunk = (ws.numel() // q) * q
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        mp = (m + q - 1) // q * q
+        ws[:m].copy_(flat[s:s + m])
+        if mp != m:
+            ws[m:mp].zero_()
+        nvops.allreduce_twoshot(heap, st.ws.c_ptrs(), mp, dt, scale, CH_USER,
+                                max_blocks=st.fabric.max_blocks)
+        oflat[s:s + m].copy_(ws[:m])
+    return out
+
+
+def allreduce(tensor, average=True, name=None, out=None):
+    """Sum (or mean) of `tensor` over all ranks.  A ``torch.sparse`` tensor is
+    reduced Horovod-style: all-gather of indices and values (duplicates kept,
+    values ÷ size when `average`)."""
+    st = _st()
+    if tensor.is_sparse:
+        t = tensor.coalesce()
+        idx = allgather(t.indices().t().contiguous(),
+                        name=None if name is None else name + ".indices")
+        val = allgather(t.values(), name=None if name is None else name + ".values")
+        if average:
+            val = val / st.comm.world
+        return torch.sparse_coo_tensor(idx.t(), val, tensor.shape)
+    _validate(name, "allreduce", tensor)
+    W = st.comm.world
+    scale = (1.0 / W) if average else 1.0
+    if out is None:
+        out = torch.empty_like(tensor)
+    if not tensor.is_cuda or not st.cuda:
+        out.copy_(tensor)
+        if W > 1:
+            dist.all_reduce(out, group=st.comm._grp_for(out))
+        if average:
+            out.div_(W) if out.is_floating_point() else out.floor_divide_(W)
+        return out
+    x = tensor.contiguous()
+    if W == 1:
+        out.copy_(x)
+        return out
+    return _allreduce_cuda(x, out, scale)
+
+
+def allreduce_(tensor, average=True, name=None):
+    return allreduce(tensor, average, name, out=tensor)
+
+
+def grouped_allreduce(tensors, average=True, name=None):
+    """Fuse several tensors of one dtype into the workspace, reduce once,
+    scatter the results back (Horovod tensor fusion,
+    `horovod/common/operations.cc:465-588`)."""
+    st = _st()
+    if not tensors:
+        return []
+    if not st.cuda or st.comm.world == 1 or len({t.dtype for t in tensors}) != 1:
+        return [allreduce(t, average, None) for t in tensors]
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    red = allreduce(flat, average, name)
+    outs, off = [], 0
+    for t in tensors:
+        outs.append(red[off:off + t.numel()].view_as(t))
+        off += t.numel()
+    return outs
+
+
+def allgather(tensor, name=None):
+    """Concatenate `tensor` from all ranks along dim 0 (first dims may differ)."""
+    st = _st()
+    _validate(name, "allgather", tensor)
+    W = st.comm.world
+    if W == 1:
+        return tensor.clone()
+    sizes = st.comm.all_gather_object(int(tensor.shape[0]))
+    if not tensor.is_cuda or not st.cuda:
+        return torch.cat(st.comm.all_gather_varlen(tensor))
+    from .parallel import nvops
+    from .parallel.symmetric import CH_USER
+    x = tensor.contiguous()
+    row = x[0].numel() if x.dim() > 1 and x.shape[0] else \
+        (int(torch.tensor(x.shape[1:]).prod()) if x.dim() > 1 else 1)
+    es = x.element_size()
+    slice_bytes = (max(sizes) * row * es + 15) // 16 * 16
+    if slice_bytes * W > st.ws_bytes:
+        # too large for the workspace: library fallback (rare, control-sized)
+        return torch.cat(st.comm.all_gather_varlen(tensor))
+    wsb = st.ws.bytes_tensor()
+    mine = wsb[st.comm.rank * slice_bytes:st.comm.rank * slice_bytes + x.numel() * es]
+    mine.copy_(x.reshape(-1).view(torch.uint8))
+    nvops.allgather(st.fabric.heap, st.ws.c_ptrs(), slice_bytes, CH_USER,
+                    max_blocks=st.fabric.max_blocks)
+    parts = []
+    for r, n in enumerate(sizes):
+        b = wsb[r * slice_bytes:r * slice_bytes + n * row * es]
+        parts.append(b.view(x.dtype).view((n,) + tuple(x.shape[1:])))
+    return torch.cat(parts)
+
+
+def broadcast(tensor, root_rank, name=None, out=None):
+    st = _st()
+    _validate(name, "broadcast", tensor, extra=(root_rank,))
+    W = st.comm.world
+    if out is None:
+        out = torch.empty_like(tensor)
+    out.copy_(tensor)
+    if W == 1:
+        return out
+    if not tensor.is_cuda or not st.cuda:
+        dist.broadcast(out, src=root_rank, group=st.comm._grp_for(out))
+        return out
+    from .parallel import nvops
+    from .parallel.symmetric import CH_USER
+    flat = out.reshape(-1).view(torch.uint8) if out.is_contiguous() else None
+    src = out.contiguous().reshape(-1).view(torch.uint8)
+    wsb = st.ws.bytes_tensor()
+    n = src.numel()
+    for s in range(0, n, st.ws_bytes):
+        m = min(st.ws_bytes, n - s)
+        mp = (m + 15) // 16 * 16
+        if st.comm.rank == root_rank:
+            wsb[:m].copy_(src[s:s + m])
+        nvops.broadcast(st.fabric.heap, st.ws.c_ptrs(), mp, root_rank, CH_USER,
+                        st.fabric.max_blocks)
+        src[s:s + m].copy_(wsb[:m])
+    if flat is None:
+        out.copy_(src.view(out.dtype).view(out.shape))
+    return out
+
+
+def broadcast_(tensor, root_rank, name=None):
+    return broadcast(tensor, root_rank, name, out=tensor)
+
+
+def broadcast_parameters(params, root_rank=0):
+    """Broadcast a state_dict / named parameters from `root_rank`
+    (`horovod/torch/__init__.py` `broadcast_parameters`,
+    `horovod/tensorflow/__init__.py:85-104`)."""
+    items = sorted(params.items()) if isinstance(params, dict) else sorted(params)
+    for name, p in items:
+        if torch.is_tensor(p):
+            with torch.no_grad():
+                broadcast_(p.data if hasattr(p, "data") else p, root_rank,
+                           name="broadcast." + name)
+
+
+# ------------------------------------------------------------- handle API
+def _enqueue(kind, fn, name):
+    st = _st()
+    with st.lock:
+        if name is not None:
+            if name in st.inflight_names:
+                raise HorovodInternalError(
+                    "Duplicate tensor name %r: a previous %s with this name has "
+                    "not completed" % (name, kind))
+            st.inflight_names.add(name)
+        h = st.next_handle
+        st.next_handle += 1
+    result = fn()
+    ev = None
+    if torch.is_tensor(result) and result.is_cuda:
+        ev = torch.cuda.Event()
+        ev.record()
+    st.handles[h] = (result, ev, name)
+    return h
+
+
+def allreduce_async(tensor, average=True, name=None):
+    return _enqueue("allreduce", lambda: allreduce(tensor, average, name), name)
+
+
+def allreduce_async_(tensor, average=True, name=None):
+    return _enqueue("allreduce", lambda: allreduce_(tensor, average, name), name)
+
+
+def allgather_async(tensor, name=None):
+    return _enqueue("allgather", lambda: allgather(tensor, name), name)
+
+
+def broadcast_async(tensor, root_rank, name=None):
+    return _enqueue("broadcast", lambda: broadcast(tensor, root_rank, name), name)
+
+
+def broadcast_async_(tensor, root_rank, name=None):
+    return _enqueue("broadcast", lambda: broadcast_(tensor, root_rank, name), name)
+
+
+def poll(handle):
+    result, ev, _ = _st().handles[handle]
+    return True if ev is None else ev.query()
+
+
+def synchronize(handle):
+    st = _st()
+    if handle not in st.handles:
+        raise ValueError("unknown handle %r" % handle)
+    result, ev, name = st.handles.pop(handle)
+    if ev is not None:
+        ev.synchronize()
+    if name is not None:
+        st.inflight_names.discard(name)
+    return result
+
+
+class DistributedOptimizer(object):
+    """Wrap a ``torch.optim.Optimizer``: gradients are averaged across ranks
+    before `step()` (`horovod/torch/__init__.py:44-177`: per-parameter hooks
+    fire `allreduce_async_` during backward, `synchronize()` waits).  Here the
+    hooks fuse gradients per dtype in reverse-registration order and reduce
+    them with the fabric kernels; sparse gradients are all-gathered unless
+    `sparse_as_dense` (`horovod/tensorflow/__init__.py:189-192`)."""
+
+    def __init__(self, optimizer, named_parameters=None, sparse_as_dense=False):
+        self.optimizer = optimizer
+        self.sparse_as_dense = sparse_as_dense
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        if named_parameters is not None:
+            names = {id(p): n for n, p in named_parameters}
+        else:
+            names = {}
+        self._names = {id(p): names.get(id(p), "param.%d" % i)
+                       for i, p in enumerate(params)}
+        dup = len(set(self._names.values())) != len(self._names)
+        if dup:
+            raise ValueError("parameter names must be unique")
+        self._params = params
+        self._synchronized = False
+
+    def synchronize(self):
+        dense = [p for p in self._params if p.grad is not None and not p.grad.is_sparse]
+        by_dtype = {}
+        for p in dense:
+            by_dtype.setdefault(p.grad.dtype, []).append(p)
+        for dt, ps in by_dtype.items():
+            outs = grouped_allreduce([p.grad for p in ps], average=True)
+            for p, o in zip(ps, outs):
+                p.grad.copy_(o)
+        for p in self._params:
+            if p.grad is not None and p.grad.is_sparse:
+                if self.sparse_as_dense:
+                    p.grad = allreduce(p.grad.to_dense(), True)
+                else:
+                    p.grad = allreduce(p.grad, True, name="grad." + self._names[id(p)])
+        self._synchronized = True
+
+    def step(self, closure=None):
+        if not self._synchronized:
+            self.synchronize()
+        self._synchronized = False
+        return self.optimizer.step(closure)
+
+    def zero_grad(self, set_to_none=True):
+        return self.optimizer.zero_grad(set_to_none=set_to_none)
+
+    def __getattr__(self, k):
+        return getattr(self.optimizer, k)

@@ -216,12 +216,29 @@ px_sparse_dedup_link_kernel(const int32_t* __restrict__ pend_ids, int n, int hbi
 // One warp per unique id: sum the rows of all positions carrying it (fp32),
 // scale, and store the row + its local index into the owner's receive ring
 // (or every rank's ring in replicated/AR mode) over NVLink.  The last CTA
-// publishes counts and the `pushed` flag.
+// publishes counts and the `pushed` flag.  CH = row chunks of 32 float4 held
+// in registers so the duplicate list is walked once (rows up to 512 floats);
+// longer rows re-walk per group of CH chunks.
 template <typename GradT>
+__device__ __forceinline__ float4 ld_grad4(const GradT* base, size_t f4_index) {
+  if (sizeof(GradT) == 4) {
+    const uint4 v = ld_v4_stream(reinterpret_cast<const float4*>(base) + f4_index);
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z),
+                       __uint_as_float(v.w));
+  } else {
+    const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(base) +
+                                                    f4_index * 8);
+    return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u),
+                       __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+  }
+}
+
+template <typename GradT, int CH>
 __global__ void __launch_bounds__(256)
 px_sparse_push_kernel(const GradT* __restrict__ pend_grads, const int32_t* __restrict__ uniq_id,
                       const int32_t* __restrict__ uniq_k, const int32_t* __restrict__ uniq_head,
-                      const int32_t* __restrict__ next, SparseCtl* ctl, char* const* __restrict__ rings, uint32_t* const* __restrict__ hdrs,
+                      const int32_t* __restrict__ next, SparseCtl* ctl,
+                      char* const* __restrict__ rings, uint32_t* const* __restrict__ hdrs,
                       size_t ring_ids_off, int cap, TableGeom g, float scale, int rank) {
   // do not overwrite a ring the owner may still be draining
   if (threadIdx.x < g.W) {
@@ -235,33 +252,37 @@ px_sparse_push_kernel(const GradT* __restrict__ pend_grads, const int32_t* __res
   const int n_uniq = ctl->n_uniq;
   for (int u = blockIdx.x * warps + (threadIdx.x >> 5); u < n_uniq; u += gridDim.x * warps) {
     const int id = uniq_id[u], k = uniq_k[u];
+    const int head = uniq_head[u];
     int owner, local;
     geom_map(g, id, owner, local);
-    for (int c0 = 0; c0 < g.D4; c0 += 32) {
-      const int c = c0 + lane;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < g.D4) {
-        for (int i = uniq_head[u]; i >= 0; i = next[i]) {
-          if (sizeof(GradT) == 4) {
-            const uint4 v = ld_v4(reinterpret_cast<const float4*>(pend_grads) + (size_t)i * g.D4 + c);
-            acc.x += __uint_as_float(v.x); acc.y += __uint_as_float(v.y);
-            acc.z += __uint_as_float(v.z); acc.w += __uint_as_float(v.w);
-          } else {
-            const uint2 v = *reinterpret_cast<const uint2*>(
-                reinterpret_cast<const char*>(pend_grads) + ((size_t)i * g.D4 + c) * 8);
-            acc.x += __uint_as_float(v.x << 16); acc.y += __uint_as_float(v.x & 0xffff0000u);
-            acc.z += __uint_as_float(v.y << 16); acc.w += __uint_as_float(v.y & 0xffff0000u);
+    for (int c0 = 0; c0 < g.D4; c0 += 32 * CH) {
+      float4 acc[CH];
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = head; i >= 0; i = next[i]) {
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) {
+          const int c = c0 + ch * 32 + lane;
+          if (c < g.D4) {
+            const float4 v = ld_grad4<GradT>(pend_grads, (size_t)i * g.D4 + c);
+            acc[ch].x += v.x; acc[ch].y += v.y; acc[ch].z += v.z; acc[ch].w += v.w;
           }
         }
-        const uint4 o = make_uint4(__float_as_uint(acc.x * scale), __float_as_uint(acc.y * scale),
-                                   __float_as_uint(acc.z * scale), __float_as_uint(acc.w * scale));
-        if (g.replicated) {
-          for (int p = 0; p < g.W; ++p) {
-            const int q = (rank + p) % g.W;
-            st_v4_stream(reinterpret_cast<float4*>(rings[q]) + ((size_t)rank * cap + k) * g.D4 + c, o);
+      }
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        const int c = c0 + ch * 32 + lane;
+        if (c < g.D4) {
+          const uint4 o = make_uint4(__float_as_uint(acc[ch].x * scale), __float_as_uint(acc[ch].y * scale),
+                                     __float_as_uint(acc[ch].z * scale), __float_as_uint(acc[ch].w * scale));
+          if (g.replicated) {
+            for (int p = 0; p < g.W; ++p) {
+              const int q = (rank + p) % g.W;
+              st_v4_stream(reinterpret_cast<float4*>(rings[q]) + ((size_t)rank * cap + k) * g.D4 + c, o);
+            }
+          } else {
+            st_v4_stream(reinterpret_cast<float4*>(rings[owner]) + ((size_t)rank * cap + k) * g.D4 + c, o);
           }
-        } else {
-          st_v4_stream(reinterpret_cast<float4*>(rings[owner]) + ((size_t)rank * cap + k) * g.D4 + c, o);
         }
       }
     }
@@ -567,26 +588,25 @@ int px_sparse_dedup(const int32_t* pend_ids, int n, int hbits, int32_t* keys, in
 int px_sparse_push(const void* pend_grads, int grad_dtype, const int32_t* uniq_id,
                    const int32_t* uniq_k, const int32_t* uniq_head, const int32_t* next,
                    void* ctl, void* rings_dev, void* hdrs_dev, size_t ring_ids_off, int cap,
-                   const PxTableGeom* g, float scale, int rank, int max_blocks,
+                   const PxTableGeom* g, float scale, int rank, int blocks,
                    cudaStream_t stream) {
   const TableGeom G = to_geom(g);
-  int blocks = max_blocks > 0 ? max_blocks : 64;
-  if (grad_dtype == 0)
-    px_sparse_push_kernel<float><<<blocks, 256, 0, stream>>>(
-        (const float*)pend_grads, uniq_id, uniq_k, uniq_head, next, (SparseCtl*)ctl,
-        (char* const*)rings_dev, (uint32_t* const*)hdrs_dev, ring_ids_off, cap, G, scale, rank);
-  else
-    px_sparse_push_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(
-        (const __nv_bfloat16*)pend_grads, uniq_id, uniq_k, uniq_head, next,
-        (SparseCtl*)ctl, (char* const*)rings_dev, (uint32_t* const*)hdrs_dev, ring_ids_off, cap, G,
-        scale, rank);
+  if (blocks < 1) blocks = 1;
+#define PUSH(T, CH)                                                                         \
+  px_sparse_push_kernel<T, CH><<<blocks, 256, 0, stream>>>(                                 \
+      (const T*)pend_grads, uniq_id, uniq_k, uniq_head, next, (SparseCtl*)ctl,              \
+      (char* const*)rings_dev, (uint32_t* const*)hdrs_dev, ring_ids_off, cap, G, scale, rank)
+  const int ch = G.D4 <= 32 ? 1 : (G.D4 <= 64 ? 2 : 4);
+  if (grad_dtype == 0) { if (ch == 1) PUSH(float, 1); else if (ch == 2) PUSH(float, 2); else PUSH(float, 4); }
+  else { if (ch == 1) PUSH(__nv_bfloat16, 1); else if (ch == 2) PUSH(__nv_bfloat16, 2); else PUSH(__nv_bfloat16, 4); }
+#undef PUSH
   return (int)cudaGetLastError();
 }
 
 int px_sparse_claim(void* ring, void* hdr, size_t ring_ids_off, int cap, int32_t* slotmap,
-                    const void* ctl, const PxTableGeom* g, int max_blocks, cudaStream_t stream) {
+                    const void* ctl, const PxTableGeom* g, int blocks, cudaStream_t stream) {
   const TableGeom G = to_geom(g);
-  int blocks = max_blocks > 0 ? max_blocks : 64;
+  if (blocks < 1) blocks = 1;
   px_sparse_claim_kernel<<<blocks, 256, 0, stream>>>((char*)ring, (uint32_t*)hdr, ring_ids_off,
                                                      cap, slotmap, (const SparseCtl*)ctl, G);
   return (int)cudaGetLastError();
@@ -595,9 +615,9 @@ int px_sparse_claim(void* ring, void* hdr, size_t ring_ids_off, int cap, int32_t
 int px_sparse_apply(void* ring, void* hdr, size_t ring_ids_off, int cap, int32_t* slotmap,
                     float* table, float* slot0, float* slot1, const float* hp, float avg, int kind,
                     void* ctl, void* hdrs_dev, const PxTableGeom* g, int rank, int use_slotmap,
-                    int max_blocks, cudaStream_t stream) {
+                    int blocks, cudaStream_t stream) {
   const TableGeom G = to_geom(g);
-  int blocks = max_blocks > 0 ? max_blocks : 64;
+  if (blocks < 1) blocks = 1;
   px_sparse_apply_kernel<<<blocks, 256, 0, stream>>>(
       (char*)ring, (uint32_t*)hdr, ring_ids_off, cap, slotmap, table, slot0, slot1, hp, avg, kind,
       (SparseCtl*)ctl, (uint32_t* const*)hdrs_dev, G, rank, use_slotmap);
@@ -607,10 +627,10 @@ int px_sparse_apply(void* ring, void* hdr, size_t ring_ids_off, int cap, int32_t
 int px_sparse_async_apply(const void* pend_grads, int grad_dtype, const int32_t* uniq_id,
                           const int32_t* uniq_head, const int32_t* next, void* ctl,
                           void* tables_dev, void* slot0s_dev, void* slot1s_dev, const float* hp,
-                          float scale, int kind, const PxTableGeom* g, int max_blocks,
+                          float scale, int kind, const PxTableGeom* g, int blocks,
                           cudaStream_t stream) {
   const TableGeom G = to_geom(g);
-  int blocks = max_blocks > 0 ? max_blocks : 64;
+  if (blocks < 1) blocks = 1;
   if (grad_dtype == 0)
     px_sparse_async_apply_kernel<float><<<blocks, 256, 0, stream>>>(
         (const float*)pend_grads, uniq_id, uniq_head, next, (SparseCtl*)ctl,

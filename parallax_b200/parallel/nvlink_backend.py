@@ -426,7 +426,7 @@ class NVSparseTable(object):
         opts = options or {}
         self.out_dtype = out_dtype or torch.float32
         self.anchor_device = self.device
-        self.max_blocks = int(opts.get("sparse_blocks", 64))
+        self.max_blocks = int(opts.get("sparse_blocks", 148 * 4))
         self.capacity_hint = (opts.get("sparse_capacity") or {}).get(name)
         L = self.layout
         rows = L.rows_local
@@ -606,28 +606,31 @@ class NVSparseTable(object):
                            self.ctl, self.geom, self.local_aggregation,
                            self.use_smem, stream=cs)
         s0d, s1d = self._sdev(0), self._sdev(1)
+        # 8 warps per CTA, one row per warp; bounded by the configured cap
+        blk_push = max(1, min(self.max_blocks, (n + 7) // 8))
+        blk_own = max(1, min(self.max_blocks, (n * self.world + 7) // 8))
         if not self.route.sync:
             nvops.sparse_async_apply(grads, self.uniq_id, self.uniq_head, self.next,
                                      self.ctl, self._tdev(), s0d, s1d, self.hp,
                                      self.scale, self.kind, self.geom,
-                                     self.max_blocks, stream=cs)
+                                     blk_push, stream=cs)
             return
         nvops.sparse_push(grads, self.uniq_id, self.uniq_k, self.uniq_head,
                           self.next, self.ctl, self.rings_dev, self.hdrs_dev,
                           self.ring_ids_off, self.cap, self.geom, self.scale,
-                          self.rank, self.max_blocks, stream=cs)
+                          self.rank, blk_push, stream=cs)
         need_claim = self.world > 1 or not self.local_aggregation
         if need_claim:
             nvops.sparse_claim(self.ring_buf.local_ptr, self.hdr_buf.local_ptr,
                                self.ring_ids_off, self.cap, self.slotmap, self.ctl,
-                               self.geom, self.max_blocks, stream=cs)
+                               self.geom, blk_own, stream=cs)
         avg = (1.0 / self.world) if self.average else 1.0
         nvops.sparse_apply(self.ring_buf.local_ptr, self.hdr_buf.local_ptr,
                            self.ring_ids_off, self.cap, self.slotmap, self.table,
                            self.slots[0] if self.nslots > 0 else None,
                            self.slots[1] if self.nslots > 1 else None, self.hp, avg,
                            self.kind, self.ctl, self.hdrs_dev, self.geom, self.rank,
-                           need_claim, self.max_blocks, stream=cs)
+                           need_claim, blk_own, stream=cs)
 
     # -------------------------------------------------------------- checkpoint
     def _gather_full(self, local):

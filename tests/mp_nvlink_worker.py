@@ -1,0 +1,109 @@
+"""Run under torchrun with >= 2 GPUs:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
+        --master-addr 127.0.0.1 --master-port 29533 tests/mp_nvlink_worker.py
+Checks the NVLink fabric (CUDA IPC symmetric heap, P2P kernels) end to end
+against the single-device oracle of tests/test_hybrid_cpu.py, and the public
+collectives against torch.distributed (NCCL)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import parallax_b200 as parallax
+from parallax_b200 import optim
+from parallax_b200.models.simple import MLPWithEmbedding
+from tests.test_hybrid_cpu import make_batch, oracle, make_opt, VOCAB
+
+
+def run_engine(run_option, opt_name, steps, average, sync=True, graph=False,
+               dense_update="sharded", dtype=None):
+    world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
+    model = MLPWithEmbedding(VOCAB, partitioner=parallax.get_partitioner(5))
+    g = parallax.Graph(model, optimizer=make_opt(opt_name))
+    sc = {"cuda_graph": graph, "dense_update": dense_update}
+    if dtype:
+        sc["compute_dtype"] = dtype
+    cfg = parallax.Config(run_option=run_option, average_sparse=average,
+                          sess_config=sc)
+    sess, nw, wid, _ = parallax.parallel_run(g, "localhost", sync=sync,
+                                             parallax_config=cfg)
+    assert sess.engine.backend == "nvlink"
+    losses = []
+    for s in range(steps):
+        ids, labels = make_batch(s, world, rank)
+        loss, _ = sess.run(["loss", "train_op"], {"ids": [ids], "labels": [labels]})
+        losses.append(loss[0])
+    sd = sess.engine.state_dict()
+    sess.close()
+    w = dict(sd["dense"]["master"])
+    w["emb.weight"] = sd["sparse"]["emb.weight"]["weight"]
+    return losses, w
+
+
+def main():
+    from parallax_b200.parallel.fabric import Comm
+    comm = Comm.from_env()
+    world, rank = comm.world, comm.rank
+    ok = True
+
+    def check(name, cond):
+        nonlocal ok
+        flags = comm.all_gather_object(bool(cond))
+        if rank == 0:
+            print("%-58s %s" % (name, "OK" if all(flags) else "FAIL %s" % flags), flush=True)
+        ok = ok and all(flags)
+
+    for run_option in ("HYBRID", "MPI", "PS"):
+        for opt_name in ("sgd", "adagrad"):
+            for graph in (False, True):
+                steps = 6 if graph else 4
+                losses, w = run_engine(run_option, opt_name, steps, True, graph=graph)
+                _, ref = oracle(world, steps, make_opt(opt_name), 1.0)
+                good = all(torch.allclose(w[n], ref[n], rtol=2e-4, atol=2e-5) for n in ref)
+                check("engine %s/%s graph=%s vs single-device oracle" %
+                      (run_option, opt_name, graph), good)
+    losses, w = run_engine("HYBRID", "adagrad", 4, False)
+    _, ref = oracle(world, 4, make_opt("adagrad"), float(world))
+    check("sparse SUM semantics (average_sparse=False)",
+          all(torch.allclose(w[n], ref[n], rtol=2e-4, atol=2e-5) for n in ref))
+    losses, w = run_engine("MPI", "momentum", 4, True, dense_update="replicated")
+    _, ref = oracle(world, 4, make_opt("momentum"), 1.0)
+    check("AR replicated update (allreduce + local optimizer)",
+          all(torch.allclose(w[n], ref[n], rtol=2e-4, atol=2e-5) for n in ref))
+    losses, _ = run_engine("PS", "sgd", 8, False, sync=False)
+    check("async PS trains (loss decreases)", losses[-1] < losses[0])
+    losses, _ = run_engine("HYBRID", "adagrad", 8, True, dtype="bf16", graph=True)
+    check("bf16 + graph trains", np.isfinite(losses).all())
+
+    # public collectives vs NCCL
+    from parallax_b200 import collectives as hvd
+    hvd.init(comm)
+    for n in (1, 1000, 65536, 1 << 20, (1 << 22) + 8):
+        for dt in (torch.float32, torch.bfloat16):
+            x = torch.randn(n, device=comm.device).to(dt)
+            ref_t = x.clone().float()
+            dist.all_reduce(ref_t)
+            got = hvd.allreduce(x, average=False)
+            tol = 1e-4 if dt == torch.float32 else 5e-2
+            check("allreduce n=%d %s" % (n, str(dt).split(".")[-1]),
+                  torch.allclose(got.float(), ref_t, rtol=tol, atol=tol))
+    x = torch.full((1000,), float(rank), device=comm.device)
+    got = hvd.broadcast(x, root_rank=world - 1)
+    check("broadcast", bool((got == world - 1).all()))
+    x = torch.full((10 + rank, 3), float(rank), device=comm.device)
+    got = hvd.allgather(x)
+    exp = torch.cat([torch.full((10 + r, 3), float(r)) for r in range(world)])
+    check("allgather (variable first dim)", torch.equal(got.cpu(), exp))
+    hvd.shutdown()
+    if rank == 0:
+        print("ALL OK" if ok else "SOME FAILED", flush=True)
+    comm.shutdown()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
