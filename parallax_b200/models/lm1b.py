@@ -71,26 +71,16 @@ class LM1B(nn.Module):
             -math.sqrt(3.0 / state_size), math.sqrt(3.0 / state_size)))
 
     def lstm(self, x, c, h):
-        """x: [B, T, E] -> outputs [B*T, P] (time-major inside), final c, h."""
+        """x: [B, T, E] -> outputs [B*T, P] (rows ordered like y.reshape(-1)),
+        final c, h.  One fused autograd node (`ops.fused.lstm_layer`)."""
+        from ..ops.fused import lstm_layer
         Bsz, T, E = x.shape
-        S = self.state_size
-        Wx, Wh = self.W[:E], self.W[E:]
-        # hoisted input GEMM for all steps: [T*B, E] @ [E, 4S] + B
-        xw = torch.addmm(self.B, x.transpose(0, 1).reshape(T * Bsz, E), Wx)
-        xw = xw.view(T, Bsz, 4 * S)
-        outs = []
-        for t in range(T):
-            gates = torch.addmm(xw[t], h, Wh)
-            i, j, f, o = gates.split(S, dim=1)
-            c = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
-            m = torch.sigmoid(o) * torch.tanh(c)
-            h = m @ self.W_P
-            out = h
-            if self.training and self.keep_prob < 1.0:
-                out = F.dropout(out, 1.0 - self.keep_prob)
-            outs.append(out)
-        # [B, T, P] order to match labels y.reshape(-1)
-        return torch.stack(outs, dim=1).reshape(Bsz * T, -1), c, h
+        H, c, h = lstm_layer(x.transpose(0, 1), self.W[:E], self.W[E:], self.B,
+                             self.W_P, c, h, forget_bias=1.0)
+        out = H.transpose(0, 1)                      # [B, T, P]
+        if self.training and self.keep_prob < 1.0:
+            out = F.dropout(out, 1.0 - self.keep_prob)
+        return out.reshape(Bsz * T, -1), c, h
 
     def forward(self, x, y, w=None, initial_state_c=None, initial_state_h=None):
         Bsz, T = x.shape
@@ -105,8 +95,7 @@ class LM1B(nn.Module):
             torch.zeros(Bsz, self.state_size, device=dev, dtype=dt)
         h = initial_state_h if initial_state_h is not None else \
             torch.zeros(Bsz, self.projected_size, device=dev, dtype=dt)
-        c, h = c.to(dt), h.to(dt)
-        inputs, c, h = self.lstm(e, c, h)
+        inputs, c, h = self.lstm(e, c.float(), h.to(dt))
         targets = y.reshape(-1)
         if self.training and self.num_sampled > 0:
             loss = self.sampled_softmax_loss(inputs, targets)
@@ -118,21 +107,15 @@ class LM1B(nn.Module):
                 "final_state_h": h.detach()}
 
     def sampled_softmax_loss(self, inputs, targets):
+        from ..ops.fused import sampled_softmax_loss
         N, S, V = targets.numel(), self.num_sampled, self.vocab_size
         sampled = log_uniform_sample(S, V, inputs.device)
         ids = torch.cat([targets.to(torch.int64), sampled])
-        w_all = self.softmax_w(ids)                 # [N+S, P]
+        w_all = self.softmax_w(ids)                 # [N+S, P]  one lookup per table
         b_all = self.softmax_b(ids).squeeze(-1)     # [N+S]
-        if w_all.dtype != inputs.dtype:
-            w_all = w_all.to(inputs.dtype)
-        true_w, samp_w = w_all[:N], w_all[N:]
         logq = log_uniform_logq(ids, S, V)
-        true_logits = (inputs * true_w).sum(-1).float() + b_all[:N].float() - logq[:N]
-        samp_logits = (inputs @ samp_w.t()).float() + (b_all[N:].float() - logq[N:])
-        hits = targets.unsqueeze(1) == sampled.unsqueeze(0)
-        samp_logits = samp_logits.masked_fill(hits, -1e30)
-        lse = torch.logsumexp(torch.cat([true_logits.unsqueeze(1), samp_logits], 1), 1)
-        return lse - true_logits
+        return sampled_softmax_loss(inputs, w_all[:N], w_all[N:], b_all[:N], b_all[N:],
+                                    logq[:N], logq[N:], targets, sampled)
 
     def full_softmax_loss(self, inputs, targets):
         ids = torch.arange(self.vocab_size, device=inputs.device)

@@ -1,0 +1,193 @@
+"""Fused model-side ops (autograd Functions) for the LM1B hot path.
+
+`lstm_layer`  — a whole unrolled LSTMP layer as ONE autograd node: the
+  sequential part per time step is 2 small GEMMs + 1 fused cell kernel
+  (forward) and 2 GEMMs + 1 fused kernel (backward); every weight gradient is
+  a single GEMM batched over all time steps (the reference's TF graph issues
+  one small GEMM + ~25 elementwise kernels per step and direction:
+  `examples/lm1b/language_model.py:76-87`).
+`sampled_softmax_loss` — logits GEMM + one fused kernel that produces the
+  loss and the softmax probabilities in place (= gradient wrt logits), so the
+  backward is two GEMMs and a few row scalings.
+
+Both have a pure-PyTorch implementation (`*_reference`) which is the numerics
+oracle in the tests and the path used on the host fabric.
+"""
+import ctypes
+
+import torch
+
+from . import lib as _lib, check as _check, register_signatures
+
+_vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+register_signatures({
+    "px_lstm_cell_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
+    "px_lstm_cell_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "px_sampled_softmax": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+})
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _p(t):
+    return _vp(t.data_ptr())
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _count(n=1):
+    from ..parallel import nvops
+    nvops.launches["n"] += n
+
+
+# ===========================================================================
+# LSTM layer
+# ===========================================================================
+def lstm_layer_reference(x, Wx, Wh, bias, W_P, c0, h0, forget_bias=1.0):
+    """x: [T, B, E] → (H [T, B, P], c_T, h_T); plain autograd-able torch."""
+    T, Bsz, E = x.shape
+    S = W_P.shape[0]
+    xw = torch.addmm(bias, x.reshape(T * Bsz, E), Wx).view(T, Bsz, 4 * S)
+    c, h, outs = c0.float(), h0, []
+    for t in range(T):
+        gates = torch.addmm(xw[t], h, Wh).float()
+        i, j, f, o = gates.split(S, dim=1)
+        c = torch.sigmoid(f + forget_bias) * c + torch.sigmoid(i) * torch.tanh(j)
+        m = (torch.sigmoid(o) * torch.tanh(c)).to(x.dtype)
+        h = m @ W_P
+        outs.append(h)
+    return torch.stack(outs), c, h
+
+
+class _LSTMLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Wx, Wh, bias, W_P, c0, h0, forget_bias):
+        L = _lib()
+        T, Bsz, E = x.shape
+        S, P = W_P.shape
+        dt = x.dtype
+        dev = x.device
+        x = x.contiguous()
+        xw = torch.addmm(bias, x.view(T * Bsz, E), Wx).view(T, Bsz, 4 * S)
+        act = torch.empty(T, Bsz, 4 * S, dtype=dt, device=dev)
+        c_all = torch.empty(T + 1, Bsz, S, dtype=torch.float32, device=dev)
+        m_all = torch.empty(T, Bsz, S, dtype=dt, device=dev)
+        h_all = torch.empty(T + 1, Bsz, P, dtype=dt, device=dev)
+        c_all[0].copy_(c0)
+        h_all[0].copy_(h0)
+        gpre = torch.empty(Bsz, 4 * S, dtype=dt, device=dev)
+        st = _stream()
+        for t in range(T):
+            torch.addmm(xw[t], h_all[t], Wh, out=gpre)
+            _check(L.px_lstm_cell_fwd(_p(gpre), _p(c_all[t]), _p(act[t]), _p(c_all[t + 1]),
+                                      _p(m_all[t]), Bsz, S, float(forget_bias), _DT[dt], st),
+                   "lstm_cell_fwd")
+            torch.mm(m_all[t], W_P, out=h_all[t + 1])
+        _count(T)
+        ctx.save_for_backward(x, Wx, Wh, W_P, act, c_all, m_all, h_all)
+        ctx.dims = (T, Bsz, E, S, P)
+        return h_all[1:], c_all[T].clone(), h_all[T].clone()
+
+    @staticmethod
+    def backward(ctx, dH, dcT, dhT):
+        L = _lib()
+        x, Wx, Wh, W_P, act, c_all, m_all, h_all = ctx.saved_tensors
+        T, Bsz, E, S, P = ctx.dims
+        dt, dev = x.dtype, x.device
+        dH = dH.contiguous()
+        dgates = torch.empty(T, Bsz, 4 * S, dtype=dt, device=dev)
+        dh_tot = torch.empty(T, Bsz, P, dtype=dt, device=dev)
+        dc = torch.zeros(Bsz, S, dtype=torch.float32, device=dev) if dcT is None \
+            else dcT.float().clone()
+        dh_rec = None if dhT is None else dhT.to(dt)
+        dm = torch.empty(Bsz, S, dtype=dt, device=dev)
+        WhT, WPT = Wh.t(), W_P.t()
+        st = _stream()
+        for t in range(T - 1, -1, -1):
+            if dh_rec is None:
+                dh_tot[t].copy_(dH[t])
+            else:
+                torch.add(dH[t], dh_rec, out=dh_tot[t])
+            torch.mm(dh_tot[t], WPT, out=dm)
+            _check(L.px_lstm_cell_bwd(_p(dm), _p(dc), _p(act[t]), _p(c_all[t]),
+                                      _p(c_all[t + 1]), _p(dgates[t]), Bsz, S, _DT[dt], st),
+                   "lstm_cell_bwd")
+            dh_rec = torch.mm(dgates[t], WhT)
+        _count(T)
+        dg2 = dgates.view(T * Bsz, 4 * S)
+        dWh = h_all[:T].reshape(T * Bsz, P).t() @ dg2
+        dWx = x.view(T * Bsz, E).t() @ dg2
+        dbias = dg2.sum(0)
+        dW_P = m_all.view(T * Bsz, S).t() @ dh_tot.view(T * Bsz, P)
+        dx = (dg2 @ Wx.t()).view(T, Bsz, E)
+        return dx, dWx, dWh, dbias, dW_P, dc, dh_rec, None
+
+
+def lstm_layer(x, Wx, Wh, bias, W_P, c0, h0, forget_bias=1.0):
+    if x.is_cuda and x.dtype in _DT:
+        return _LSTMLayerFn.apply(x, Wx, Wh, bias, W_P, c0, h0, forget_bias)
+    return lstm_layer_reference(x, Wx, Wh, bias, W_P, c0, h0, forget_bias)
+
+
+# ===========================================================================
+# sampled softmax
+# ===========================================================================
+def sampled_softmax_reference(inputs, true_w, samp_w, true_b, samp_b, logq_true,
+                              logq_samp, targets, sampled):
+    """Per-example loss [N] (tf.nn.sampled_softmax_loss semantics)."""
+    true_logits = (inputs * true_w).sum(-1).float() + true_b.float() - logq_true
+    samp_logits = (inputs @ samp_w.t()).float() + (samp_b.float() - logq_samp)
+    hits = targets.unsqueeze(1) == sampled.unsqueeze(0)
+    samp_logits = samp_logits.masked_fill(hits, float("-inf"))
+    lse = torch.logsumexp(torch.cat([true_logits.unsqueeze(1), samp_logits], 1), 1)
+    return lse - true_logits
+
+
+class _SampledSoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs, true_w, samp_w, true_b, samp_b, logq_true, logq_samp,
+                targets, sampled):
+        L = _lib()
+        N, S = inputs.shape[0], samp_w.shape[0]
+        dt = inputs.dtype
+        logits = inputs @ samp_w.t()                               # [N, S]  (cuBLAS)
+        true_dot = (inputs.float() * true_w.float()).sum(-1)
+        adj_t = (true_b.float() - logq_true).contiguous()
+        adj_s = (samp_b.float() - logq_samp).contiguous()
+        loss = torch.empty(N, dtype=torch.float32, device=inputs.device)
+        dtrue = torch.empty(N, dtype=torch.float32, device=inputs.device)
+        tg = targets.to(torch.int64).contiguous()
+        sm = sampled.to(torch.int64).contiguous()
+        _check(L.px_sampled_softmax(_p(logits), _p(true_dot), _p(adj_t), _p(adj_s), _p(tg),
+                                    _p(sm), _p(loss), _p(dtrue), N, S, _DT[dt], _stream()),
+               "sampled_softmax")
+        _count(1)
+        ctx.save_for_backward(inputs, true_w, samp_w, logits, dtrue)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        inputs, true_w, samp_w, probs, dtrue = ctx.saved_tensors
+        dt = inputs.dtype
+        g = g.float()
+        gt = (g * dtrue).unsqueeze(1)                              # [N,1]
+        d_inputs = ((probs @ samp_w).float() * g.unsqueeze(1) +
+                    gt * true_w.float()).to(dt)
+        gi = (inputs.float() * g.unsqueeze(1)).to(dt)              # diag(g)·H
+        d_samp_w = probs.t() @ gi
+        d_true_w = (gt * inputs.float()).to(dt)
+        d_samp_b = (probs.float().t() @ g) if probs.dtype == torch.float32 else \
+            (probs.t() @ g.to(dt).unsqueeze(1)).squeeze(1).float()
+        d_true_b = gt.squeeze(1)
+        return d_inputs, d_true_w, d_samp_w, d_true_b, d_samp_b, None, None, None, None
+
+
+def sampled_softmax_loss(inputs, true_w, samp_w, true_b, samp_b, logq_true, logq_samp,
+                         targets, sampled):
+    if inputs.is_cuda and inputs.dtype in _DT and samp_w.shape[0] <= 256 * 64:
+        return _SampledSoftmaxFn.apply(inputs, true_w.to(inputs.dtype),
+                                       samp_w.to(inputs.dtype), true_b, samp_b,
+                                       logq_true, logq_samp, targets, sampled)
+    return sampled_softmax_reference(inputs, true_w, samp_w, true_b, samp_b, logq_true,
+                                     logq_samp, targets, sampled)
