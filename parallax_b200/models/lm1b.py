@@ -17,9 +17,11 @@ Parity: `parallax/parallax/examples/lm1b/language_model.py:18-110` (model) and
 * Adagrad(lr 0.2, initial accumulator 1.0); embedding grads × batch_size; LSTM
   grads clipped to global norm 10; EMA(0.999) over the LSTM variables.
 
-Differences: negatives are drawn with replacement on the device (no host
-round-trip for TF's rejection loop), expected counts adjusted accordingly;
-the input half of the LSTM matmul for all time steps is hoisted into one GEMM.
+Differences: TF's unique log-uniform sampler loops on the host until 8192
+distinct ids were drawn; here the same distribution/semantics (first 8192
+distinct values of the draw sequence, expected counts from `num_tries`) is
+computed on the device with static shapes; the LSTM layer and the sampled
+softmax run as fused autograd nodes (`ops/fused.py`).
 """
 import math
 
@@ -46,6 +48,35 @@ def log_uniform_logq(ids, num_sampled, range_max):
     idf = ids.to(torch.float32)
     p = (torch.log(idf + 2.0) - torch.log(idf + 1.0)) / math.log(range_max + 1.0)
     return torch.log(p * num_sampled)
+
+
+def log_uniform_sample_unique(num_sampled, range_max, device, oversample=3):
+    """TF's `log_uniform_candidate_sampler(unique=True)`: keep drawing until
+    `num_sampled` distinct ids were seen; returns (ids [num_sampled] in draw
+    order, num_tries) — with static shapes and no host round-trip (TF loops on
+    the host): draw `oversample·num_sampled` candidates at once, keep the first
+    occurrence of each value, take the first `num_sampled` of those."""
+    M = int(oversample * num_sampled)
+    d = log_uniform_sample(M, range_max, device)
+    vals, order = torch.sort(d, stable=True)
+    first_sorted = torch.ones(M, dtype=torch.bool, device=device)
+    first_sorted[1:] = vals[1:] != vals[:-1]
+    first = torch.zeros(M, dtype=torch.bool, device=device)
+    first[order] = first_sorted
+    cum = torch.cumsum(first.to(torch.int32), 0)
+    sel = first & (cum <= num_sampled)
+    slot = torch.where(sel, cum - 1, torch.full_like(cum, num_sampled)).to(torch.int64)
+    out = torch.zeros(num_sampled + 1, dtype=torch.int64, device=device)
+    out.scatter_(0, slot, d)
+    num_tries = ((cum < num_sampled).sum() + 1).clamp(max=M).to(torch.float32)
+    return out[:num_sampled], num_tries
+
+
+def log_uniform_logq_unique(ids, num_tries, range_max):
+    """log expected count under unique sampling: Q = -expm1(tries·log1p(-p))."""
+    idf = ids.to(torch.float32)
+    p = (torch.log(idf + 2.0) - torch.log(idf + 1.0)) / math.log(range_max + 1.0)
+    return torch.log(-torch.expm1(num_tries * torch.log1p(-p)))
 
 
 class LM1B(nn.Module):
@@ -109,11 +140,11 @@ class LM1B(nn.Module):
     def sampled_softmax_loss(self, inputs, targets):
         from ..ops.fused import sampled_softmax_loss
         N, S, V = targets.numel(), self.num_sampled, self.vocab_size
-        sampled = log_uniform_sample(S, V, inputs.device)
+        sampled, tries = log_uniform_sample_unique(S, V, inputs.device)
         ids = torch.cat([targets.to(torch.int64), sampled])
         w_all = self.softmax_w(ids)                 # [N+S, P]  one lookup per table
         b_all = self.softmax_b(ids).squeeze(-1)     # [N+S]
-        logq = log_uniform_logq(ids, S, V)
+        logq = log_uniform_logq_unique(ids, tries, V)
         return sampled_softmax_loss(inputs, w_all[:N], w_all[N:], b_all[:N], b_all[N:],
                                     logq[:N], logq[N:], targets, sampled)
 

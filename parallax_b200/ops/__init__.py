@@ -65,10 +65,10 @@ _SIGS = {
     "px_sparse_dedup": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 ctypes.POINTER(PxTableGeom), c_int, c_int, c_void_p]),
-    "px_sparse_push": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                               c_int, ctypes.POINTER(PxTableGeom), c_float, c_int,
-                               c_int, c_void_p]),
+    "px_sparse_push": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_size_t, c_int, ctypes.POINTER(PxTableGeom), c_float,
+                               c_int, c_int, c_void_p]),
     "px_sparse_claim": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p,
                                 c_void_p, ctypes.POINTER(PxTableGeom), c_int,
                                 c_void_p]),
@@ -77,9 +77,9 @@ _SIGS = {
                                 c_int, c_void_p, c_void_p,
                                 ctypes.POINTER(PxTableGeom), c_int, c_int, c_int,
                                 c_void_p]),
-    "px_sparse_async_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                      c_void_p, c_void_p, c_void_p, c_void_p,
-                                      c_void_p, c_float, c_int,
+    "px_sparse_async_apply": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_float, c_int,
                                       ctypes.POINTER(PxTableGeom), c_int, c_void_p]),
 }
 

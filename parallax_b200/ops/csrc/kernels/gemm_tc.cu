@@ -1,0 +1,339 @@
+// tcgen05 / TMEM / TMA GEMM for the skinny recurrent products of the LSTM
+// (M = batch = 128·k rows, huge K or huge N) — hand-written for sm_100a.
+//
+//   C[M,N] (bf16) = A[M,K] (bf16, K-contiguous) · B[N,K]^T (bf16, K-contiguous)
+//                   (+ addend[M,N] bf16)                        "TN" GEMM
+//
+// Roles (one CTA = 8 warps): warp 0 TMA producer (cp.async.bulk.tensor, 128B
+// swizzle), warp 1 single-thread tcgen05.mma issuer (UMMA 128×BN×16, fp32
+// accumulator in TMEM), warp 2 TMEM allocator, warps 4-7 epilogue
+// (tcgen05.ld 32x32b → registers → global).  STAGES-deep smem ring with
+// full/empty mbarriers; MMA completion is signalled with tcgen05.commit.
+//
+// Split-K: grid.z CTAs each reduce a K-slice and red.add their fp32 tile into
+// an L2-resident workspace; the last CTA to arrive for a tile (atomic ticket)
+// converts (+addend) to bf16, stores C and re-zeroes the workspace — so a
+// [128, 8192]·[8192, 512] product runs on 4·32 CTAs instead of 4, without a
+// second launch.  The reference reaches these products through cuBLAS
+// (tensorflow/core/kernels/matmul_op.cc:252-369 → cuda_blas.cc:2229); cuBLAS'
+// heuristic picks a 64x8-tile kernel for this shape that takes ~11 µs.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace tc {
+
+constexpr int BM = 128;       // UMMA M
+constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// K-major operand tile, 128B swizzle: rows at 128 B pitch, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address
+  d |= (uint64_t)0 << 16;                             // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // SBO
+  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::
+               "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct GemmArgs {
+  __nv_bfloat16* C;            // [M, N]
+  const __nv_bfloat16* addend; // [M, N] or null
+  float* ws;                   // [M, N] fp32, zero between calls (split-K only)
+  unsigned int* tickets;       // [(M/128) * (N/BN)] zero between calls (split-K only)
+  int M, N, K;                 // K = full reduction length
+  int k_per_split;             // multiple of BK
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+px_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                  const __grid_constant__ CUtensorMap tmap_b, GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [STAGES][A 16 KB][B BN*128 B] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  __shared__ unsigned int s_last;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
+  const int k0 = split * g.k_per_split;
+  const int num_kb = g.k_per_split / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::
+                 "r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* sa = smem + s * STAGE_BYTES;
+      uint8_t* sb = sa + A_BYTES;
+      mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+      tma_load_2d(sa, &tmap_a, &full_bar[s], k0 + kb * BK, m_tile * BM);
+      tma_load_2d(sb, &tmap_b, &full_bar[s], k0 + kb * BK, n_tile * BN);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------- MMA issuer -------------------------------
+    // instr desc: D=f32 (1<<4), A=bf16 (1<<7), B=bf16 (1<<10), K-major both,
+    // N>>3 at bit 17, M>>4 at bit 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tcgen05_fence_after();
+      const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+      const uint32_t sb = sa + A_BYTES;
+      const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
+#pragma unroll
+      for (int k = 0; k < BK / UMMA_K; ++k) {
+        // advance 32 B (= UMMA_K bf16) inside the swizzle atom: +2 in the
+        // 16-byte-granular start-address field
+        umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                  (kb | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(&empty_bar[s]);          // frees the smem slot when the MMAs retire
+    }
+    umma_commit(tmem_full);                // accumulator complete
+  } else if (warp >= 4) {
+    // -------------------------------- epilogue --------------------------------
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    const int wq = warp - 4;                         // TMEM lane quarter
+    const int row = m_tile * BM + wq * 32 + lane;    // output row of this thread
+    const bool splitk = gridDim.z > 1;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, r);
+      const size_t off = (size_t)row * g.N + (size_t)n_tile * BN + c0;
+      if (row < g.M) {
+        if (splitk) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            atomicAdd(reinterpret_cast<float4*>(g.ws + off + i),
+                      make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                  __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+        } else {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
+          if (g.addend) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              float a[8];
+              Vec16<__nv_bfloat16>::unpack(ld_v4(g.addend + off + i), a);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[i + j] += a[j];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) st_v4(g.C + off + i, Vec16<__nv_bfloat16>::pack(f + i));
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)BN) : "memory");
+  }
+  if (gridDim.z > 1) {
+    // last-arriving split for this tile finalises: ws (+addend) -> bf16 C, ws := 0
+    __threadfence();
+    __syncthreads();
+    const unsigned int tile_id = m_tile * gridDim.x + n_tile;
+    if (threadIdx.x == 0) s_last = (atomicAdd(&g.tickets[tile_id], 1u) == gridDim.z - 1) ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (int idx = threadIdx.x; idx < BM * BN / 8; idx += blockDim.x) {
+        const int rr = idx / (BN / 8), cc = (idx % (BN / 8)) * 8;
+        const int row = m_tile * BM + rr;
+        if (row >= g.M) continue;
+        const size_t off = (size_t)row * g.N + (size_t)n_tile * BN + cc;
+        float f[8];
+        const uint4 lo = __ldcg(reinterpret_cast<const uint4*>(g.ws + off));
+        const uint4 hi = __ldcg(reinterpret_cast<const uint4*>(g.ws + off + 4));
+        f[0] = __uint_as_float(lo.x); f[1] = __uint_as_float(lo.y); f[2] = __uint_as_float(lo.z);
+        f[3] = __uint_as_float(lo.w); f[4] = __uint_as_float(hi.x); f[5] = __uint_as_float(hi.y);
+        f[6] = __uint_as_float(hi.z); f[7] = __uint_as_float(hi.w);
+        if (g.addend) {
+          float a[8];
+          Vec16<__nv_bfloat16>::unpack(ld_v4(g.addend + off), a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += a[j];
+        }
+        st_v4(g.C + off, Vec16<__nv_bfloat16>::pack(f));
+        __stcg(reinterpret_cast<uint4*>(g.ws + off), make_uint4(0, 0, 0, 0));
+        __stcg(reinterpret_cast<uint4*>(g.ws + off + 4), make_uint4(0, 0, 0, 0));
+      }
+      if (threadIdx.x == 0) g.tickets[tile_id] = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128B swizzle
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols,
+                     uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -10;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -11;
+}
+
+}  // namespace tc
+
+extern "C" {
+
+// C[M,N] = A[M,K] · B[N,K]^T (+ addend).  splits > 1 needs ws (fp32 [M,N], zero)
+// and tickets (uint32 [tiles], zero).  Returns 0 or a negative error.
+int px_gemm_tc(const void* A, const void* B, void* C, const void* addend, float* ws,
+               unsigned int* tickets, int M, int N, int K, int splits, int bn,
+               cudaStream_t stream) {
+  using namespace tc;
+  if (M % BM || K % BK || (bn != 64 && bn != 128) || N % bn) return -1;
+  if (splits < 1 || K % (splits * BK)) return -2;
+  if (splits > 1 && (!ws || !tickets)) return -3;
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A, M, K, BM);
+  if (rc) return rc;
+  rc = make_tmap(&tb, B, N, K, bn);
+  if (rc) return rc;
+  GemmArgs g;
+  g.C = (__nv_bfloat16*)C; g.addend = (const __nv_bfloat16*)addend; g.ws = ws;
+  g.tickets = tickets; g.M = M; g.N = N; g.K = K; g.k_per_split = K / splits;
+  dim3 grid(N / bn, M / BM, splits);
+  constexpr int STAGES = 4;
+  if (bn == 128) {
+    constexpr int SMEM = STAGES * (BM * BK * 2 + 128 * BK * 2) + 1024 + 256;
+    static bool set128 = false;
+    if (!set128) {
+      cudaFuncSetAttribute(px_gemm_tc_kernel<128, STAGES>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+      set128 = true;
+    }
+    px_gemm_tc_kernel<128, STAGES><<<grid, 256, SMEM, stream>>>(ta, tb, g);
+  } else {
+    constexpr int SMEM = STAGES * (BM * BK * 2 + 64 * BK * 2) + 1024 + 256;
+    static bool set64 = false;
+    if (!set64) {
+      cudaFuncSetAttribute(px_gemm_tc_kernel<64, STAGES>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+      set64 = true;
+    }
+    px_gemm_tc_kernel<64, STAGES><<<grid, 256, SMEM, stream>>>(ta, tb, g);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -104,8 +104,10 @@ px_sparse_lookup_kernel(const IdT* __restrict__ ids, int n, float* const* __rest
 
 // ------------------------------------------------------------------- dedup
 // Outputs (compact, per unique id u): uniq_id[u], uniq_k[u] (index inside its
-// owner bucket), uniq_head[u] (head of the linked list of positions carrying
-// that id; next[i] links on).  ctl->n_uniq, ctl->owner_cnt[o].
+// owner bucket), uniq_cnt[u] (how many positions carry that id) and, per
+// position i, pos2u[i] (its unique slot, -1 for padding).  ctl->n_uniq,
+// ctl->owner_cnt[o].  (Arrays are named uniq_head/next at the ABI for
+// historical reasons: uniq_head == uniq_cnt, next == pos2u.)
 
 // Single-CTA variant: the hash table lives in shared memory ("local
 // aggregation dedups indices in SMEM before shipping").  n <= smem capacity.
@@ -121,7 +123,7 @@ px_sparse_dedup_smem_kernel(const int32_t* __restrict__ pend_ids, int n, int hbi
   __shared__ int s_nuniq;
   __shared__ int s_owner_cnt[PX_MAX_RANKS];
   for (int h = threadIdx.x; h < H; h += blockDim.x) keys[h] = -1;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) uniq_head[i] = -1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) uniq_head[i] = 0;
   if (threadIdx.x < PX_MAX_RANKS) s_owner_cnt[threadIdx.x] = 0;
   if (threadIdx.x == 0) s_nuniq = 0;
   __syncthreads();
@@ -133,7 +135,7 @@ px_sparse_dedup_smem_kernel(const int32_t* __restrict__ pend_ids, int n, int hbi
       int owner, local; geom_map(g, id, owner, local);
       const int u = atomicAdd(&s_nuniq, 1);
       uniq_id[u] = id; uniq_k[u] = atomicAdd(&s_owner_cnt[owner], 1);
-      uniq_head[u] = i; next[i] = -1;
+      uniq_head[u] = 1; next[i] = u;
       continue;
     }
     uint32_t h = hash_id(id) & (H - 1);
@@ -150,15 +152,17 @@ px_sparse_dedup_smem_kernel(const int32_t* __restrict__ pend_ids, int n, int hbi
     }
   }
   __syncthreads();
-  // pass 2: link positions to their unique entry
-  if (dedup)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int id = pend_ids[i];
-      if (id < 0) continue;
-      uint32_t h = hash_id(id) & (H - 1);
-      while (keys[h] != id) h = (h + 1) & (H - 1);
-      next[i] = atomicExch(&uniq_head[slot_u[h]], i);
-    }
+  // pass 2: map positions to their unique entry and count them
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int id = pend_ids[i];
+    if (id < 0) { next[i] = -1; continue; }
+    if (!dedup) continue;
+    uint32_t h = hash_id(id) & (H - 1);
+    while (keys[h] != id) h = (h + 1) & (H - 1);
+    const int u = slot_u[h];
+    next[i] = u;
+    atomicAdd(&uniq_head[u], 1);
+  }
   __syncthreads();
   if (threadIdx.x == 0) ctl->n_uniq = s_nuniq;
   if (threadIdx.x < PX_MAX_RANKS) ctl->owner_cnt[threadIdx.x] = s_owner_cnt[threadIdx.x];
@@ -174,12 +178,12 @@ px_sparse_dedup_insert_kernel(const int32_t* __restrict__ pend_ids, int n, int h
   const int H = 1 << hbits;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int id = pend_ids[i];
-    if (id < 0) continue;
+    if (id < 0) { next[i] = -1; continue; }
     if (!dedup) {
       int owner, local; geom_map(g, id, owner, local);
       const int u = atomicAdd(&ctl->n_uniq, 1);
       uniq_id[u] = id; uniq_k[u] = atomicAdd(&ctl->owner_cnt[owner], 1);
-      uniq_head[u] = i; next[i] = -1;
+      uniq_head[u] = 1; next[i] = u;
       continue;
     }
     uint32_t h = hash_id(id) & (H - 1);
@@ -189,7 +193,7 @@ px_sparse_dedup_insert_kernel(const int32_t* __restrict__ pend_ids, int n, int h
         int owner, local; geom_map(g, id, owner, local);
         const int u = atomicAdd(&ctl->n_uniq, 1);
         slot_u[h] = u; uniq_id[u] = id; uniq_k[u] = atomicAdd(&ctl->owner_cnt[owner], 1);
-        uniq_head[u] = -1;
+        uniq_head[u] = 0;
         break;
       }
       if (old == id) break;
@@ -208,7 +212,9 @@ px_sparse_dedup_link_kernel(const int32_t* __restrict__ pend_ids, int n, int hbi
     uint32_t h = hash_id(id) & (H - 1);
     while (ld_volatile_u32(reinterpret_cast<const uint32_t*>(keys) + h) != (uint32_t)id)
       h = (h + 1) & (H - 1);
-    next[i] = atomicExch(&uniq_head[slot_u[h]], i);
+    const int u = slot_u[h];
+    next[i] = u;
+    atomicAdd(&uniq_head[u], 1);
   }
 }
 
@@ -230,127 +236,6 @@ __device__ __forceinline__ float4 ld_grad4(const GradT* base, size_t f4_index) {
                                                     f4_index * 8);
     return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u),
                        __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
-  }
-}
-
-template <typename GradT, int CH>
-__global__ void __launch_bounds__(256)
-px_sparse_push_kernel(const GradT* __restrict__ pend_grads, const int32_t* __restrict__ uniq_id,
-                      const int32_t* __restrict__ uniq_k, const int32_t* __restrict__ uniq_head,
-                      const int32_t* __restrict__ next, SparseCtl* ctl,
-                      char* const* __restrict__ rings, uint32_t* const* __restrict__ hdrs,
-                      size_t ring_ids_off, int cap, TableGeom g, float scale, int rank) {
-  // do not overwrite a ring the owner may still be draining
-  if (threadIdx.x < g.W) {
-    const uint32_t need = ctl->step;
-    const uint32_t* applied = hdrs[rank] + PX_MAX_RANKS;
-    while ((int32_t)(ld_acquire_sys(applied + threadIdx.x) - need) < 0) { }
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warps = blockDim.x >> 5;
-  const int n_uniq = ctl->n_uniq;
-  for (int u = blockIdx.x * warps + (threadIdx.x >> 5); u < n_uniq; u += gridDim.x * warps) {
-    const int id = uniq_id[u], k = uniq_k[u];
-    const int head = uniq_head[u];
-    int owner, local;
-    geom_map(g, id, owner, local);
-    for (int c0 = 0; c0 < g.D4; c0 += 32 * CH) {
-      float4 acc[CH];
-#pragma unroll
-      for (int ch = 0; ch < CH; ++ch) acc[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int i = head; i >= 0; i = next[i]) {
-#pragma unroll
-        for (int ch = 0; ch < CH; ++ch) {
-          const int c = c0 + ch * 32 + lane;
-          if (c < g.D4) {
-            const float4 v = ld_grad4<GradT>(pend_grads, (size_t)i * g.D4 + c);
-            acc[ch].x += v.x; acc[ch].y += v.y; acc[ch].z += v.z; acc[ch].w += v.w;
-          }
-        }
-      }
-#pragma unroll
-      for (int ch = 0; ch < CH; ++ch) {
-        const int c = c0 + ch * 32 + lane;
-        if (c < g.D4) {
-          const uint4 o = make_uint4(__float_as_uint(acc[ch].x * scale), __float_as_uint(acc[ch].y * scale),
-                                     __float_as_uint(acc[ch].z * scale), __float_as_uint(acc[ch].w * scale));
-          if (g.replicated) {
-            for (int p = 0; p < g.W; ++p) {
-              const int q = (rank + p) % g.W;
-              st_v4_stream(reinterpret_cast<float4*>(rings[q]) + ((size_t)rank * cap + k) * g.D4 + c, o);
-            }
-          } else {
-            st_v4_stream(reinterpret_cast<float4*>(rings[owner]) + ((size_t)rank * cap + k) * g.D4 + c, o);
-          }
-        }
-      }
-    }
-    if (lane == 0) {
-      if (g.replicated) {
-        for (int p = 0; p < g.W; ++p)
-          reinterpret_cast<int32_t*>(rings[p] + ring_ids_off)[(size_t)rank * cap + k] = local;
-      } else {
-        reinterpret_cast<int32_t*>(rings[owner] + ring_ids_off)[(size_t)rank * cap + k] = local;
-      }
-    }
-  }
-  // ---- completion: last CTA publishes counts + flag, resets local counters
-  __threadfence_system();
-  __syncthreads();
-  __shared__ bool s_last;
-  if (threadIdx.x == 0) s_last = (atomicAdd(&ctl->push_done, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence_system();
-  const uint32_t step = ctl->step + 1;
-  if (threadIdx.x < g.W) {
-    const int o = threadIdx.x;
-    const int cnt = g.replicated ? ctl->owner_cnt[0] : ctl->owner_cnt[o];
-    uint32_t* hdr = hdrs[o];
-    reinterpret_cast<volatile int32_t*>(hdr + 2 * PX_MAX_RANKS)[rank] = cnt;   // cnt[src]
-    __threadfence_system();
-    st_release_sys(hdr + rank, step);                                          // pushed[src]
-  }
-  __syncthreads();
-  if (threadIdx.x < PX_MAX_RANKS) ctl->owner_cnt[threadIdx.x] = 0;
-  if (threadIdx.x == 0) { ctl->n_uniq = 0; ctl->push_done = 0; }
-}
-
-// ------------------------------------------------------------------ owner
-__device__ __forceinline__ void wait_pushed(const uint32_t* hdr, const SparseCtl* ctl, int W) {
-  if (threadIdx.x < W) {
-    const uint32_t need = ctl->step + 1;
-    while ((int32_t)(ld_acquire_sys(hdr + threadIdx.x) - need) < 0) { }
-  }
-  __syncthreads();
-}
-
-// claim: merge duplicate rows arriving from different sources.  The first
-// entry to claim a row becomes its accumulator; later ones add into it.
-__global__ void __launch_bounds__(256)
-px_sparse_claim_kernel(char* ring, uint32_t* hdr, size_t ring_ids_off, int cap, int32_t* slotmap,
-                       const SparseCtl* ctl, TableGeom g) {
-  wait_pushed(hdr, ctl, g.W);
-  const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
-  const int32_t* cnt = reinterpret_cast<const int32_t*>(hdr + 2 * PX_MAX_RANKS);
-  const int32_t* ids = reinterpret_cast<const int32_t*>(ring + ring_ids_off);
-  float4* rows = reinterpret_cast<float4*>(ring);
-  for (int s = 0; s < g.W; ++s) {
-    const int c = ld_volatile_u32(reinterpret_cast<const uint32_t*>(cnt) + s);
-    for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < c; j += gridDim.x * warps) {
-      const int e = s * cap + j;
-      const int r = ids[e];
-      int old = 0;
-      if (lane == 0) old = atomicCAS(&slotmap[r], -1, e);
-      old = __shfl_sync(0xffffffffu, old, 0);
-      if (old != -1) {
-        for (int cidx = lane; cidx < g.D4; cidx += 32) {
-          const float4 v = rows[(size_t)e * g.D4 + cidx];
-          atomicAdd(&rows[(size_t)old * g.D4 + cidx], v);
-        }
-      }
-    }
   }
 }
 
@@ -389,6 +274,186 @@ __device__ __forceinline__ void sparse_update4(int kind, float lr, float a, floa
   w = make_float4(ww[0], ww[1], ww[2], ww[3]);
   s0 = make_float4(a0[0], a0[1], a0[2], a0[3]);
   s1 = make_float4(a1[0], a1[1], a1[2], a1[3]);
+}
+
+// Kernel A — position-parallel (LPR lanes per position): a position whose id
+// is unique in this batch goes straight to its destination (owner's ring, or a
+// remote optimizer application in async mode); positions sharing an id are
+// summed with vector atomics into a local fp32 staging row.  Duplicate-heavy
+// (Zipfian) batches therefore cost O(1) depth instead of a serial list walk.
+struct PushDst {
+  char* const* rings; size_t ring_ids_off; int cap; int rank;           // sync: rings
+  float* const* tables; float* const* slot0s; float* const* slot1s;      // async: remote apply
+  const float* hp; int kind;
+};
+
+__device__ __forceinline__ void emit_row4(const PushDst& d, const TableGeom& g, int owner,
+                                          int local, int k, int c, float4 v, bool async) {
+  if (!async) {
+    const uint4 o = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z),
+                               __float_as_uint(v.w));
+    if (g.replicated) {
+      for (int p = 0; p < g.W; ++p) {
+        const int q = (d.rank + p) % g.W;
+        st_v4_stream(reinterpret_cast<float4*>(d.rings[q]) + ((size_t)d.rank * d.cap + k) * g.D4 + c, o);
+      }
+    } else {
+      st_v4_stream(reinterpret_cast<float4*>(d.rings[owner]) + ((size_t)d.rank * d.cap + k) * g.D4 + c, o);
+    }
+  } else {
+    float4* pw = reinterpret_cast<float4*>(d.tables[owner]) + (size_t)local * g.D4 + c;
+    float4* p0 = d.slot0s ? reinterpret_cast<float4*>(d.slot0s[owner]) + (size_t)local * g.D4 + c : nullptr;
+    float4* p1 = d.slot1s ? reinterpret_cast<float4*>(d.slot1s[owner]) + (size_t)local * g.D4 + c : nullptr;
+    float4 w = *pw, s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);
+    if (p0) s0 = *p0;
+    if (p1) s1 = *p1;
+    sparse_update4(d.kind, d.hp[0], d.hp[1], d.hp[2], d.hp[3], d.hp[7], v, w, s0, s1);
+    *pw = w;
+    if (p0) *p0 = s0;
+    if (p1) *p1 = s1;
+  }
+}
+
+__device__ __forceinline__ void emit_id(const PushDst& d, const TableGeom& g, int owner, int local,
+                                        int k) {
+  if (g.replicated) {
+    for (int p = 0; p < g.W; ++p)
+      reinterpret_cast<int32_t*>(d.rings[p] + d.ring_ids_off)[(size_t)d.rank * d.cap + k] = local;
+  } else {
+    reinterpret_cast<int32_t*>(d.rings[owner] + d.ring_ids_off)[(size_t)d.rank * d.cap + k] = local;
+  }
+}
+
+template <typename GradT, bool ASYNC>
+__global__ void __launch_bounds__(256)
+px_sparse_scatter_kernel(const GradT* __restrict__ pend_grads, int n,
+                         const int32_t* __restrict__ pos2u, const int32_t* __restrict__ uniq_id,
+                         const int32_t* __restrict__ uniq_k, const int32_t* __restrict__ uniq_cnt,
+                         float* __restrict__ staging, const SparseCtl* ctl, PushDst d,
+                         uint32_t* const* __restrict__ hdrs, TableGeom g, float scale, int lpr) {
+  if (!ASYNC) {   // do not overwrite a ring the owner may still be draining
+    if (threadIdx.x < g.W) {
+      const uint32_t need = ctl->step;
+      const uint32_t* applied = hdrs[d.rank] + PX_MAX_RANKS;
+      while ((int32_t)(ld_acquire_sys(applied + threadIdx.x) - need) < 0) { }
+    }
+    __syncthreads();
+  }
+  const int rows_per_block = blockDim.x / lpr;
+  const int sub = threadIdx.x % lpr;
+  const float mul = ASYNC ? scale * d.hp[6] : scale;
+  for (int i = blockIdx.x * rows_per_block + threadIdx.x / lpr; i < n;
+       i += gridDim.x * rows_per_block) {
+    const int u = pos2u[i];
+    if (u < 0) continue;
+    const int cnt = uniq_cnt[u];
+    if (cnt == 1) {
+      const int id = uniq_id[u], k = uniq_k[u];
+      int owner, local;
+      geom_map(g, id, owner, local);
+      for (int c = sub; c < g.D4; c += lpr) {
+        float4 v = ld_grad4<GradT>(pend_grads, (size_t)i * g.D4 + c);
+        v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
+        emit_row4(d, g, owner, local, k, c, v, ASYNC);
+      }
+      if (!ASYNC && sub == 0) emit_id(d, g, owner, local, k);
+    } else {
+      float4* dst = reinterpret_cast<float4*>(staging) + (size_t)u * g.D4;
+      for (int c = sub; c < g.D4; c += lpr)
+        atomicAdd(dst + c, ld_grad4<GradT>(pend_grads, (size_t)i * g.D4 + c));
+    }
+  }
+}
+
+// Kernel B — unique-parallel: flush the staged (duplicate) rows, re-zero the
+// staging rows, then the last CTA publishes counts + `pushed` flag (sync) or
+// bumps the step (async) and re-arms the local counters.
+template <bool ASYNC>
+__global__ void __launch_bounds__(256)
+px_sparse_flush_kernel(const int32_t* __restrict__ uniq_id, const int32_t* __restrict__ uniq_k,
+                       const int32_t* __restrict__ uniq_cnt, float* __restrict__ staging,
+                       SparseCtl* ctl, PushDst d, uint32_t* const* __restrict__ hdrs, TableGeom g,
+                       float scale, int lpr) {
+  const int rows_per_block = blockDim.x / lpr;
+  const int sub = threadIdx.x % lpr;
+  const int n_uniq = ctl->n_uniq;
+  const float mul = ASYNC ? scale * d.hp[6] : scale;
+  for (int u = blockIdx.x * rows_per_block + threadIdx.x / lpr; u < n_uniq;
+       u += gridDim.x * rows_per_block) {
+    if (uniq_cnt[u] <= 1) continue;
+    const int id = uniq_id[u], k = uniq_k[u];
+    int owner, local;
+    geom_map(g, id, owner, local);
+    float4* src = reinterpret_cast<float4*>(staging) + (size_t)u * g.D4;
+    for (int c = sub; c < g.D4; c += lpr) {
+      float4 v = src[c];
+      src[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
+      emit_row4(d, g, owner, local, k, c, v, ASYNC);
+    }
+    if (!ASYNC && sub == 0) emit_id(d, g, owner, local, k);
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) s_last = (atomicAdd(&ctl->push_done, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  const uint32_t step = ctl->step + 1;
+  if (!ASYNC) {
+    if (threadIdx.x < g.W) {
+      const int o = threadIdx.x;
+      const int cnt = g.replicated ? ctl->owner_cnt[0] : ctl->owner_cnt[o];
+      uint32_t* hdr = hdrs[o];
+      reinterpret_cast<volatile int32_t*>(hdr + 2 * PX_MAX_RANKS)[d.rank] = cnt;   // cnt[src]
+      __threadfence_system();
+      st_release_sys(hdr + d.rank, step);                                          // pushed[src]
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < PX_MAX_RANKS) ctl->owner_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    ctl->n_uniq = 0; ctl->push_done = 0;
+    if (ASYNC) ctl->step = step;
+  }
+}
+
+// ------------------------------------------------------------------ owner
+__device__ __forceinline__ void wait_pushed(const uint32_t* hdr, const SparseCtl* ctl, int W) {
+  if (threadIdx.x < W) {
+    const uint32_t need = ctl->step + 1;
+    while ((int32_t)(ld_acquire_sys(hdr + threadIdx.x) - need) < 0) { }
+  }
+  __syncthreads();
+}
+
+// claim: merge duplicate rows arriving from different sources.  The first
+// entry to claim a row becomes its accumulator; later ones add into it.
+__global__ void __launch_bounds__(256)
+px_sparse_claim_kernel(char* ring, uint32_t* hdr, size_t ring_ids_off, int cap, int32_t* slotmap,
+                       const SparseCtl* ctl, TableGeom g) {
+  wait_pushed(hdr, ctl, g.W);
+  const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const int32_t* cnt = reinterpret_cast<const int32_t*>(hdr + 2 * PX_MAX_RANKS);
+  const int32_t* ids = reinterpret_cast<const int32_t*>(ring + ring_ids_off);
+  float4* rows = reinterpret_cast<float4*>(ring);
+  for (int s = 0; s < g.W; ++s) {
+    const int c = ld_volatile_u32(reinterpret_cast<const uint32_t*>(cnt) + s);
+    for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < c; j += gridDim.x * warps) {
+      const int e = s * cap + j;
+      const int r = ids[e];
+      int old = 0;
+      if (lane == 0) old = atomicCAS(&slotmap[r], -1, e);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old != -1) {
+        for (int cidx = lane; cidx < g.D4; cidx += 32) {
+          const float4 v = rows[(size_t)e * g.D4 + cidx];
+          atomicAdd(&rows[(size_t)old * g.D4 + cidx], v);
+        }
+      }
+    }
+  }
 }
 
 // apply: every claimed row gets exactly one optimizer application with the
@@ -447,61 +512,6 @@ px_sparse_apply_kernel(char* ring, uint32_t* hdr, size_t ring_ids_off, int cap, 
   if (threadIdx.x < g.W) st_release_sys(hdrs[threadIdx.x] + PX_MAX_RANKS + rank, step);
   __syncthreads();
   if (threadIdx.x == 0) { ctl->step = step; ctl->apply_done = 0; }
-}
-
-// ------------------------------------------------------------------- async
-// Hogwild: sum this rank's duplicate rows and apply them straight onto the
-// owner's table/slots over NVLink — no ring, no flags, no step barrier
-// (reference sync=False: ps/between_graph_parallel.py:137-146).
-template <typename GradT>
-__global__ void __launch_bounds__(256)
-px_sparse_async_apply_kernel(const GradT* __restrict__ pend_grads,
-                             const int32_t* __restrict__ uniq_id,
-                             const int32_t* __restrict__ uniq_head,
-                             const int32_t* __restrict__ next, SparseCtl* ctl,
-                             float* const* __restrict__ tables, float* const* __restrict__ slot0s,
-                             float* const* __restrict__ slot1s, const float* hp, float scale,
-                             int kind, TableGeom g) {
-  const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
-  const int n_uniq = ctl->n_uniq;
-  const float lr = hp[0], ha = hp[1], hb = hp[2], eps = hp[3], nesterov = hp[7];
-  const float gmul = scale * hp[6];
-  for (int u = blockIdx.x * warps + (threadIdx.x >> 5); u < n_uniq; u += gridDim.x * warps) {
-    int owner, local;
-    geom_map(g, uniq_id[u], owner, local);
-    for (int c = lane; c < g.D4; c += 32) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int i = uniq_head[u]; i >= 0; i = next[i]) {
-        if (sizeof(GradT) == 4) {
-          const float4 v = reinterpret_cast<const float4*>(pend_grads)[(size_t)i * g.D4 + c];
-          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        } else {
-          const uint2 v = *reinterpret_cast<const uint2*>(
-              reinterpret_cast<const char*>(pend_grads) + ((size_t)i * g.D4 + c) * 8);
-          acc.x += __uint_as_float(v.x << 16); acc.y += __uint_as_float(v.x & 0xffff0000u);
-          acc.z += __uint_as_float(v.y << 16); acc.w += __uint_as_float(v.y & 0xffff0000u);
-        }
-      }
-      acc.x *= gmul; acc.y *= gmul; acc.z *= gmul; acc.w *= gmul;
-      float4* pw = reinterpret_cast<float4*>(tables[owner]) + (size_t)local * g.D4 + c;
-      float4* p0 = slot0s ? reinterpret_cast<float4*>(slot0s[owner]) + (size_t)local * g.D4 + c : nullptr;
-      float4* p1 = slot1s ? reinterpret_cast<float4*>(slot1s[owner]) + (size_t)local * g.D4 + c : nullptr;
-      float4 w = *pw, s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);
-      if (p0) s0 = *p0;
-      if (p1) s1 = *p1;
-      sparse_update4(kind, lr, ha, hb, eps, nesterov, acc, w, s0, s1);
-      *pw = w;
-      if (p0) *p0 = s0;
-      if (p1) *p1 = s1;
-    }
-  }
-  __syncthreads();
-  __shared__ bool s_last;
-  if (threadIdx.x == 0) s_last = (atomicAdd(&ctl->push_done, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  if (threadIdx.x < PX_MAX_RANKS) ctl->owner_cnt[threadIdx.x] = 0;
-  if (threadIdx.x == 0) { ctl->n_uniq = 0; ctl->push_done = 0; ctl->step += 1; }
 }
 
 // copy + scale + (optional) cast of a lookup's grad_output into the pending buffer
@@ -585,21 +595,30 @@ int px_sparse_dedup(const int32_t* pend_ids, int n, int hbits, int32_t* keys, in
 }
 
 // grad_dtype 0 fp32 / 1 bf16.  rings_dev/hdrs_dev: device arrays of `world` pointers.
-int px_sparse_push(const void* pend_grads, int grad_dtype, const int32_t* uniq_id,
-                   const int32_t* uniq_k, const int32_t* uniq_head, const int32_t* next,
-                   void* ctl, void* rings_dev, void* hdrs_dev, size_t ring_ids_off, int cap,
-                   const PxTableGeom* g, float scale, int rank, int blocks,
-                   cudaStream_t stream) {
+// sync push: scatter (position-parallel) + flush (duplicates, flags).
+int px_sparse_push(const void* pend_grads, int grad_dtype, int n, const int32_t* pos2u,
+                   const int32_t* uniq_id, const int32_t* uniq_k, const int32_t* uniq_cnt,
+                   float* staging, void* ctl, void* rings_dev, void* hdrs_dev,
+                   size_t ring_ids_off, int cap, const PxTableGeom* g, float scale, int rank,
+                   int max_blocks, cudaStream_t stream) {
   const TableGeom G = to_geom(g);
+  PushDst d{};
+  d.rings = (char* const*)rings_dev; d.ring_ids_off = ring_ids_off; d.cap = cap; d.rank = rank;
+  const int lpr = pick_lpr(G.D4), rpb = 256 / lpr;
+  int blocks = (n + rpb - 1) / rpb;
+  if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
-#define PUSH(T, CH)                                                                         \
-  px_sparse_push_kernel<T, CH><<<blocks, 256, 0, stream>>>(                                 \
-      (const T*)pend_grads, uniq_id, uniq_k, uniq_head, next, (SparseCtl*)ctl,              \
-      (char* const*)rings_dev, (uint32_t* const*)hdrs_dev, ring_ids_off, cap, G, scale, rank)
-  const int ch = G.D4 <= 32 ? 1 : (G.D4 <= 64 ? 2 : 4);
-  if (grad_dtype == 0) { if (ch == 1) PUSH(float, 1); else if (ch == 2) PUSH(float, 2); else PUSH(float, 4); }
-  else { if (ch == 1) PUSH(__nv_bfloat16, 1); else if (ch == 2) PUSH(__nv_bfloat16, 2); else PUSH(__nv_bfloat16, 4); }
-#undef PUSH
+  if (grad_dtype == 0)
+    px_sparse_scatter_kernel<float, false><<<blocks, 256, 0, stream>>>(
+        (const float*)pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging,
+        (const SparseCtl*)ctl, d, (uint32_t* const*)hdrs_dev, G, scale, lpr);
+  else
+    px_sparse_scatter_kernel<__nv_bfloat16, false><<<blocks, 256, 0, stream>>>(
+        (const __nv_bfloat16*)pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging,
+        (const SparseCtl*)ctl, d, (uint32_t* const*)hdrs_dev, G, scale, lpr);
+  px_sparse_flush_kernel<false><<<blocks, 256, 0, stream>>>(
+      uniq_id, uniq_k, uniq_cnt, staging, (SparseCtl*)ctl, d, (uint32_t* const*)hdrs_dev, G,
+      scale, lpr);
   return (int)cudaGetLastError();
 }
 
@@ -624,23 +643,29 @@ int px_sparse_apply(void* ring, void* hdr, size_t ring_ids_off, int cap, int32_t
   return (int)cudaGetLastError();
 }
 
-int px_sparse_async_apply(const void* pend_grads, int grad_dtype, const int32_t* uniq_id,
-                          const int32_t* uniq_head, const int32_t* next, void* ctl,
-                          void* tables_dev, void* slot0s_dev, void* slot1s_dev, const float* hp,
-                          float scale, int kind, const PxTableGeom* g, int blocks,
-                          cudaStream_t stream) {
+int px_sparse_async_apply(const void* pend_grads, int grad_dtype, int n, const int32_t* pos2u,
+                          const int32_t* uniq_id, const int32_t* uniq_k,
+                          const int32_t* uniq_cnt, float* staging, void* ctl, void* tables_dev,
+                          void* slot0s_dev, void* slot1s_dev, const float* hp, float scale,
+                          int kind, const PxTableGeom* g, int max_blocks, cudaStream_t stream) {
   const TableGeom G = to_geom(g);
+  PushDst d{};
+  d.tables = (float* const*)tables_dev; d.slot0s = (float* const*)slot0s_dev;
+  d.slot1s = (float* const*)slot1s_dev; d.hp = hp; d.kind = kind;
+  const int lpr = pick_lpr(G.D4), rpb = 256 / lpr;
+  int blocks = (n + rpb - 1) / rpb;
+  if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   if (grad_dtype == 0)
-    px_sparse_async_apply_kernel<float><<<blocks, 256, 0, stream>>>(
-        (const float*)pend_grads, uniq_id, uniq_head, next, (SparseCtl*)ctl,
-        (float* const*)tables_dev, (float* const*)slot0s_dev, (float* const*)slot1s_dev, hp, scale,
-        kind, G);
+    px_sparse_scatter_kernel<float, true><<<blocks, 256, 0, stream>>>(
+        (const float*)pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging,
+        (const SparseCtl*)ctl, d, nullptr, G, scale, lpr);
   else
-    px_sparse_async_apply_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(
-        (const __nv_bfloat16*)pend_grads, uniq_id, uniq_head, next, (SparseCtl*)ctl,
-        (float* const*)tables_dev, (float* const*)slot0s_dev, (float* const*)slot1s_dev, hp, scale,
-        kind, G);
+    px_sparse_scatter_kernel<__nv_bfloat16, true><<<blocks, 256, 0, stream>>>(
+        (const __nv_bfloat16*)pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging,
+        (const SparseCtl*)ctl, d, nullptr, G, scale, lpr);
+  px_sparse_flush_kernel<true><<<blocks, 256, 0, stream>>>(
+      uniq_id, uniq_k, uniq_cnt, staging, (SparseCtl*)ctl, d, nullptr, G, scale, lpr);
   return (int)cudaGetLastError();
 }
 

@@ -102,7 +102,10 @@ class _LSTMLayerFn(torch.autograd.Function):
             else dcT.float().clone()
         dh_rec = None if dhT is None else dhT.to(dt)
         dm = torch.empty(Bsz, S, dtype=dt, device=dev)
-        WhT, WPT = Wh.t(), W_P.t()
+        # materialise the transposed weights once per backward: the per-step
+        # [B,4S]@[4S,P] product then runs as a plain NN GEMM (the strided-view
+        # variant made cuBLAS pick a 3x slower split kernel)
+        WhT, WPT = Wh.t().contiguous(), W_P.t().contiguous()
         st = _stream()
         for t in range(T - 1, -1, -1):
             if dh_rec is None:

@@ -529,7 +529,10 @@ class NVSparseTable(object):
             cap = max(int(n * 1.25) + 16, 64)
             dev = self.device
             mk = lambda: torch.empty(cap, dtype=torch.int32, device=dev)
-            self.uniq_id, self.uniq_k, self.uniq_head, self.next = mk(), mk(), mk(), mk()
+            self.uniq_id, self.uniq_k, self.uniq_cnt, self.pos2u = mk(), mk(), mk(), mk()
+            # fp32 staging rows for ids carried by several positions (kept zero
+            # between steps by the flush kernel)
+            self.staging = torch.zeros(cap, self.Dp, dtype=torch.float32, device=dev)
             self.hbits = max(6, int(math.ceil(math.log2(max(2 * cap, 2)))))
             self.use_smem = cap <= self.SMEM_MAX_N
             if not self.use_smem:
@@ -602,23 +605,22 @@ class NVSparseTable(object):
             pend_ids.record_stream(cs)
             grads.record_stream(cs)
         nvops.sparse_dedup(pend_ids, n, self.hbits, self.keys, self.slot_u,
-                           self.uniq_id, self.uniq_k, self.uniq_head, self.next,
+                           self.uniq_id, self.uniq_k, self.uniq_cnt, self.pos2u,
                            self.ctl, self.geom, self.local_aggregation,
                            self.use_smem, stream=cs)
         s0d, s1d = self._sdev(0), self._sdev(1)
         # 8 warps per CTA, one row per warp; bounded by the configured cap
-        blk_push = max(1, min(self.max_blocks, (n + 7) // 8))
         blk_own = max(1, min(self.max_blocks, (n * self.world + 7) // 8))
         if not self.route.sync:
-            nvops.sparse_async_apply(grads, self.uniq_id, self.uniq_head, self.next,
-                                     self.ctl, self._tdev(), s0d, s1d, self.hp,
-                                     self.scale, self.kind, self.geom,
-                                     blk_push, stream=cs)
+            nvops.sparse_async_apply(grads, n, self.pos2u, self.uniq_id, self.uniq_k,
+                                     self.uniq_cnt, self.staging, self.ctl,
+                                     self._tdev(), s0d, s1d, self.hp, self.scale,
+                                     self.kind, self.geom, self.max_blocks, stream=cs)
             return
-        nvops.sparse_push(grads, self.uniq_id, self.uniq_k, self.uniq_head,
-                          self.next, self.ctl, self.rings_dev, self.hdrs_dev,
-                          self.ring_ids_off, self.cap, self.geom, self.scale,
-                          self.rank, blk_push, stream=cs)
+        nvops.sparse_push(grads, n, self.pos2u, self.uniq_id, self.uniq_k,
+                          self.uniq_cnt, self.staging, self.ctl, self.rings_dev,
+                          self.hdrs_dev, self.ring_ids_off, self.cap, self.geom,
+                          self.scale, self.rank, self.max_blocks, stream=cs)
         need_claim = self.world > 1 or not self.local_aggregation
         if need_claim:
             nvops.sparse_claim(self.ring_buf.local_ptr, self.hdr_buf.local_ptr,

@@ -128,24 +128,24 @@ def sparse_lookup(ids, n, tables_dev, out, pend_ids, geom, hdr_ptr, ctl, wait,
         1 if wait else 0, _s(stream)), "sparse_lookup")
 
 
-def sparse_dedup(pend_ids, n, hbits, keys, slot_u, uniq_id, uniq_k, uniq_head,
-                 nxt, ctl, geom, dedup, use_smem, stream=None):
+def sparse_dedup(pend_ids, n, hbits, keys, slot_u, uniq_id, uniq_k, uniq_cnt,
+                 pos2u, ctl, geom, dedup, use_smem, stream=None):
     L = ops.lib()
     _count(1 if use_smem else (3 if dedup else 1))
     ops.check(L.px_sparse_dedup(_p(pend_ids), n, hbits, _p(keys), _p(slot_u),
-                                _p(uniq_id), _p(uniq_k), _p(uniq_head), _p(nxt),
+                                _p(uniq_id), _p(uniq_k), _p(uniq_cnt), _p(pos2u),
                                 _p(ctl), ctypes.byref(geom), 1 if dedup else 0,
                                 1 if use_smem else 0, _s(stream)), "sparse_dedup")
 
 
-def sparse_push(pend_grads, uniq_id, uniq_k, uniq_head, nxt, ctl, rings_dev,
-                hdrs_dev, ring_ids_off, cap, geom, scale, rank, max_blocks=64,
-                stream=None):
+def sparse_push(pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging, ctl,
+                rings_dev, hdrs_dev, ring_ids_off, cap, geom, scale, rank,
+                max_blocks=592, stream=None):
     L = ops.lib()
-    _count()
-    ops.check(L.px_sparse_push(_p(pend_grads), DT[pend_grads.dtype], _p(uniq_id),
-                               _p(uniq_k), _p(uniq_head), _p(nxt), _p(ctl),
-                               _p(rings_dev), _p(hdrs_dev), ring_ids_off, cap,
+    _count(2)
+    ops.check(L.px_sparse_push(_p(pend_grads), DT[pend_grads.dtype], n, _p(pos2u),
+                               _p(uniq_id), _p(uniq_k), _p(uniq_cnt), _p(staging),
+                               _p(ctl), _p(rings_dev), _p(hdrs_dev), ring_ids_off, cap,
                                ctypes.byref(geom), scale, rank, max_blocks,
                                _s(stream)), "sparse_push")
 
@@ -171,13 +171,13 @@ def sparse_apply(ring_ptr, hdr_ptr, ring_ids_off, cap, slotmap, table, slot0,
                                 max_blocks, _s(stream)), "sparse_apply")
 
 
-def sparse_async_apply(pend_grads, uniq_id, uniq_head, nxt, ctl, tables_dev,
-                       slot0s_dev, slot1s_dev, hp, scale, kind, geom,
-                       max_blocks=64, stream=None):
+def sparse_async_apply(pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging, ctl,
+                       tables_dev, slot0s_dev, slot1s_dev, hp, scale, kind, geom,
+                       max_blocks=592, stream=None):
     L = ops.lib()
-    _count()
+    _count(2)
     ops.check(L.px_sparse_async_apply(
-        _p(pend_grads), DT[pend_grads.dtype], _p(uniq_id), _p(uniq_head), _p(nxt),
-        _p(ctl), _p(tables_dev), _p(slot0s_dev), _p(slot1s_dev), _p(hp), scale,
-        KIND_ID[kind], ctypes.byref(geom), max_blocks, _s(stream)),
-        "sparse_async_apply")
+        _p(pend_grads), DT[pend_grads.dtype], n, _p(pos2u), _p(uniq_id), _p(uniq_k),
+        _p(uniq_cnt), _p(staging), _p(ctl), _p(tables_dev), _p(slot0s_dev),
+        _p(slot1s_dev), _p(hp), scale, KIND_ID[kind], ctypes.byref(geom), max_blocks,
+        _s(stream)), "sparse_async_apply")
