@@ -102,21 +102,34 @@ class _LSTMLayerFn(torch.autograd.Function):
             else dcT.float().clone()
         dh_rec = None if dhT is None else dhT.to(dt)
         dm = torch.empty(Bsz, S, dtype=dt, device=dev)
-        # materialise the transposed weights once per backward: the per-step
-        # [B,4S]@[4S,P] product then runs as a plain NN GEMM (the strided-view
-        # variant made cuBLAS pick a 3x slower split kernel)
-        WhT, WPT = Wh.t().contiguous(), W_P.t().contiguous()
+        # dm_t = dh_t @ W_P^T runs as a plain NN GEMM on a materialised W_P^T.
+        WPT = W_P.t().contiguous()
+        # dh_{t-1} = dH_{t-1} + dgates_t @ Wh^T : Wh [P, 4S] is already the
+        # K-contiguous "B^T" operand, so this skinny product (M=B, N=P, K=4S)
+        # goes to our tcgen05 split-K kernel with the +dH addend fused in.
+        from . import gemm as _gemm
+        use_tc = (dt == torch.bfloat16 and Bsz % 128 == 0 and P % 64 == 0 and
+                  (4 * S) % 1024 == 0 and Wh.is_contiguous())
+        WhT = None if use_tc else Wh.t().contiguous()
         st = _stream()
+        if dh_rec is None:
+            dh_tot[T - 1].copy_(dH[T - 1])
+        else:
+            torch.add(dH[T - 1], dh_rec, out=dh_tot[T - 1])
         for t in range(T - 1, -1, -1):
-            if dh_rec is None:
-                dh_tot[t].copy_(dH[t])
-            else:
-                torch.add(dH[t], dh_rec, out=dh_tot[t])
             torch.mm(dh_tot[t], WPT, out=dm)
             _check(L.px_lstm_cell_bwd(_p(dm), _p(dc), _p(act[t]), _p(c_all[t]),
                                       _p(c_all[t + 1]), _p(dgates[t]), Bsz, S, _DT[dt], st),
                    "lstm_cell_bwd")
-            dh_rec = torch.mm(dgates[t], WhT)
+            if t > 0:
+                if use_tc:
+                    _gemm.gemm_tn(dgates[t], Wh, addend=dH[t - 1], splits=16, bn=64,
+                                  out=dh_tot[t - 1])
+                else:
+                    torch.addmm(dH[t - 1], dgates[t], WhT, out=dh_tot[t - 1])
+            else:
+                dh_rec = _gemm.gemm_tn(dgates[0], Wh, splits=16, bn=64) if use_tc \
+                    else torch.mm(dgates[0], WhT)
         _count(T)
         dg2 = dgates.view(T * Bsz, 4 * S)
         dWh = h_all[:T].reshape(T * Bsz, P).t() @ dg2

@@ -33,6 +33,30 @@ def test_lstm_layer_matches_reference(dtype, tol):
             (float((r - g).abs().max()), scale)
 
 
+def test_lstm_layer_bf16_tcgen05_backward_path():
+    """B=128, 4S multiple of 1024: the recurrent backward product runs on the
+    tcgen05 split-K kernel with the fused addend."""
+    from parallax_b200.ops.fused import lstm_layer, lstm_layer_reference
+    torch.manual_seed(0)
+    T, B, E, S, P = 3, 128, 64, 256, 64
+    mk = lambda *s: (torch.randn(*s, device="cuda") * 0.2)
+    x, Wx, Wh, b, WP = mk(T, B, E), mk(E, 4 * S), mk(P, 4 * S), mk(4 * S), mk(S, P)
+    c0, h0, gH = mk(B, S), mk(B, P), mk(T, B, P)
+
+    def run(fn, dt):
+        args = [t.clone().to(dt).requires_grad_(True) for t in (x, Wx, Wh, b, WP)]
+        c = c0.clone().requires_grad_(True)
+        h = h0.clone().to(dt).requires_grad_(True)
+        H, cT, hT = fn(args[0], args[1], args[2], args[3], args[4], c, h, 1.0)
+        (H.float() * gH).sum().backward()
+        return [H.float()] + [a.grad.float() for a in args] + [h.grad.float()]
+    ref = run(lstm_layer_reference, torch.float32)
+    got = run(lstm_layer, torch.bfloat16)
+    for r, g in zip(ref, got):
+        scale = float(r.detach().abs().max()) + 1e-6
+        assert float((r - g).detach().abs().max()) <= 6e-2 * scale + 6e-2
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 4e-2)])
 @pytest.mark.parametrize("S", [100, 1024, 8192])
 def test_sampled_softmax_matches_reference(dtype, tol, S):

@@ -4,16 +4,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from parallax_b200.ops.gemm import gemm_tn, pick_splits
 
-def timeit(fn, n=50):
-    for _ in range(5): fn()
+def timeit(fn, n=40):
+    """Device time per call: n calls captured in one CUDA graph (no launch gaps),
+    weights L2-resident exactly as inside the unrolled LSTM."""
+    for _ in range(3): fn()
     torch.cuda.synchronize()
-    # flush L2 between iterations would hide the fact that weights are L2-resident in
-    # the real loop; report both warm (chained, as in the LSTM) numbers
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n): fn()
+    g.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n): fn()
+    for _ in range(5): g.replay()
     e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / n
+    return e0.elapsed_time(e1) * 1e3 / (5 * n)
 
 shapes = [("dh_rec  dgates@Wh^T", 128, 512, 8192), ("proj    m@W_P", 128, 512, 2048),
           ("gates   h@Wh", 128, 8192, 512), ("dm      dh@W_P^T", 128, 2048, 512)]
