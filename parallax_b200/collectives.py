@@ -69,6 +69,8 @@ def init(comm=None, workspace_bytes=64 << 20, oneshot_bytes=256 << 10):
         return
     comm = comm or Comm.from_env()
     _state = _State(comm, workspace_bytes, oneshot_bytes)
+    import os
+    _registry_lib().px_registry_reset(int(os.environ.get("PARALLAX_CACHE_CAPACITY", 1024)))
 
 
 def shutdown():
@@ -109,22 +111,59 @@ def local_size():
 
 
 # ---------------------------------------------------------------------------
+def _sig_hash(sig):
+    import hashlib
+    return int.from_bytes(hashlib.blake2b(repr(sig).encode(), digest_size=8).digest(),
+                          "little")
+
+
 def _validate(name, kind, tensor, extra=()):
     """First use of `name`: exchange (kind, dtype, shape[1:] or shape) and
-    raise on every rank if they differ — Horovod's mismatch errors."""
+    raise on every rank if they differ — Horovod's mismatch errors.  Validated
+    signatures live in the native LRU registry (`runtime/registry.cpp`, the
+    response-cache analogue): a HIT skips the exchange entirely."""
     st = _st()
-    if name is None or not st.comm.distributed:
+    if name is None:
         return
     shape = tuple(tensor.shape[1:]) if kind == "allgather" else tuple(tensor.shape)
     sig = (kind, str(tensor.dtype), shape, tensor.device.type) + tuple(extra)
-    if st.registry.get(name) == sig:
+    L = _registry_lib()
+    h = _sig_hash(sig)
+    state = L.px_registry_lookup(name.encode(), h)
+    if state == 1:
         return                                  # cache hit: no negotiation
-    sigs = st.comm.all_gather_object(sig)
-    if len(set(sigs)) != 1:
-        st.registry.pop(name, None)
-        raise HorovodInternalError(
-            "Mismatched %s for tensor %r across ranks: %s" % (kind, name, sigs))
-    st.registry[name] = sig
+    if st.comm.distributed:
+        sigs = st.comm.all_gather_object(sig)
+        if len(set(sigs)) != 1:
+            L.px_registry_erase(name.encode())
+            raise HorovodInternalError(
+                "Mismatched %s for tensor %r across ranks: %s" % (kind, name, sigs))
+    L.px_registry_put(name.encode(), h)
+
+
+def _registry_lib():
+    from . import ops
+    global _reg_ready
+    if not globals().get("_reg_ready"):
+        u64 = ctypes.c_uint64
+        ops.register_signatures({
+            "px_registry_reset": (None, [ctypes.c_int]),
+            "px_registry_lookup": (ctypes.c_int, [ctypes.c_char_p, u64]),
+            "px_registry_put": (ctypes.c_int, [ctypes.c_char_p, u64]),
+            "px_registry_erase": (ctypes.c_int, [ctypes.c_char_p]),
+            "px_registry_bits": (ctypes.c_int, [ctypes.POINTER(u64), ctypes.c_int]),
+            "px_registry_stats": (None, [ctypes.POINTER(ctypes.c_long)] * 5),
+        })
+        _reg_ready = True
+    return ops.lib()
+
+
+def registry_stats():
+    L = _registry_lib()
+    v = [ctypes.c_long() for _ in range(5)]
+    L.px_registry_stats(*[ctypes.byref(x) for x in v])
+    return dict(zip(("hits", "misses", "invalid", "evictions", "size"),
+                    [x.value for x in v]))
 
 
 def _vn(dtype):

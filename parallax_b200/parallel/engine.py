@@ -125,6 +125,7 @@ class TrainEngine(object):
         self.step_times = []
         self._build()
         self._consistency_check()
+        self._start_aux()
         if config.export_graph_path:
             self.export_report(config.export_graph_path)
 
@@ -167,6 +168,26 @@ class TrainEngine(object):
             build_nvlink(self)
         else:
             raise ValueError("unknown fabric %r" % self.backend)
+
+    def _start_aux(self):
+        """Timeline, stall watchdog and autotuner."""
+        from ..utils import timeline
+        self.timeline = timeline
+        self.watchdog = None
+        self.autotuner = None
+        try:
+            timeline.start_from_env(self.comm.rank)
+        except Exception as e:  # pragma: no cover
+            parallax_log.warning("timeline disabled: %s", e)
+        if self.backend == "nvlink":
+            from ..utils.watchdog import Watchdog
+            from ..utils.autotune import EngineAutotuner
+            if self.comm.world > 1 or os.environ.get(
+                    consts.PARALLAX_STALL_CHECK_TIME_SECONDS):
+                self.watchdog = Watchdog(self.comm.rank, self.comm.world,
+                                         self.fabric.heap)
+            if EngineAutotuner.wanted():
+                self.autotuner = EngineAutotuner(self)
 
     def _consistency_check(self):
         """Cross-rank check of the static schedule — reproduces Horovod's
@@ -242,12 +263,27 @@ class TrainEngine(object):
         memory, so a replay is exactly a re-execution."""
         t0 = time.perf_counter()
         step = self.global_step + 1
+        tl = self.timeline.enabled()
+        tuning = self.autotuner is not None and not self.autotuner.done
+        if tuning:
+            self.autotuner.step_begin()
+        if tl:
+            self.timeline.instant("CYCLE_START", args="step %d" % step)
+            self.timeline.begin("step", "STEP", "global_step %d" % step)
         self._begin_step(step)
-        if self._use_graph():
+        # traced / tuned steps run eagerly (CUDA-event ranges and changing grid
+        # sizes cannot live inside a captured graph)
+        if self._use_graph() and not tl and not tuning:
             out = self._graph_step(feeds, step)
         else:
             out = self._step_body(feeds, step)
         self.global_step = step
+        if tl:
+            self.timeline.end("step", "STEP")
+        if tuning:
+            self.autotuner.step_end()
+        if self.watchdog is not None:
+            self.watchdog.step_enqueued(step)
         self.step_times.append(time.perf_counter() - t0)
         return out
 
@@ -345,6 +381,9 @@ class TrainEngine(object):
         for t in self.tables.values():
             if hasattr(t, "close"):
                 t.close()
+        if getattr(self, "watchdog", None) is not None:
+            self.watchdog.stop()
+            self.watchdog = None
         fab = getattr(self, "fabric", None)
         if fab is not None:
             fab.close()

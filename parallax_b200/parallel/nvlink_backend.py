@@ -229,6 +229,16 @@ class NVDenseGroup(object):
             self._next += 1
 
     def _launch(self, b):
+        from ..utils import timeline
+        if timeline.enabled():
+            with timeline.activity("bucket%d" % b.index, "DENSE_STEP", gpu=True,
+                                   stream=self.fabric.comm_stream,
+                                   args="%s n=%d %s" % (self.update, b.n, self.kind)):
+                self._launch_impl(b)
+        else:
+            self._launch_impl(b)
+
+    def _launch_impl(self, b):
         fab, heap, cs = self.fabric, self.heap, self.fabric.comm_stream
         cs.wait_event(b.event)
         W = self.world
@@ -587,6 +597,16 @@ class NVSparseTable(object):
         self.hp.copy_(self.hp_host, non_blocking=True)
 
     def finish_step(self, step, stream=None):
+        from ..utils import timeline
+        if timeline.enabled():
+            cs = stream if stream is not None else self.fabric.comm_stream
+            with timeline.activity(self.name, "SPARSE_PUSH_APPLY", gpu=True, stream=cs,
+                                   args="rows=%d" % sum(c[0].numel() for c in self.calls)):
+                self._finish_step_impl(step, stream)
+        else:
+            self._finish_step_impl(step, stream)
+
+    def _finish_step_impl(self, step, stream=None):
         cs = stream if stream is not None else self.fabric.comm_stream
         calls, self.calls = self.calls, []
         if calls:
