@@ -17,6 +17,9 @@ import torch.distributed as dist
 from ..log import parallax_log
 
 
+_GLOO_GROUPS = {}      # one gloo side group per process, shared by all Comms
+
+
 class Comm(object):
     def __init__(self, rank=0, world=1, local_rank=0, device=None, group=None,
                  owns_pg=False):
@@ -75,7 +78,10 @@ class Comm(object):
             if dist.get_backend(self.group) == "gloo":
                 self._host_group = self.group
             else:
-                self._host_group = dist.new_group(backend="gloo")
+                key = id(self.group)
+                if key not in _GLOO_GROUPS:
+                    _GLOO_GROUPS[key] = dist.new_group(backend="gloo")
+                self._host_group = _GLOO_GROUPS[key]
         return self._host_group
 
     # -- control plane -------------------------------------------------------
