@@ -310,10 +310,15 @@ class TrainEngine(object):
             torch.cuda.synchronize(dev)
             if self.comm.distributed:
                 self.comm.barrier()
+            from . import nvops
             g = torch.cuda.CUDAGraph()
+            l0 = nvops.launches["n"]
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 out = self._step_body(static, step)
-            st = {"sig": sig, "graph": g, "in": static, "out": out}
+            # our own kernels recorded in the graph: each replay launches them again
+            st = {"sig": sig, "graph": g, "in": static, "out": out,
+                  "launches": nvops.launches["n"] - l0}
+            nvops.launches["n"] = l0
             self._graph_state = st
             self.graph_captured = True
             parallax_log.info("captured the training step into a CUDA graph")
@@ -321,6 +326,8 @@ class TrainEngine(object):
             for k, v in feeds.items():
                 st["in"][k].copy_(v, non_blocking=True)
         st["graph"].replay()
+        from . import nvops
+        nvops.launches["n"] += st["launches"]
         return st["out"]
 
     def eval_step(self, feeds):

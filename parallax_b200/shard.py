@@ -49,6 +49,7 @@ class _Registry(object):
         self.num_shards = None
         self.shard_id = None
         self.filters = []
+        self.assignment = None      # (num_workers, worker_id, replicas) once known
 
 
 _registry = _Registry()
@@ -69,6 +70,8 @@ def create_num_shards_and_shard_id():
         raise ValueError('"shard_id" already exists.')
     _registry.num_shards = ShardValue(1, NUM_SHARDS)
     _registry.shard_id = ShardValue(0, SHARD_ID)
+    if _registry.assignment is not None:     # created after parallel_run
+        update_shard_values_for_worker(*_registry.assignment)
     return _registry.num_shards, _registry.shard_id
 
 
@@ -119,6 +122,7 @@ def update_shard_values_for_worker(num_workers, worker_id,
     ``shard_id += num_replicas_per_worker * worker_id``
     (reference `graph_transform_lib.py:707-722`).  Idempotent per process:
     values are recomputed from the planted base (1, 0)."""
+    _registry.assignment = (num_workers, worker_id, num_replicas_per_worker)
     if _registry.num_shards is None:
         return None
     _registry.num_shards.value = 1 * num_workers * num_replicas_per_worker

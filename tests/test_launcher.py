@@ -1,0 +1,67 @@
+"""Master/launcher path: process spawning over a resource file, env protocol,
+redirect logs, analysis export, data sharding, and the partition search loop
+(reference `common/runner.py:62-137`, `common/partitions.py:53-170`)."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCRIPT = os.path.join(ROOT, "tests", "launch_script.py")
+
+
+def _run(tmp_path, run_option, steps, search, timeout=300):
+    res = tmp_path / "resource_info"
+    res.write_text("localhost\nlocalhost\n")          # two CPU workers on this host
+    env = dict(os.environ)
+    for k in list(env):
+        if k.startswith("PARALLAX_") or k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+            env.pop(k)
+    env["PARALLAX_FABRIC"] = "host"
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    env["OMP_NUM_THREADS"] = "1"
+    r = subprocess.run([sys.executable, SCRIPT, str(tmp_path), str(res), run_option,
+                        str(steps), "1" if search else "0"], env=env, capture_output=True,
+                       text=True, timeout=timeout)
+    return r
+
+
+def test_master_spawns_workers_and_exits(tmp_path):
+    r = _run(tmp_path, "HYBRID", 5, False)
+    assert r.returncode == 0, r.stderr[-2000:]
+    outs = sorted(glob.glob(str(tmp_path / "worker_*.json")))
+    assert len(outs) == 2
+    infos = [json.load(open(o)) for o in outs]
+    assert sorted(i["worker_id"] for i in infos) == [0, 1]
+    for i in infos:
+        assert i["num_workers"] == 2 and i["global_step"] == 5
+        assert i["env_role"] == "PARALLAX_RUN_HYBRID"
+        # shard(ds): element k kept iff k % 2 == worker_id
+        assert i["first"] == [i["worker_id"], i["worker_id"] + 2, i["worker_id"] + 4]
+    # redirect files + per-worker analysis dump
+    assert os.path.exists(tmp_path / "logs" / "log_worker0_stderr")
+    assert os.path.exists(tmp_path / "graph" / "analysis_worker_1.json")
+    rep = json.load(open(tmp_path / "graph" / "analysis_worker_0.json"))
+    assert rep["num_sparse"] == 1 and rep["tables"]["emb.weight"]["P"] == 2
+
+
+def test_partition_search_relaunches_and_converges(tmp_path):
+    """The launcher re-runs the job with P = 2, 4, ... measuring steps 50-100,
+    stops when a candidate is slower / out of range, then runs the final job
+    with the fitted optimum."""
+    r = _run(tmp_path, "HYBRID", 110, True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    outs = glob.glob(str(tmp_path / "worker_*.json"))
+    # the final (non-search) run completed on both workers with one agreed P
+    final = [json.load(open(o)) for o in outs]
+    ps = {}
+    for i in final:
+        ps.setdefault(i["partitions"], []).append(i["worker_id"])
+    assert any(sorted(v) == [0, 1] for v in ps.values())
+    assert "partition search: trying P=2" in r.stderr
+    assert "optimal partitions" in r.stderr
+    for i in final:
+        assert i["tableP"] == i["partitions"]
