@@ -1,0 +1,184 @@
+"""Unit tests of the API surface: config validation, resource (de)serialisation,
+shard arithmetic, partition search maths, mode degeneration, checkpoint
+save/restore-on-start/resume-under-a-different-layout, profile steps."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import parallax_b200 as parallax
+from parallax_b200 import optim, shard
+from parallax_b200.analyzer import analyze, greedy_load_balance
+from parallax_b200.models.simple import MLPWithEmbedding
+from parallax_b200.partitions import SearchState, find_optimal_p, fit_cost_model
+from parallax_b200.resource import (parse_resource_info, serialize_resource_info,
+                                    deserialize_resource_info, worker_layout,
+                                    get_cluster_str_for_hosts)
+
+
+def test_public_api_names():
+    for n in ["parallel_run", "Config", "PSConfig", "MPIConfig", "CommunicationConfig",
+              "CheckPointConfig", "ProfileConfig", "get_partitioner", "shard", "log"]:
+        assert hasattr(parallax, n)
+    import parallax as alias
+    assert alias.parallel_run is parallax.parallel_run
+    assert alias.shard.shard is parallax.shard.shard
+
+
+def test_config_defaults_and_validation():
+    c = parallax.Config()
+    assert c.run_option == "HYBRID" and c.average_sparse is False
+    assert c.search_partitions is True
+    ps = c.communication_config.ps_config
+    assert (ps.protocol, ps.replicate_variables, ps.local_aggregation) == ("grpc", True, True)
+    assert ps.boundary_among_servers and ps.boundary_between_workers_and_servers
+    assert parallax.Config(run_option="AR").normalized_run_option() == "MPI"
+    cfg = parallax.Config()
+    cfg.run_option = "PS",                       # the reference docs' stray tuple
+    assert cfg.normalized_run_option() == "PS"
+    with pytest.raises(ValueError):
+        parallax.Config(run_option="TP").normalized_run_option()
+    m = parallax.MPIConfig(mpirun_options=["-x", "NCCL_DEBUG=INFO", "-mca", "btl", "^openib"])
+    assert m.mpirun_options == "-x NCCL_DEBUG=INFO -mca btl ^openib"
+    assert m.exported_env() == {"NCCL_DEBUG": "INFO"}
+    with pytest.raises(AssertionError):
+        parallax.ProfileConfig(profile_dir="/tmp/x", profile_steps=[1], profile_range=(1, 2))
+    with pytest.raises(AssertionError):
+        parallax.CommunicationConfig(ps_config="nope")
+
+
+def test_resource_info_roundtrip(tmp_path):
+    f = tmp_path / "resource_info"
+    f.write_text("hostA:0,1,2\nhostB:4,5\n\n")
+    info = parse_resource_info(str(f), "HYBRID")
+    assert info["master"][0]["hostname"] == "hostA"
+    assert [w["gpus"] for w in info["worker"]] == [[0, 1, 2], [4, 5]]
+    assert len(info["ps"]) == 2                                   # one PS entry per host
+    assert len(info["worker"][0]["port"]) == 3                    # HYBRID: port per GPU
+    assert len(parse_resource_info(str(f), "PS")["worker"][0]["port"]) == 1
+    back = deserialize_resource_info(serialize_resource_info(info))
+    assert back == info
+    lay = worker_layout(info)
+    assert [(h, m, l, g) for h, m, l, g in lay] == [
+        ("hostA", 0, 0, 0), ("hostA", 0, 1, 1), ("hostA", 0, 2, 2),
+        ("hostB", 1, 0, 4), ("hostB", 1, 1, 5)]
+    assert get_cluster_str_for_hosts(info["worker"], True) == "hostA:3,hostB:2"
+
+
+def test_shard_arithmetic():
+    shard.reset()
+    ns, sid = shard.create_num_shards_and_shard_id()
+    with pytest.raises(ValueError):
+        shard.create_num_shards_and_shard_id()
+    ds = shard.shard(list(range(20)))
+    assert list(ds) == list(range(20))                 # (1, 0) before parallel_run
+    assert shard.update_shard_values_for_worker(4, 3, 1) == (4, 3)
+    assert list(ds) == [3, 7, 11, 15, 19] and len(ds) == 5 and ds[1] == 7
+    assert shard.update_shard_values_for_worker(2, 1, 3) == (6, 3)   # in-graph replicas
+    samp = shard.DistributedShardSampler(list(range(12)))
+    assert list(samp) == [3, 9]
+
+
+def test_partition_search_math():
+    f = lambda p: 0.01 * (p - 1) + 4.0 / p + 1.0
+    a, b, c = fit_cost_model([2, 4, 8, 16, 32], [f(p) for p in [2, 4, 8, 16, 32]])
+    assert abs(a - 0.01) < 1e-6 and abs(b - 4.0) < 1e-6 and abs(c - 1.0) < 1e-6
+    assert find_optimal_p([8, 16, 32], [f(8), f(16), f(32)]) == 20
+    s = SearchState(8)
+    keep = True
+    while keep:
+        keep, p = s.report(f(s.p_to_test))
+    assert s.p_list == [8, 16, 32] and p == 20
+    # a candidate that crashes (OOM) doubles the minimum
+    s = SearchState(4)
+    keep, p = s.report(0.0, alive=False)
+    assert keep and p == 8 and s.min_partitions == 8
+    part = parallax.get_partitioner(16)
+    assert part.num_partitions == 16 and os.environ["PARALLAX_MIN_PARTITIONS"] == "16"
+    os.environ["PARALLAX_PARTITIONS"] = "64"
+    try:
+        assert parallax.get_partitioner(16).num_partitions == 64
+    finally:
+        del os.environ["PARALLAX_PARTITIONS"]
+
+
+def test_analyzer_and_mode_degeneration():
+    a = analyze(MLPWithEmbedding(64), world=4)
+    assert [v.name for v in a.sparse] == ["emb.weight"] and len(a.dense) == 4
+    assert a.variables["emb.weight"].partitions == 4
+    assert a.effective_run_option("HYBRID") == "HYBRID"
+    dense_only = analyze(torch.nn.Linear(3, 3))
+    assert dense_only.effective_run_option("HYBRID") == "MPI"
+    sparse_only = analyze(parallax.nn.Embedding(10, 4))
+    assert sparse_only.effective_run_option("HYBRID") == "PS"
+    assert greedy_load_balance([10, 1, 1, 1, 8], 2) == [0, 1, 1, 1, 1]
+
+
+def _train(cfg, steps, seed=0, model_kw=None):
+    torch.manual_seed(seed)
+    model = MLPWithEmbedding(64, partitioner=parallax.get_partitioner(3), **(model_kw or {}))
+    g = parallax.Graph(model, optimizer=optim.Adagrad(0.2, 1.0),
+                       ema=parallax.ExponentialMovingAverage(0.9, ["fc2.*"]))
+    sess, *_ = parallax.parallel_run(g, "localhost", parallax_config=cfg)
+    gen = torch.Generator().manual_seed(1 + sess.engine.global_step)
+    out = []
+    for _ in range(steps):
+        ids = torch.randint(0, 64, (4, 3), generator=gen)
+        labels = torch.randint(0, 4, (4,), generator=gen)
+        out.append(sess.run(["loss", "global_step", "train_op"],
+                            {"ids": [ids], "labels": [labels]}))
+    return sess, out
+
+
+def test_checkpoint_save_and_restore_on_start(tmp_path):
+    ck = parallax.CheckPointConfig(ckpt_dir=str(tmp_path / "ckpt"), save_ckpt_steps=2)
+    cfg = parallax.Config(ckpt_config=ck, sess_config={"fabric": "host"})
+    sess, out = _train(cfg, 5)
+    files = sorted(os.listdir(tmp_path / "ckpt"))
+    assert "checkpoint" in files and "model.ckpt-2.pt" in files and "model.ckpt-4.pt" in files
+    assert open(tmp_path / "ckpt" / "checkpoint").read() == "model.ckpt-4.pt"
+    ref = sess.engine.state_dict()
+    sess.close()
+    # a new job with the same ckpt_dir resumes from step 4 — under a different run option
+    cfg2 = parallax.Config(run_option="PS", ckpt_config=ck, sess_config={"fabric": "host"})
+    sess2, out2 = _train(cfg2, 1)
+    assert out2[0][1] == [5]
+    sd = torch.load(tmp_path / "ckpt" / "model.ckpt-4.pt", weights_only=False)
+    assert sd["global_step"] == 4
+    assert set(sd["sparse"]["emb.weight"]) == {"weight", "slots"}
+    assert sd["sparse"]["emb.weight"]["weight"].shape == (64, 8)
+    assert "fc2.weight" in sd["dense"]["ema"]
+    sess2.close()
+
+
+def test_profile_steps_dump(tmp_path):
+    pc = parallax.ProfileConfig(profile_dir=str(tmp_path / "prof"), profile_steps=[1, 3])
+    cfg = parallax.Config(profile_config=pc, sess_config={"fabric": "host"})
+    sess, _ = _train(cfg, 4)
+    sess.close()
+    import socket
+    d = tmp_path / "prof" / socket.gethostname() / "worker:0" / "run_meta"
+    got = sorted(os.listdir(d))
+    assert "run_meta_1.json" in got and "run_meta_3.json" in got and "run_meta_2.json" not in got
+    assert "worker:0" in open(tmp_path / "prof" / socket.gethostname() / "task_info").read()
+
+
+def test_session_feed_fetch_contract():
+    cfg = parallax.Config(sess_config={"fabric": "host"})
+    sess, out = _train(cfg, 1)
+    loss, gs, train = out[0]
+    assert isinstance(loss, list) and len(loss) == 1 and gs == [1] and train == [None]
+    ids = torch.randint(0, 64, (4, 3))
+    labels = torch.zeros(4, dtype=torch.long)
+    r = sess.run({"l": "loss", "both": ["logits", "global_step"]},
+                 {"ids": [ids], "labels": [labels]})
+    assert set(r) == {"l", "both"} and r["both"][0][0].shape == (4, 4) and r["both"][1] == [1]
+    with pytest.raises(ValueError):
+        sess.run("loss", {"ids": [ids, ids], "labels": [labels]})
+    with pytest.raises(KeyError):
+        sess.run("loss", {"nope": [ids]})
+    with pytest.raises(KeyError):
+        sess.run("not_a_tensor", {"ids": [ids], "labels": [labels]})
+    sess.close()
