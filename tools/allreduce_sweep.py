@@ -51,6 +51,19 @@ def timed(fn, iters):
     return float(t) * 1e-3
 
 
+from parallax_b200.parallel import multicast
+mcbuf = None
+try:
+    if multicast.supported(comm):
+        mcbuf = multicast.MulticastBuffer(st.fabric, args.max_bytes)
+        if rank == 0:
+            print("NVLS multicast buffer ready (%d MiB)" % (mcbuf.nbytes >> 20), flush=True)
+    elif rank == 0:
+        print("NVLS multicast not supported on this box", flush=True)
+except Exception as e:
+    mcbuf = None
+    if rank == 0:
+        print("NVLS setup failed:", e, flush=True)
 rows = []
 size = 1024
 buf = hvd.symmetric_empty(args.max_bytes // 2, torch.bfloat16)     # one symmetric segment
@@ -73,15 +86,34 @@ while size <= args.max_bytes:
                                                        1.0, CH_USER, max_blocks=args.blocks),
                        args.iters)
         algo = "twoshot"
+    t_nvls = None
+    if mcbuf is not None and size >= 65536:
+        mx = mcbuf.tensor(torch.bfloat16, npad)
+        mx.normal_()
+        if size == 65536:      # correctness check against NCCL once
+            ref = mx.clone().float()
+            dist.all_reduce(ref)
+            torch.cuda.synchronize(); dist.barrier()
+            mcbuf.allreduce_(npad, torch.bfloat16, 1.0, CH_USER, max_blocks=args.blocks)
+            torch.cuda.synchronize()
+            err = float((mx.float() - ref).abs().max())
+            if rank == 0:
+                print("NVLS correctness: max |err| = %.4f (ref max %.2f)" % (err, float(ref.abs().max())), flush=True)
+        t_nvls = timed(lambda: mcbuf.allreduce_(npad, torch.bfloat16, 1.0, CH_USER,
+                                                max_blocks=args.blocks), args.iters)
     f = 2.0 * (W - 1) / W
     row = {"bytes": size, "algo": algo, "ours_us": t_ours * 1e6, "nccl_us": t_nccl * 1e6,
+           "nvls_us": None if t_nvls is None else t_nvls * 1e6,
+           "nvls_busbw_GBs": None if t_nvls is None else size / t_nvls * f / 1e9,
            "ours_busbw_GBs": size / t_ours * f / 1e9, "nccl_busbw_GBs": size / t_nccl * f / 1e9,
            "speedup": t_nccl / t_ours, "n_gpus": W}
     rows.append(row)
     if rank == 0:
         print("%11d B %8s  ours %9.1f us (%7.1f GB/s bus)   nccl %9.1f us (%7.1f GB/s bus)  x%.2f"
               % (size, algo, row["ours_us"], row["ours_busbw_GBs"], row["nccl_us"],
-                 row["nccl_busbw_GBs"], row["speedup"]), flush=True)
+                 row["nccl_busbw_GBs"], row["speedup"]) +
+              ("" if t_nvls is None else "   nvls %9.1f us (%7.1f GB/s bus)" %
+               (row["nvls_us"], row["nvls_busbw_GBs"])), flush=True)
     size *= 4
 if rank == 0 and args.out:
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
