@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="parallax_b200",
                     choices=["parallax_b200", "reference", "nccl"])
-    ap.add_argument("--model", default="lm1b", choices=["lm1b", "resnet50"])
+    ap.add_argument("--model", default="lm1b", choices=["lm1b", "resnet50", "ncf", "bert"])
     ap.add_argument("--run-option", default="HYBRID")
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--batch", type=int, default=None)
@@ -169,6 +169,42 @@ def build_resnet(args, parallax, torch):
     return graph, make_batch, desc, "resnet50_images_per_sec", "images/s", BASELINE_RESNET_IPS
 
 
+def build_ncf(args, parallax, torch):
+    from parallax_b200.models.ncf import NeuMF, ncf_graph
+    users = 1_000_000 if args.small else 100_000_000
+    items = 100_000 if args.small else 1_000_000
+    batch = args.batch or (4096 if args.small else 65536)
+    model = NeuMF(users, items, num_partitions=8, lazy=True)
+    graph = ncf_graph(model)
+
+    def make_batch(gen):
+        return {"users": torch.randint(0, users, (batch,), generator=gen),
+                "items": torch.randint(0, items, (batch,), generator=gen),
+                "labels": torch.randint(0, 2, (batch,), generator=gen)}
+    desc = {"model": "neumf(users=%d,items=%d,dim=64+128)" % (users, items),
+            "per_gpu_batch": batch, "seq_len": 1, "optimizer": "adam(1e-3, lazy sparse)",
+            "items_per_step": batch}
+    return graph, make_batch, desc, "ncf_samples_per_sec", "samples/s", None
+
+
+def build_bert(args, parallax, torch):
+    from parallax_b200.models.bert import Bert, bert_graph
+    if args.small:
+        model, batch, T = Bert(hidden=256, layers=4, heads=4, ff=1024), args.batch or 8, 128
+    else:
+        model, batch, T = Bert(), args.batch or 16, 512
+    graph = bert_graph(model)
+    nm = max(1, int(T * 0.15))
+
+    def make_batch(gen):
+        return {"input_ids": torch.randint(0, 30522, (batch, T), generator=gen),
+                "mlm_positions": torch.randint(0, T, (batch, nm), generator=gen),
+                "mlm_labels": torch.randint(0, 30522, (batch, nm), generator=gen)}
+    desc = {"model": "bert_large" if not args.small else "bert_small", "per_gpu_batch": batch,
+            "seq_len": T, "optimizer": "adam(1e-4)+clip(1.0)", "items_per_step": batch * T}
+    return graph, make_batch, desc, "bert_tokens_per_sec", "tokens/s", None
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -188,7 +224,8 @@ def main():
         print(json.dumps({"error": "no CUDA device", "metric": "lm1b_words_per_sec"}))
         return 1
     torch.manual_seed(1234 + rank)
-    builder = build_lm1b if args.model == "lm1b" else build_resnet
+    builder = {"lm1b": build_lm1b, "resnet50": build_resnet, "ncf": build_ncf,
+               "bert": build_bert}[args.model]
     graph, make_batch, desc, metric, unit, baseline = builder(args, parallax, torch)
     sc = {"compute_dtype": args.dtype, "cuda_graph": not args.no_graph}
     cfg = parallax.Config(run_option=args.run_option, search_partitions=False,
@@ -263,7 +300,7 @@ def main():
             "metric": metric, "value": value, "unit": unit, "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": value / baseline, "dtype": args.dtype,
+            "vs_baseline": (value / baseline) if baseline else None, "dtype": args.dtype,
             "data": "synthetic (random ids / images, random-init weights)",
             "impl": "parallax_b200",
             "config": {"model": desc["model"],

@@ -253,6 +253,22 @@ int px_allgather(const void* const* bufs, void* pads_dev, void* epoch_ctr, int c
 // result to every GPU with ONE multimem.st — (N+1)/N·n bytes cross this GPU's
 // links instead of 2(N-1)/N·n, and no SM does the adds.
 template <typename T>
+__device__ __forceinline__ uint4 mm_ld_reduce(const T* p) {
+  uint4 r;
+  if (sizeof(T) == 2)
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  else
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void mm_st(void* p, const uint4& r) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               ::"l"(p), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w) : "memory");
+}
+
+template <typename T, int UNROLL>
 __global__ void __launch_bounds__(512)
 px_allreduce_nvls_kernel(T* __restrict__ mc, uint32_t* const* pads, uint32_t* epoch_ctr,
                          int ch_start, int ch_end, size_t n, float scale, int rank, int world) {
@@ -262,24 +278,28 @@ px_allreduce_nvls_kernel(T* __restrict__ mc, uint32_t* const* pads, uint32_t* ep
   const size_t nvec = slice / VN;
   const size_t base = (size_t)rank * slice;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-    T* p = mc + base + v * VN;
-    uint4 r;
-    if (sizeof(T) == 2)
-      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    else
-      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-    if (scale != 1.f) {
-      float f[VN];
-      Vec16<T>::unpack(r, f);
+  for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec;
+       v0 += stride * UNROLL) {
+    uint4 r[UNROLL];
 #pragma unroll
-      for (int i = 0; i < VN; ++i) f[i] *= scale;
-      r = Vec16<T>::pack(f);
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t v = v0 + (size_t)u * stride;
+      if (v < nvec) r[u] = mm_ld_reduce<T>(mc + base + v * VN);
     }
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
-                 ::"l"(p), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w) : "memory");
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t v = v0 + (size_t)u * stride;
+      if (v < nvec) {
+        if (scale != 1.f) {
+          float f[VN];
+          Vec16<T>::unpack(r[u], f);
+#pragma unroll
+          for (int i = 0; i < VN; ++i) f[i] *= scale;
+          r[u] = Vec16<T>::pack(f);
+        }
+        mm_st(mc + base + v * VN, r[u]);
+      }
+    }
   }
   px_block_barrier(pads, epoch_ctr, ch_end, rank, world);
 }
@@ -289,13 +309,13 @@ extern "C" int px_allreduce_nvls(void* mc_ptr, void* pads_dev, void* epoch_ctr, 
                                  int max_blocks, cudaStream_t stream) {
   const int vn = dtype == 0 ? 4 : 8;
   if (n % ((size_t)world * vn) != 0) return -1;
-  const int blocks = px_clamp_blocks(n / world / vn, 512 * 2, max_blocks);
+  const int blocks = px_clamp_blocks(n / world / vn, 512 * 8, max_blocks);
   if (dtype == 0)
-    px_allreduce_nvls_kernel<float><<<blocks, 512, 0, stream>>>(
+    px_allreduce_nvls_kernel<float, 8><<<blocks, 512, 0, stream>>>(
         (float*)mc_ptr, (uint32_t* const*)pads_dev, (uint32_t*)epoch_ctr, ch_start, ch_end, n,
         scale, rank, world);
   else
-    px_allreduce_nvls_kernel<__nv_bfloat16><<<blocks, 512, 0, stream>>>(
+    px_allreduce_nvls_kernel<__nv_bfloat16, 8><<<blocks, 512, 0, stream>>>(
         (__nv_bfloat16*)mc_ptr, (uint32_t* const*)pads_dev, (uint32_t*)epoch_ctr, ch_start,
         ch_end, n, scale, rank, world);
   return (int)cudaGetLastError();
