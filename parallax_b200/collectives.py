@@ -233,7 +233,51 @@ def _allreduce_cuda(x, out, scale):
     return out
 
 
-def allreduce(tensor, average=True, name=None, out=None):
+class Compression(object):
+    """Gradient compression for all-reduce (`horovod/tensorflow/compression.py:46-64`:
+    ``Compression.none`` / ``Compression.fp16``).  bf16 is the Blackwell-native
+    16-bit wire format; fp16 is kept for parity."""
+
+    class none(object):
+        @staticmethod
+        def compress(t):
+            return t, None
+
+        @staticmethod
+        def decompress(t, ctx):
+            return t
+
+    class fp16(object):
+        @staticmethod
+        def compress(t):
+            return (t.to(torch.float16), t.dtype) if t.is_floating_point() else (t, None)
+
+        @staticmethod
+        def decompress(t, ctx):
+            return t.to(ctx) if ctx is not None else t
+
+    class bf16(object):
+        @staticmethod
+        def compress(t):
+            return (t.to(torch.bfloat16), t.dtype) if t.is_floating_point() else (t, None)
+
+        @staticmethod
+        def decompress(t, ctx):
+            return t.to(ctx) if ctx is not None else t
+
+
+def allreduce(tensor, average=True, name=None, out=None, compression=None):
+    if compression is not None and compression is not Compression.none:
+        c, ctx = compression.compress(tensor)
+        r = compression.decompress(allreduce(c, average, name), ctx)
+        if out is not None:
+            out.copy_(r)
+            return out
+        return r
+    return _allreduce_impl(tensor, average, name, out)
+
+
+def _allreduce_impl(tensor, average=True, name=None, out=None):
     """Sum (or mean) of `tensor` over all ranks.  A ``torch.sparse`` tensor is
     reduced Horovod-style: all-gather of indices and values (duplicates kept,
     values ÷ size when `average`)."""

@@ -66,6 +66,17 @@ class NVDenseGroup(object):
         self.update = opts.get("dense_update", "sharded")   # or "replicated"
         if not route.sync:
             self.update = "async"
+        # PSConfig.protocol == "nccl": library fallback for the dense reduction
+        # (the in-engine baseline); every other protocol value = NVLink kernels.
+        self.protocol = opts.get("_protocol", "nvlink")
+        if self.protocol == "nccl" and route.sync:
+            self.update = "replicated"
+        # PSConfig.replicate_variables (PS run option): True = owners push the
+        # updated values into every mirror right after the update; False =
+        # workers pull the owners' slices at the start of the next step.
+        self.pull_mirrors = (route.run_option == "PS" and route.sync and
+                             not opts.get("_replicate_variables", True) and
+                             self.update == "sharded" and self.world > 1)
         self.names = [n for n, _ in named_params]
         self.params = [p for _, p in named_params]
         self.kind = optimizer.kind
@@ -199,6 +210,14 @@ class NVDenseGroup(object):
         for i, v in enumerate(hp):
             self.hp_host[i] = v
         self.hp.copy_(self.hp_host, non_blocking=True)
+        if self.pull_mirrors and step > 1:
+            # mirror refresh deferred to "first use": all-gather of the owners'
+            # parameter slices before the forward pass
+            cur = torch.cuda.current_stream(self.device)
+            for b in self.buckets:
+                nvops.allgather(self.heap, b.param_buf.c_ptrs(),
+                                (b.n // self.world) * _ES[b.dtype], CH_MAIN,
+                                self.fabric.max_blocks, stream=cur)
 
     def _bucket_ready(self, b):
         views, grads = [], []
@@ -249,7 +268,7 @@ class NVDenseGroup(object):
         st = self.clip_state.get(b.clip)
         if self.update == "sharded":
             if st is None:
-                nvops.dense_step(heap, b.grad_buf.c_ptrs(), b.param_buf.c_ptrs(),
+                nvops.dense_step(heap, b.grad_buf.c_ptrs(), self._param_targets(b),
                                  b.master, s0, s1, b.ema, None, self.hp, None,
                                  None, b.n, 1.0 / W, ema_decay, self.kind,
                                  MODE_FUSED, b.dtype, CH_COMM, max_blocks=mb,
@@ -266,17 +285,28 @@ class NVDenseGroup(object):
                         t0 = bb.slots[0] if self.nslots > 0 else None
                         t1 = bb.slots[1] if self.nslots > 1 else None
                         nvops.dense_step(heap, bb.grad_buf.c_ptrs(),
-                                         bb.param_buf.c_ptrs(), bb.master, t0, t1,
+                                         self._param_targets(bb), bb.master, t0, t1,
                                          bb.ema, bb.red, self.hp, st.scale, None,
                                          bb.n, 1.0 / W, ema_decay, self.kind,
                                          MODE_UPDATE, bb.dtype, CH_COMM,
                                          max_blocks=mb, stream=cs)
         elif self.update == "replicated":
             # classic AR: all-reduce (mean) then every replica updates itself
-            nvops.allreduce_twoshot(heap, b.grad_buf.c_ptrs(), b.n, b.dtype,
-                                    1.0 / W, CH_COMM,
-                                    sumsq=st.local if st is not None else None,
-                                    max_blocks=mb, stream=cs)
+            if self.protocol == "nccl" and W > 1:
+                import torch.distributed as dist
+                with torch.cuda.stream(cs):
+                    dist.all_reduce(b.grad_flat, group=self.fabric.comm.group)
+                    b.grad_flat.mul_(1.0 / W)
+                    if st is not None:
+                        # slice-local Σg² so the cross-rank sum equals the global norm²
+                        sl = b.n // W
+                        st.local[0] += b.grad_flat[self.rank * sl:(self.rank + 1) * sl] \
+                            .float().pow(2).sum()
+            else:
+                nvops.allreduce_twoshot(heap, b.grad_buf.c_ptrs(), b.n, b.dtype,
+                                        1.0 / W, CH_COMM,
+                                        sumsq=st.local if st is not None else None,
+                                        max_blocks=mb, stream=cs)
             if st is None:
                 self._local_update(b, None, cs)
             elif b is st.buckets[-1]:
@@ -295,6 +325,17 @@ class NVDenseGroup(object):
             else:
                 self._async_update(b, clip, cs)
         b.launched = True
+
+    def _param_targets(self, b):
+        """Where the fused kernel stores updated parameters: every peer's mirror
+        (push) or only the local buffer (pull mode; peers fetch later)."""
+        if not self.pull_mirrors:
+            return b.param_buf.c_ptrs()
+        arr = getattr(b, "_self_targets", None)
+        if arr is None:
+            arr = (ctypes.c_void_p * self.world)(*([b.param_buf.local_ptr] * self.world))
+            b._self_targets = arr
+        return arr
 
     def _finish_clip(self, st, cs):
         rule = self.clip_rules[st.buckets[0].clip]
@@ -702,6 +743,9 @@ def build_nvlink(engine):
     ops.lib()      # loud failure if the native library is missing
     g, comm, cfg = engine.graph, engine.comm, engine.config
     opts = dict(cfg.sess_config) if isinstance(cfg.sess_config, dict) else {}
+    ps_cfg = cfg.communication_config.ps_config
+    opts["_protocol"] = "nccl" if ps_cfg.protocol == "nccl" else "nvlink"
+    opts["_replicate_variables"] = bool(ps_cfg.replicate_variables)
     fabric = NVFabric(comm, exchange=opts.get("_exchange"), options=opts)
     engine.fabric = fabric
     dev = comm.device

@@ -20,7 +20,7 @@ from tests.test_hybrid_cpu import make_batch, oracle, make_opt, VOCAB
 
 
 def run_engine(run_option, opt_name, steps, average, sync=True, graph=False,
-               dense_update="sharded", dtype=None):
+               dense_update="sharded", dtype=None, ps=None):
     world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
     model = MLPWithEmbedding(VOCAB, partitioner=parallax.get_partitioner(5))
     g = parallax.Graph(model, optimizer=make_opt(opt_name))
@@ -29,6 +29,8 @@ def run_engine(run_option, opt_name, steps, average, sync=True, graph=False,
         sc["compute_dtype"] = dtype
     cfg = parallax.Config(run_option=run_option, average_sparse=average,
                           sess_config=sc)
+    if ps is not None:
+        cfg.communication_config = parallax.CommunicationConfig(ps)
     sess, nw, wid, _ = parallax.parallel_run(g, "localhost", sync=sync,
                                              parallax_config=cfg)
     assert sess.engine.backend == "nvlink"
@@ -73,6 +75,14 @@ def main():
     losses, w = run_engine("MPI", "momentum", 4, True, dense_update="replicated")
     _, ref = oracle(world, 4, make_opt("momentum"), 1.0)
     check("AR replicated update (allreduce + local optimizer)",
+          all(torch.allclose(w[n], ref[n], rtol=2e-4, atol=2e-5) for n in ref))
+    losses, w = run_engine("PS", "adagrad", 4, True,
+                           ps=parallax.PSConfig(replicate_variables=False))
+    _, ref = oracle(world, 4, make_opt("adagrad"), 1.0)
+    check("PS replicate_variables=False (pull mirrors at next step)",
+          all(torch.allclose(w[n], ref[n], rtol=2e-4, atol=2e-5) for n in ref))
+    losses, w = run_engine("MPI", "adagrad", 4, True, ps=parallax.PSConfig(protocol="nccl"))
+    check("protocol=nccl library fallback for dense",
           all(torch.allclose(w[n], ref[n], rtol=2e-4, atol=2e-5) for n in ref))
     losses, _ = run_engine("PS", "adagrad", 10, False, sync=False)
     check("async PS trains (finite, loss decreases)",
