@@ -742,6 +742,12 @@ def build_nvlink(engine):
         raise RuntimeError("the NVLink fabric needs a CUDA device")
     ops.lib()      # loud failure if the native library is missing
     g, comm, cfg = engine.graph, engine.comm, engine.config
+    # convolution algorithms are picked by measurement during the eager warm-up
+    # steps (shapes are static per graph); TF's cuDNN autotune did the same for the
+    # reference (tensorflow/core/kernels/conv_ops.cc:746-783)
+    torch.backends.cudnn.benchmark = bool(
+        (cfg.sess_config or {}).get("cudnn_benchmark", True)
+        if isinstance(cfg.sess_config, dict) else True)
     opts = dict(cfg.sess_config) if isinstance(cfg.sess_config, dict) else {}
     ps_cfg = cfg.communication_config.ps_config
     opts["_protocol"] = "nccl" if ps_cfg.protocol == "nccl" else "nvlink"
