@@ -293,6 +293,17 @@ def main():
                "ms_per_step": ms2 / K, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "last_loss": float(loss[0])}
     clocks = sampler.stop() if rank == 0 else None
+    # exposed (non-overlapped) comm per step, dense vs sparse — eager steps, device events
+    comm_bd = None
+    try:
+        comm_bd = eng.comm_breakdown(batches[0], steps=5)
+        tb = torch.tensor([comm_bd[k] for k in sorted(comm_bd)], device=dev)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        comm_bd = {k: round(float(v), 4) for k, v in zip(sorted(comm_bd), tb)}
+        comm_bd["note"] = "eager (ungraphed) steps; max over ranks"
+    except Exception as e:  # pragma: no cover
+        comm_bd = {"error": str(e)}
 
     value = desc["items_per_step"] * world * K / (ms / 1e3)
     if rank == 0:
@@ -314,7 +325,7 @@ def main():
                        "valid": not args.small},
             "baseline": {"value": baseline,
                          "what": "Parallax-HYBRID on 48x TITAN Xp (BASELINE.md)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "comm": comm_bd,
             "loss": loss_val,
         }
         print(json.dumps(rec))

@@ -235,19 +235,30 @@ class TrainEngine(object):
         """forward + backward + aggregation + update.  The order in which
         peer-synchronising work is issued is static: dense buckets (from
         autograd hooks, in bucket order) then sparse tables in name order."""
+        ev = getattr(self, "_comm_events", None)
+        if ev is not None:
+            ev["start"].record()
         out = self.forward(feeds)
         loss = out[self.graph.loss]
         if self.graph.loss_scale != 1.0:
             (loss * self.graph.loss_scale).backward()
         else:
             loss.backward()
+        if ev is not None:
+            ev["bwd"].record()
         if self.dense is not None:
             self.dense.finish_step(step)
+        if ev is not None:
+            ev["dense"].record(self.fabric.comm_stream)
         for t in self._table_order():
             t.finish_step(step)
+        if ev is not None:
+            ev["sparse"].record(self.fabric.comm_stream)
         if self.backend == "nvlink":
             torch.cuda.current_stream(self.comm.device).wait_stream(
                 self.fabric.comm_stream)
+        if ev is not None:
+            ev["end"].record()
         return {k: (v.detach() if torch.is_tensor(v) else v)
                 for k, v in out.items()}
 
@@ -286,6 +297,33 @@ class TrainEngine(object):
             self.watchdog.step_enqueued(step)
         self.step_times.append(time.perf_counter() - t0)
         return out
+
+    def comm_breakdown(self, feeds, steps=5):
+        """Exposed (non-overlapped) communication time per step, dense vs sparse
+        (BASELINE.json metric), measured with CUDA events on eager steps:
+        dense kernels are launched from autograd hooks and overlap backward; what
+        is *exposed* is whatever finishes after backward does."""
+        assert self.backend == "nvlink"
+        mk = lambda: torch.cuda.Event(enable_timing=True)
+        acc = {"step_ms": 0.0, "fwd_bwd_ms": 0.0, "exposed_dense_ms": 0.0,
+               "exposed_sparse_ms": 0.0}
+        for _ in range(steps):
+            self._comm_events = {k: mk() for k in ("start", "bwd", "dense", "sparse", "end")}
+            step = self.global_step + 1
+            self._begin_step(step)
+            self._step_body(feeds, step)
+            self.global_step = step
+            torch.cuda.synchronize(self.comm.device)
+            e = self._comm_events
+            t_b = e["start"].elapsed_time(e["bwd"])
+            t_d = e["start"].elapsed_time(e["dense"])
+            t_s = e["start"].elapsed_time(e["sparse"])
+            acc["step_ms"] += e["start"].elapsed_time(e["end"])
+            acc["fwd_bwd_ms"] += t_b
+            acc["exposed_dense_ms"] += max(0.0, t_d - t_b)
+            acc["exposed_sparse_ms"] += max(0.0, t_s - max(t_d, t_b))
+        self._comm_events = None
+        return {k: v / steps for k, v in acc.items()}
 
     # ------------------------------------------------------------ CUDA graph
     def _use_graph(self):
