@@ -41,7 +41,25 @@ struct DenseStepArgs {
   float avg;         // 1/num_workers (or 1)
   float ema_decay;
   int rank, ch_start, ch_end, kind, mode;
+  int use_mc;        // 1: grads.p[0] / params.p[0] are NVSwitch multicast addresses
 };
+
+// NVLS: the switch reduces (fp32 accumulate) / broadcasts; see collectives.cu
+template <typename T>
+__device__ __forceinline__ uint4 ds_mm_ld_reduce(const T* p) {
+  uint4 r;
+  if (sizeof(T) == 2)
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  else
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void ds_mm_st(void* p, const uint4& r) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               ::"l"(p), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w) : "memory");
+}
 
 __device__ __forceinline__ void px_update(int kind, float lr, float a, float b, float eps,
                                           float wd, float nesterov, float g, float& w, float& s0,
@@ -108,6 +126,9 @@ px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr
     float g[VN];
     if (mode == 2) {
       ld_f32<VN>(a.red + e, g);
+    } else if (a.use_mc) {
+      // one switch-side reduction instead of W peer loads
+      Vec16<T>::unpack(ds_mm_ld_reduce<T>(reinterpret_cast<const T*>(a.grads.p[0]) + base + e), g);
     } else {
       uint4 in[W];
 #pragma unroll
@@ -148,9 +169,13 @@ px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr
       st_f32<VN>(a.ema + e, m);
     }
     const uint4 out = Vec16<T>::pack(w);
+    if (a.use_mc) {
+      ds_mm_st(reinterpret_cast<T*>(a.params.p[0]) + base + e, out);   // switch broadcast
+    } else {
 #pragma unroll
-    for (int p = 0; p < W; ++p)
-      st_v4_stream(reinterpret_cast<T*>(a.params.p[p]) + base + e, out);
+      for (int p = 0; p < W; ++p)
+        st_v4_stream(reinterpret_cast<T*>(a.params.p[p]) + base + e, out);
+    }
   }
   if (mode == 1 && a.sumsq != nullptr) block_atomic_sum(ss, a.sumsq);
   if (W > 1 && mode != 1) px_block_barrier(pads, epoch_ctr, a.ch_end, a.rank, W);
@@ -235,13 +260,21 @@ int px_dense_step(const void* const* grads, const void* const* params, float* ma
                   float* slot0, float* slot1, float* ema, float* red, const float* hp,
                   const float* clip, float* sumsq, size_t n, float avg, float ema_decay,
                   int kind, int mode, int dtype, void* pads_dev, void* epoch_ctr, int ch_start,
-                  int ch_end, int rank, int world, int max_blocks, cudaStream_t stream) {
+                  int ch_end, int rank, int world, int max_blocks, int use_mc,
+                  cudaStream_t stream) {
   if (world < 1 || world > 8) return -3;
   const int vn = dtype == 0 ? 4 : 8;
   if (n % ((size_t)world * vn) != 0) return -1;
   DenseStepArgs a;
+  a.use_mc = use_mc;
+  if (use_mc) {            // entry 0 = multicast address; no peer pointers needed
+    a.grads = PeerPtrs{}; a.params = PeerPtrs{};
+    a.grads.p[0] = const_cast<void*>(grads[0]);
+    a.params.p[0] = const_cast<void*>(params[0]);
+  } else {
   a.grads = px_rotate(grads, rank, world);
   a.params = px_rotate(params, rank, world);
+  }
   a.master = master; a.slot0 = slot0; a.slot1 = slot1; a.ema = ema; a.red = red;
   a.hp = hp; a.clip = clip; a.sumsq = sumsq; a.n = n; a.avg = avg; a.ema_decay = ema_decay;
   a.rank = rank; a.ch_start = ch_start; a.ch_end = ch_end; a.kind = kind; a.mode = mode;

@@ -141,7 +141,8 @@ long long px_mc_round_size(size_t bytes, int world) {
   prop.size = bytes;
   prop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
   size_t g = 0;
-  CK(p_cuMulticastGetGranularity(&g, &prop, CU_MULTICAST_GRANULARITY_RECOMMENDED), "granularity");
+  CK(p_cuMulticastGetGranularity(&g, &prop, CU_MULTICAST_GRANULARITY_MINIMUM), "granularity");
+  if (g < (2u << 20)) g = 2u << 20;                       // VMM allocation granularity
   return (long long)((bytes + g - 1) / g * g);
 }
 

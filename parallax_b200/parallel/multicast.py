@@ -104,6 +104,19 @@ class MulticastBuffer(object):
         comm.barrier()
         self._bytes = None
 
+    # -- SymmBuffer-compatible face (used by the dense engine) -----------------
+    @property
+    def local_ptr(self):
+        return self.uc_ptr
+
+    def mc_c_ptrs(self):
+        """ctypes array whose entry 0 is the multicast address."""
+        arr = getattr(self, "_mc_arr", None)
+        if arr is None:
+            arr = (ctypes.c_void_p * 1)(self.mc_ptr)
+            self._mc_arr = arr
+        return arr
+
     def tensor(self, dtype, numel=None):
         if self._bytes is None:
             self._bytes = torch.as_tensor(_CAI(self.uc_ptr, self.nbytes, self),

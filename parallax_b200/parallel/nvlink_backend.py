@@ -62,6 +62,7 @@ class NVDenseGroup(object):
         self.rank, self.world = fabric.rank, fabric.world
         self.device = fabric.device
         opts = options or {}
+        self.options = opts
         self.bucket_bytes = int(opts.get("bucket_bytes", 32 << 20))
         self.update = opts.get("dense_update", "sharded")   # or "replicated"
         if not route.sync:
@@ -119,14 +120,38 @@ class NVDenseGroup(object):
                 del open_b[key]
         self.buckets = buckets
         heap = self.heap
+        # NVLS: bucket buffers bound to an NVSwitch multicast object, the fused
+        # kernel then reduces with multimem.ld_reduce and broadcasts parameters
+        # with multimem.st.  Measured (profiles/allreduce_sweep_8gpu.json): wins
+        # from 256 KB up at 8 GPUs, loses at 2 — "auto" enables it for world >= 4.
+        want = self.options.get("dense_nvls", "auto")
+        self.nvls = False
+        if W > 1 and self.update == "sharded" and not self.pull_mirrors and want:
+            from . import multicast
+            if want is True or (want == "auto" and W >= 4):
+                try:
+                    self.nvls = multicast.supported(self.fabric.comm)
+                except Exception:
+                    self.nvls = False
         for bi, b in enumerate(buckets):
             vn = 16 // _ES[b.dtype]
             quantum = W * vn * 32
             b.index = bi
             b.n = (b.n + quantum - 1) // quantum * quantum
             es = _ES[b.dtype]
-            b.grad_buf = heap.alloc(b.n * es, "grad%d" % bi)
-            b.param_buf = heap.alloc(b.n * es, "param%d" % bi)
+            b.mc = False
+            if self.nvls:
+                from . import multicast
+                try:
+                    b.grad_buf = multicast.MulticastBuffer(self.fabric, b.n * es)
+                    b.param_buf = multicast.MulticastBuffer(self.fabric, b.n * es)
+                    b.mc = True
+                except multicast.MulticastError as e:
+                    parallax_log.warning("NVLS unavailable (%s); using P2P kernels", e)
+                    self.nvls = False
+            if not b.mc:
+                b.grad_buf = heap.alloc(b.n * es, "grad%d" % bi)
+                b.param_buf = heap.alloc(b.n * es, "param%d" % bi)
             b.grad_flat = b.grad_buf.tensor(b.dtype, b.n)
             b.param_flat = b.param_buf.tensor(b.dtype, b.n)
             b.grad_views, b.scales = [], []
@@ -145,8 +170,11 @@ class NVDenseGroup(object):
         if W > 1:
             torch.cuda.synchronize(self.device)
             for b in buckets:
-                nvops.broadcast(heap, b.param_buf.c_ptrs(), b.n * _ES[b.dtype], 0,
-                                CH_MAIN, self.fabric.max_blocks)
+                if b.mc:      # bootstrap only: no peer unicast mappings on NVLS buffers
+                    self.fabric.comm.broadcast_(b.param_flat, 0)
+                else:
+                    nvops.broadcast(heap, b.param_buf.c_ptrs(), b.n * _ES[b.dtype], 0,
+                                    CH_MAIN, self.fabric.max_blocks)
             torch.cuda.synchronize(self.device)
         for b in buckets:
             self._alloc_state(b)
@@ -268,28 +296,28 @@ class NVDenseGroup(object):
         st = self.clip_state.get(b.clip)
         if self.update == "sharded":
             if st is None:
-                nvops.dense_step(heap, b.grad_buf.c_ptrs(), self._param_targets(b),
+                nvops.dense_step(heap, self._grad_sources(b), self._param_targets(b),
                                  b.master, s0, s1, b.ema, None, self.hp, None,
                                  None, b.n, 1.0 / W, ema_decay, self.kind,
                                  MODE_FUSED, b.dtype, CH_COMM, max_blocks=mb,
-                                 stream=cs)
+                                 stream=cs, use_mc=b.mc)
             else:
-                nvops.dense_step(heap, b.grad_buf.c_ptrs(), b.param_buf.c_ptrs(),
+                nvops.dense_step(heap, self._grad_sources(b), self._param_targets(b),
                                  b.master, s0, s1, b.ema, b.red, self.hp, None,
                                  st.local, b.n, 1.0 / W, ema_decay, self.kind,
                                  MODE_REDUCE, b.dtype, CH_COMM, max_blocks=mb,
-                                 stream=cs)
+                                 stream=cs, use_mc=b.mc)
                 if b is st.buckets[-1]:
                     self._finish_clip(st, cs)
                     for bb in st.buckets:
                         t0 = bb.slots[0] if self.nslots > 0 else None
                         t1 = bb.slots[1] if self.nslots > 1 else None
-                        nvops.dense_step(heap, bb.grad_buf.c_ptrs(),
+                        nvops.dense_step(heap, self._grad_sources(bb),
                                          self._param_targets(bb), bb.master, t0, t1,
                                          bb.ema, bb.red, self.hp, st.scale, None,
                                          bb.n, 1.0 / W, ema_decay, self.kind,
                                          MODE_UPDATE, bb.dtype, CH_COMM,
-                                         max_blocks=mb, stream=cs)
+                                         max_blocks=mb, stream=cs, use_mc=bb.mc)
         elif self.update == "replicated":
             # classic AR: all-reduce (mean) then every replica updates itself
             if self.protocol == "nccl" and W > 1:
@@ -326,9 +354,15 @@ class NVDenseGroup(object):
                 self._async_update(b, clip, cs)
         b.launched = True
 
+    def _grad_sources(self, b):
+        return b.grad_buf.mc_c_ptrs() if b.mc else b.grad_buf.c_ptrs()
+
     def _param_targets(self, b):
         """Where the fused kernel stores updated parameters: every peer's mirror
-        (push) or only the local buffer (pull mode; peers fetch later)."""
+        (push; one multimem.st on NVLS buffers) or only the local buffer (pull
+        mode; peers fetch later)."""
+        if b.mc:
+            return b.param_buf.mc_c_ptrs()
         if not self.pull_mirrors:
             return b.param_buf.c_ptrs()
         arr = getattr(b, "_self_targets", None)

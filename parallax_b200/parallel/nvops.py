@@ -70,7 +70,7 @@ def allgather(heap, buf_cptrs, slice_bytes, channels, max_blocks=32, stream=None
 
 def dense_step(heap, grads_cptrs, params_cptrs, master, slot0, slot1, ema, red,
                hp, clip, sumsq, n, avg, ema_decay, kind, mode, dtype, channels,
-               rank=None, world=None, max_blocks=32, stream=None):
+               rank=None, world=None, max_blocks=32, stream=None, use_mc=False):
     L = ops.lib()
     _count()
     ops.check(L.px_dense_step(
@@ -79,8 +79,8 @@ def dense_step(heap, grads_cptrs, params_cptrs, master, slot0, slot1, ema, red,
         mode, DT[dtype], _p(heap.pads_dev()) if heap is not None else _vp(0),
         _p(heap.epoch) if heap is not None else _vp(0), channels[0], channels[1],
         heap.rank if rank is None else rank,
-        heap.world if world is None else world, max_blocks, _s(stream)),
-        "dense_step")
+        heap.world if world is None else world, max_blocks, 1 if use_mc else 0,
+        _s(stream)), "dense_step")
 
 
 def clip_scale(sumsq_total, max_norm, scale_out, norm_out, zero_after, stream=None):

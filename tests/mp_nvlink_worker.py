@@ -20,11 +20,11 @@ from tests.test_hybrid_cpu import make_batch, oracle, make_opt, VOCAB
 
 
 def run_engine(run_option, opt_name, steps, average, sync=True, graph=False,
-               dense_update="sharded", dtype=None, ps=None):
+               dense_update="sharded", dtype=None, ps=None, nvls="auto"):
     world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
     model = MLPWithEmbedding(VOCAB, partitioner=parallax.get_partitioner(5))
     g = parallax.Graph(model, optimizer=make_opt(opt_name))
-    sc = {"cuda_graph": graph, "dense_update": dense_update}
+    sc = {"cuda_graph": graph, "dense_update": dense_update, "dense_nvls": nvls}
     if dtype:
         sc["compute_dtype"] = dtype
     cfg = parallax.Config(run_option=run_option, average_sparse=average,
@@ -76,6 +76,16 @@ def main():
     _, ref = oracle(world, 4, make_opt("momentum"), 1.0)
     check("AR replicated update (allreduce + local optimizer)",
           all(torch.allclose(w[n], ref[n], rtol=2e-4, atol=2e-5) for n in ref))
+    from parallax_b200.parallel import multicast
+    if multicast.supported(comm):
+        for graph in (False, True):
+            steps = 6 if graph else 4
+            losses, w = run_engine("HYBRID", "adagrad", steps, True, graph=graph, nvls=True)
+            _, ref = oracle(world, steps, make_opt("adagrad"), 1.0)
+            check("NVLS fused dense step (multimem) graph=%s vs oracle" % graph,
+                  all(torch.allclose(w[n], ref[n], rtol=2e-4, atol=2e-5) for n in ref))
+    elif rank == 0:
+        print("NVLS multicast unsupported here: skipped", flush=True)
     losses, w = run_engine("PS", "adagrad", 4, True,
                            ps=parallax.PSConfig(replicate_variables=False))
     _, ref = oracle(world, 4, make_opt("adagrad"), 1.0)
