@@ -60,6 +60,18 @@ class _State(object):
             self.oneshot_bytes = int(oneshot_bytes)
             self.stage = heap.alloc(2 * self.oneshot_bytes, "oneshot_stage")
             self.user_bufs = {}
+            # NVLS workspace: measured best from 256 KB up at >= 4 GPUs
+            # (profiles/allreduce_sweep_8gpu.json)
+            self.ws_mc = None
+            self.nvls_min_bytes = 256 << 10
+            if comm.world >= 4:
+                try:
+                    from .parallel import multicast
+                    if multicast.supported(comm):
+                        self.ws_mc = multicast.MulticastBuffer(self.fabric, self.ws_bytes)
+                except Exception as e:  # pragma: no cover
+                    parallax_log.warning("NVLS workspace unavailable: %s", e)
+                    self.ws_mc = None
 
 
 def init(comm=None, workspace_bytes=64 << 20, oneshot_bytes=256 << 10):
@@ -218,17 +230,21 @@ def _allreduce_cuda(x, out, scale):
             nvops.allreduce_oneshot(heap, flat, oflat, st.stage, n, dt, scale,
                                     CH_USER[0])
         return out
-    ws = st.ws.tensor(dt)
+    use_mc = st.ws_mc is not None and n * es >= st.nvls_min_bytes
+    ws = (st.ws_mc if use_mc else st.ws).tensor(dt)
     q = W * _vn(dt)
-    chunk = (ws.numel() // q) * q
+    chunk = (min(ws.numel(), st.ws_bytes // es) // q) * q
     for s in range(0, n, chunk):
         m = min(chunk, n - s)
         mp = (m + q - 1) // q * q
         ws[:m].copy_(flat[s:s + m])
         if mp != m:
             ws[m:mp].zero_()
-        nvops.allreduce_twoshot(heap, st.ws.c_ptrs(), mp, dt, scale, CH_USER,
-                                max_blocks=st.fabric.max_blocks)
+        if use_mc:
+            st.ws_mc.allreduce_(mp, dt, scale, CH_USER, max_blocks=64)
+        else:
+            nvops.allreduce_twoshot(heap, st.ws.c_ptrs(), mp, dt, scale, CH_USER,
+                                    max_blocks=st.fabric.max_blocks)
         oflat[s:s + m].copy_(ws[:m])
     return out
 

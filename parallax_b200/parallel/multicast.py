@@ -98,7 +98,14 @@ class MulticastBuffer(object):
         if not all(o for o, _ in oks):
             raise MulticastError("multicast setup failed: %s" % [e for o, e in oks if not o])
         mc = _vp()
-        _ck(L.px_mc_bind_map(seg, ctypes.byref(mc)), "bind_map")
+        ok, err = True, ""
+        try:
+            _ck(L.px_mc_bind_map(seg, ctypes.byref(mc)), "bind_map")
+        except MulticastError as e:
+            ok, err = False, str(e)
+        oks = comm.all_gather_object((ok, err))
+        if not all(o for o, _ in oks):
+            raise MulticastError("multicast bind/map failed: %s" % [e for o, e in oks if not o])
         self.mc_ptr = mc.value
         torch.cuda.synchronize(self.device)
         comm.barrier()

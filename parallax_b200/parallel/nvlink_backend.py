@@ -147,6 +147,8 @@ class NVDenseGroup(object):
                     b.param_buf = multicast.MulticastBuffer(self.fabric, b.n * es)
                     b.mc = True
                 except multicast.MulticastError as e:
+                    # MulticastBuffer agrees on success/failure across ranks, so
+                    # every rank takes this branch together
                     parallax_log.warning("NVLS unavailable (%s); using P2P kernels", e)
                     self.nvls = False
             if not b.mc:
