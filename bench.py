@@ -181,7 +181,7 @@ def build_ncf(args, parallax, torch):
         return {"users": torch.randint(0, users, (batch,), generator=gen),
                 "items": torch.randint(0, items, (batch,), generator=gen),
                 "labels": torch.randint(0, 2, (batch,), generator=gen)}
-    desc = {"model": "neumf(users=%d,items=%d,dim=64+128)" % (users, items),
+    desc = {"model": "neumf(users=%d,items=%d,row=32+32 fp32)" % (users, items),
             "per_gpu_batch": batch, "seq_len": 1, "optimizer": "adam(1e-3, lazy sparse)",
             "items_per_step": batch}
     return graph, make_batch, desc, "ncf_samples_per_sec", "samples/s", None

@@ -15,8 +15,8 @@ from ..partitions import get_partitioner
 
 
 class NeuMF(nn.Module):
-    def __init__(self, num_users=100_000_000, num_items=1_000_000, mf_dim=64,
-                 mlp_layers=(256, 128, 64), num_partitions=8, lazy=True):
+    def __init__(self, num_users=100_000_000, num_items=1_000_000, mf_dim=32,
+                 mlp_layers=(64, 32, 16), num_partitions=8, lazy=True):
         super().__init__()
         part = get_partitioner(num_partitions)
         d_mlp = mlp_layers[0] // 2

@@ -43,14 +43,19 @@ hp = torch.tensor(optim.Adagrad(0.2, 1.0).hyper(1), device=dev)
 for _ in range(REP):
     nvops.dense_step(f.heap, gb.c_ptrs(), pb.c_ptrs(), master, acc, None, ema, None, hp,
                      None, None, n, 1.0, 0.999, "adagrad", 0, torch.bfloat16, CH_COMM)
-# ---- two-shot all-reduce + fused RS/opt/AG with a 2-rank world simulated on this GPU
-fabs2 = make_world(2, options={"comm_blocks": 32})
+# ---- two-shot all-reduce with a 2-rank world simulated on this GPU.  ncu serialises
+# kernels, so spinning peer kernels cannot be profiled: only with --with-allreduce
+# (plain run, no ncu) is this section executed.
+if "--with-allreduce" not in sys.argv:
+    fabs2 = []
+else:
+  fabs2 = make_world(2, options={"comm_blocks": 32})
 n2 = 8 << 20
 bufs = [ff.heap.alloc(n2 * 2, "x") for ff in fabs2]
 for b in bufs:
     b.tensor(torch.bfloat16, n2).normal_()
 torch.cuda.synchronize()
-for _ in range(REP):
+for _ in range(REP if fabs2 else 0):
     for r, ff in enumerate(fabs2):
         nvops.allreduce_twoshot(ff.heap, bufs[r].c_ptrs(), n2, torch.bfloat16, 0.5, CH_COMM,
                                 max_blocks=32, stream=ff.comm_stream)
