@@ -616,7 +616,9 @@ int px_sparse_push(const void* pend_grads, int grad_dtype, int n, const int32_t*
     px_sparse_scatter_kernel<__nv_bfloat16, false><<<blocks, 256, 0, stream>>>(
         (const __nv_bfloat16*)pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging,
         (const SparseCtl*)ctl, d, (uint32_t* const*)hdrs_dev, G, scale, lpr);
-  px_sparse_flush_kernel<false><<<blocks, 256, 0, stream>>>(
+  // only ids carried by several positions are staged: a small grid suffices
+  const int fblocks = blocks > 96 ? 96 : blocks;
+  px_sparse_flush_kernel<false><<<fblocks, 256, 0, stream>>>(
       uniq_id, uniq_k, uniq_cnt, staging, (SparseCtl*)ctl, d, (uint32_t* const*)hdrs_dev, G,
       scale, lpr);
   return (int)cudaGetLastError();
@@ -664,7 +666,8 @@ int px_sparse_async_apply(const void* pend_grads, int grad_dtype, int n, const i
     px_sparse_scatter_kernel<__nv_bfloat16, true><<<blocks, 256, 0, stream>>>(
         (const __nv_bfloat16*)pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging,
         (const SparseCtl*)ctl, d, nullptr, G, scale, lpr);
-  px_sparse_flush_kernel<true><<<blocks, 256, 0, stream>>>(
+  const int fblocks = blocks > 96 ? 96 : blocks;
+  px_sparse_flush_kernel<true><<<fblocks, 256, 0, stream>>>(
       uniq_id, uniq_k, uniq_cnt, staging, (SparseCtl*)ctl, d, nullptr, G, scale, lpr);
   return (int)cudaGetLastError();
 }

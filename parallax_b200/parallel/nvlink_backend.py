@@ -39,6 +39,8 @@ class NVFabric(object):
         # double-buffered staging for the one-shot all-reduce (norms, scalars)
         self.small_stage = self.heap.alloc(2 * 65536, "oneshot_stage")
         self.max_blocks = int(self.options.get("comm_blocks", 32))
+        if isinstance(ex, IpcExchange):
+            self.heap.pads_dev()        # eager: no lazy H2D inside a step
         if comm.distributed:
             comm.barrier()
 

@@ -31,4 +31,12 @@ def make_world(world, device="cuda:0", options=None):
         opts = {"comm_blocks": 4}
         opts.update(options or {})
         fabrics.append(NVFabric(comm, exchange=lw.exchange_for(r), options=opts))
+    # Upload every rank's pad-pointer table NOW: a lazy (blocking) H2D copy issued
+    # for rank k while rank 0's barrier kernel is already spinning on the same GPU
+    # can stall behind it.  Nothing host-blocking may happen between the launches
+    # of the simulated ranks.
+    import torch
+    for f in fabrics:
+        f.heap.pads_dev()
+    torch.cuda.synchronize()
     return fabrics
