@@ -686,6 +686,15 @@ class NVSparseTable(object):
             self._finish_step_impl(step, stream)
 
     def _finish_step_impl(self, step, stream=None):
+        self.stage_push(step, stream)
+        if self.route.sync:
+            self.stage_apply(step, stream)
+
+    def stage_push(self, step, stream=None):
+        """Sender side: local aggregation + push (or remote apply in async
+        mode).  Separate from `stage_apply` so that a world simulated on one GPU
+        can enqueue every rank's push before any rank's (spinning) owner kernels —
+        streams of one process may share a hardware queue."""
         cs = stream if stream is not None else self.fabric.comm_stream
         calls, self.calls = self.calls, []
         if calls:
@@ -696,6 +705,7 @@ class NVSparseTable(object):
             grads = torch.empty((0, self.Dp), dtype=torch.float32, device=self.device)
         n = int(pend_ids.numel())
         self._ensure_capacity(max(n, 1))
+        self._last_n = n
         self.stats["pushed_rows"] += n
         self.stats["steps"] += 1
         cur = torch.cuda.current_stream(self.device)
@@ -708,8 +718,6 @@ class NVSparseTable(object):
                            self.ctl, self.geom, self.local_aggregation,
                            self.use_smem, stream=cs)
         s0d, s1d = self._sdev(0), self._sdev(1)
-        # 8 warps per CTA, one row per warp; bounded by the configured cap
-        blk_own = max(1, min(self.max_blocks, (n * self.world + 7) // 8))
         if not self.route.sync:
             nvops.sparse_async_apply(grads, n, self.pos2u, self.uniq_id, self.uniq_k,
                                      self.uniq_cnt, self.staging, self.ctl,
@@ -720,6 +728,13 @@ class NVSparseTable(object):
                           self.uniq_cnt, self.staging, self.ctl, self.rings_dev,
                           self.hdrs_dev, self.ring_ids_off, self.cap, self.geom,
                           self.scale, self.rank, self.max_blocks, stream=cs)
+
+    def stage_apply(self, step, stream=None):
+        """Owner side: merge rows from all sources, apply the sparse optimizer."""
+        cs = stream if stream is not None else self.fabric.comm_stream
+        n = getattr(self, "_last_n", 1)
+        # 8 warps per CTA, one row per warp; bounded by the configured cap
+        blk_own = max(1, min(self.max_blocks, (n * self.world + 7) // 8))
         need_claim = self.world > 1 or not self.local_aggregation
         if need_claim:
             nvops.sparse_claim(self.ring_buf.local_ptr, self.hdr_buf.local_ptr,

@@ -190,17 +190,22 @@ def test_dense_step_two_phase_clip():
     hp = torch.tensor(hp_list, device="cuda")
     max_norm = 10.0
     torch.cuda.synchronize()
+    # phase-interleaved launches: the simulated ranks' streams share one process
+    # (and possibly one hardware queue), so no rank may enqueue a later phase in
+    # front of a peer's earlier one
     for r, f in enumerate(fabs):
-        cs = f.comm_stream
         nvops.dense_step(f.heap, gb[r].c_ptrs(), pb[r].c_ptrs(), master[r], acc[r],
                          None, None, red[r], hp, None, loc[r], n, 1.0 / world, 0.0,
-                         "adagrad", 1, dtype, CH_COMM, max_blocks=4, stream=cs)
+                         "adagrad", 1, dtype, CH_COMM, max_blocks=4, stream=f.comm_stream)
+    for r, f in enumerate(fabs):
         nvops.allreduce_oneshot(f.heap, loc[r], tot[r], f.small_stage, 4,
-                                torch.float32, 1.0, CH_SMALL, stream=cs)
-        nvops.clip_scale(tot[r], max_norm, scale[r], norm[r], loc[r], stream=cs)
+                                torch.float32, 1.0, CH_SMALL, stream=f.comm_stream)
+    for r, f in enumerate(fabs):
+        nvops.clip_scale(tot[r], max_norm, scale[r], norm[r], loc[r], stream=f.comm_stream)
         nvops.dense_step(f.heap, gb[r].c_ptrs(), pb[r].c_ptrs(), master[r], acc[r],
                          None, None, red[r], hp, scale[r], None, n, 1.0 / world,
-                         0.0, "adagrad", 2, dtype, CH_COMM, max_blocks=4, stream=cs)
+                         0.0, "adagrad", 2, dtype, CH_COMM, max_blocks=4,
+                         stream=f.comm_stream)
     torch.cuda.synchronize()
     gmean = torch.stack(grads).sum(0) / world
     gn = float(gmean.norm())

@@ -31,6 +31,17 @@ def _tables(world, V, D, P, opt, run_option="HYBRID", sync=True, average=False,
     return fabs, tabs, W0
 
 
+def _finish_all(tabs, step):
+    """Every simulated rank's sender stage is enqueued before any rank's owner
+    stage: the ranks' streams live in one process and may share a hardware
+    queue, so a spinning owner kernel must never sit in front of a peer's push."""
+    for t in tabs:
+        t.stage_push(step)
+    for t in tabs:
+        t.stage_apply(step)
+    torch.cuda.synchronize()
+
+
 def _full(tabs, V, D):
     out = torch.zeros(V, D)
     L = tabs[0].layout
@@ -100,9 +111,7 @@ def test_push_claim_apply(world, run_option, kind, local_agg):
             t.add_pending(toks[r], all_g[r].cuda())
             t.begin_step(step)
         torch.cuda.synchronize()
-        for r, t in enumerate(tabs):
-            t.finish_step(step)
-        torch.cuda.synchronize()
+        _finish_all(tabs, step)
         ids_c, g_c = torch.cat(all_ids), torch.cat(all_g)
         u, inv = torch.unique(ids_c, return_inverse=True)
         gsum = torch.zeros(u.numel(), D).index_add_(0, inv, g_c)
@@ -144,9 +153,7 @@ def test_large_n_uses_global_hash_and_bf16_grads():
         t.add_pending(toks[r], all_g[r].cuda())
         t.begin_step(1)
     torch.cuda.synchronize()
-    for t in tabs:
-        t.finish_step(1)
-    torch.cuda.synchronize()
+    _finish_all(tabs, 1)
     ids_c, g_c = torch.cat(all_ids), torch.cat(all_g).float()
     u, inv = torch.unique(ids_c, return_inverse=True)
     gsum = torch.zeros(u.numel(), D).index_add_(0, inv, g_c)
