@@ -24,6 +24,13 @@ from .resource import (is_local_host, serialize_resource_info, worker_layout,
                        get_empty_port)
 
 
+def remote_copy(remote_machine, local_path, remote_path, port=22):
+    """scp a file to `remote_machine` (reference `common/lib.py:70-76`)."""
+    cmd = ["scp", "-P", str(port), local_path, "%s:%s" % (remote_machine, remote_path)]
+    parallax_log.warning("\033[91m%s\033[0m", " ".join(cmd))
+    return subprocess.call(cmd)
+
+
 def remote_exec(bash_script, remote_machine, stdout=None, stderr=None,
                 env=None, python_venv=None, port=22):
     """Run `bash_script` on `remote_machine` over ssh with `env` exported."""

@@ -58,11 +58,13 @@ def log_uniform_sample_unique(num_sampled, range_max, device, oversample=3):
     occurrence of each value, take the first `num_sampled` of those."""
     M = int(oversample * num_sampled)
     d = log_uniform_sample(M, range_max, device)
-    vals, order = torch.sort(d, stable=True)
-    first_sorted = torch.ones(M, dtype=torch.bool, device=device)
-    first_sorted[1:] = vals[1:] != vals[:-1]
-    first = torch.zeros(M, dtype=torch.bool, device=device)
-    first[order] = first_sorted
+    # first occurrence of each value = the draw whose position is the minimum over
+    # all draws of that value: one scatter-min into a [range_max] table (3 small
+    # kernels) instead of a 64-bit radix sort of the candidates
+    pos = torch.arange(M, device=device, dtype=torch.int32)
+    first_pos = torch.full((range_max,), M, dtype=torch.int32, device=device)
+    first_pos.scatter_reduce_(0, d, pos, reduce="amin", include_self=True)
+    first = first_pos[d] == pos
     cum = torch.cumsum(first.to(torch.int32), 0)
     sel = first & (cum <= num_sampled)
     slot = torch.where(sel, cum - 1, torch.full_like(cum, num_sampled)).to(torch.int64)

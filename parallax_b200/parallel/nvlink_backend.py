@@ -512,6 +512,12 @@ class NVSparseTable(object):
         ps = config.communication_config.ps_config
         self.local_aggregation = bool(ps.local_aggregation)
         self.scale = graph.scale_for(name)
+        # PSConfig.boundary_between_workers_and_servers: where gradient
+        # post-processing (the ScaleGradients factor) runs — on the sender inside
+        # the push kernel (True, the reference moves such ops to the side that
+        # shrinks/keeps the wire traffic, graph_transform_lib.py:1315-1370) or on
+        # the owner inside the apply kernel (False).
+        self.scale_on_sender = bool(ps.boundary_between_workers_and_servers)
         opts = options or {}
         self.out_dtype = out_dtype or torch.float32
         self.anchor_device = self.device
@@ -727,7 +733,8 @@ class NVSparseTable(object):
         nvops.sparse_push(grads, n, self.pos2u, self.uniq_id, self.uniq_k,
                           self.uniq_cnt, self.staging, self.ctl, self.rings_dev,
                           self.hdrs_dev, self.ring_ids_off, self.cap, self.geom,
-                          self.scale, self.rank, self.max_blocks, stream=cs)
+                          self.scale if self.scale_on_sender else 1.0, self.rank,
+                          self.max_blocks, stream=cs)
 
     def stage_apply(self, step, stream=None):
         """Owner side: merge rows from all sources, apply the sparse optimizer."""
@@ -741,6 +748,8 @@ class NVSparseTable(object):
                                self.ring_ids_off, self.cap, self.slotmap, self.ctl,
                                self.geom, blk_own, stream=cs)
         avg = (1.0 / self.world) if self.average else 1.0
+        if not self.scale_on_sender:
+            avg *= self.scale
         nvops.sparse_apply(self.ring_buf.local_ptr, self.hdr_buf.local_ptr,
                            self.ring_ids_off, self.cap, self.slotmap, self.table,
                            self.slots[0] if self.nslots > 0 else None,
