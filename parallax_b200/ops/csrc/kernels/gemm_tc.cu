@@ -259,6 +259,156 @@ px_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]),
+                 "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_(float x) {
+  const float e = __expf(-2.f * fabsf(x));
+  return copysignf((1.f - e) / (1.f + e), x);
+}
+
+// ---------------------------------------------------------------------------
+// Recurrent LSTM step with the whole cell fused into the GEMM epilogue:
+//   gates = xw_t + h_{t-1} · Wh          (tcgen05, accumulator in TMEM)
+//   c_t = σ(f+fb)·c_{t-1} + σ(i)·tanh(j);  m_t = σ(o)·tanh(c_t)
+// The 4S gate columns are stored GATE-INTERLEAVED: tile n (128 columns) holds
+// [i | j | f | o] × 32 hidden units (n·32 … n·32+31), so one CTA owns every
+// gate of its 32 units and the cell update never leaves the SM.  Each epilogue
+// thread owns one batch row of the TMEM tile.  Replaces cuBLAS addmm + the
+// stand-alone cell kernel (and the [B,4S] pre-activation round trip).
+struct LstmArgs {
+  const __nv_bfloat16* xw;   // [M, 4S] permuted layout (input half + bias)
+  const float* c_prev;       // [M, S]
+  float* c_new;              // [M, S]
+  __nv_bfloat16* m_out;      // [M, S]
+  __nv_bfloat16* act;        // [M, 4S] permuted layout: σ(i) | tanh(j) | σ(f+fb) | σ(o)
+  int M, S, K;
+  float forget_bias;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(256, 1)
+px_lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                        const __grid_constant__ CUtensorMap tmap_b, LstmArgs g) {
+  constexpr int BN = 128;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+  const int num_kb = g.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::
+                 "r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* sa = smem + s * STAGE_BYTES;
+      mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+      tma_load_2d(sa, &tmap_a, &full_bar[s], kb * BK, m_tile * BM);
+      tma_load_2d(sa + A_BYTES, &tmap_b, &full_bar[s], kb * BK, n_tile * BN);
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tcgen05_fence_after();
+      const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+      const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+      for (int k = 0; k < BK / UMMA_K; ++k)
+        umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                  (kb | k) != 0 ? 1u : 0u);
+      umma_commit(&empty_bar[s]);
+    }
+    umma_commit(tmem_full);
+  } else if (warp >= 4) {
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    const int wq = warp - 4;
+    const int row = m_tile * BM + wq * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const size_t gcol0 = (size_t)row * 4 * g.S + (size_t)n_tile * BN;   // permuted column base
+    const size_t ccol0 = (size_t)row * g.S + (size_t)n_tile * 32;       // hidden-unit base
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {                                       // 8 hidden units per pass
+      uint32_t ri[8], rj[8], rf[8], ro[8];
+      tmem_ld8(trow + 0 * 32 + q * 8, ri);
+      tmem_ld8(trow + 1 * 32 + q * 8, rj);
+      tmem_ld8(trow + 2 * 32 + q * 8, rf);
+      tmem_ld8(trow + 3 * 32 + q * 8, ro);
+      tmem_ld_wait();
+      if (row < g.M) {
+        float xi[8], xj[8], xf[8], xo[8], cp[8];
+        Vec16<__nv_bfloat16>::unpack(ld_v4(g.xw + gcol0 + 0 * 32 + q * 8), xi);
+        Vec16<__nv_bfloat16>::unpack(ld_v4(g.xw + gcol0 + 1 * 32 + q * 8), xj);
+        Vec16<__nv_bfloat16>::unpack(ld_v4(g.xw + gcol0 + 2 * 32 + q * 8), xf);
+        Vec16<__nv_bfloat16>::unpack(ld_v4(g.xw + gcol0 + 3 * 32 + q * 8), xo);
+        Vec16<float>::unpack(ld_v4(g.c_prev + ccol0 + q * 8), cp);
+        Vec16<float>::unpack(ld_v4(g.c_prev + ccol0 + q * 8 + 4), cp + 4);
+        float si[8], tj[8], sf[8], so[8], cn[8], mo[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          // the reference keeps pre-activations in bf16 between the GEMM and the
+          // non-linearities; here they stay fp32 (TMEM accumulator + bf16 addend)
+          si[u] = sigm(__uint_as_float(ri[u]) + xi[u]);
+          tj[u] = tanh_(__uint_as_float(rj[u]) + xj[u]);
+          sf[u] = sigm(__uint_as_float(rf[u]) + xf[u] + g.forget_bias);
+          so[u] = sigm(__uint_as_float(ro[u]) + xo[u]);
+          cn[u] = sf[u] * cp[u] + si[u] * tj[u];
+          mo[u] = so[u] * tanh_(cn[u]);
+        }
+        st_v4(g.c_new + ccol0 + q * 8, Vec16<float>::pack(cn));
+        st_v4(g.c_new + ccol0 + q * 8 + 4, Vec16<float>::pack(cn + 4));
+        st_v4(g.m_out + ccol0 + q * 8, Vec16<__nv_bfloat16>::pack(mo));
+        st_v4(g.act + gcol0 + 0 * 32 + q * 8, Vec16<__nv_bfloat16>::pack(si));
+        st_v4(g.act + gcol0 + 1 * 32 + q * 8, Vec16<__nv_bfloat16>::pack(tj));
+        st_v4(g.act + gcol0 + 2 * 32 + q * 8, Vec16<__nv_bfloat16>::pack(sf));
+        st_v4(g.act + gcol0 + 3 * 32 + q * 8, Vec16<__nv_bfloat16>::pack(so));
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)BN) : "memory");
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -333,6 +483,35 @@ int px_gemm_tc(const void* A, const void* B, void* C, const void* addend, float*
     }
     px_gemm_tc_kernel<64, STAGES><<<grid, 256, SMEM, stream>>>(ta, tb, g);
   }
+  return (int)cudaGetLastError();
+}
+
+// Fused recurrent LSTM step (see px_lstm_gates_tc_kernel).  h: [M,K] bf16;
+// WhP: [4S, K] bf16 gate-interleaved rows; xw/act: [M,4S] gate-interleaved.
+int px_lstm_gates_tc(const void* h, const void* WhP, const void* xw, const float* c_prev,
+                     float* c_new, void* m_out, void* act, int M, int S, int K,
+                     float forget_bias, cudaStream_t stream) {
+  using namespace tc;
+  if (M % BM || K % BK || S % 32) return -1;
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, h, M, K, BM);
+  if (rc) return rc;
+  rc = make_tmap(&tb, WhP, 4 * (uint64_t)S, K, 128);
+  if (rc) return rc;
+  LstmArgs g;
+  g.xw = (const __nv_bfloat16*)xw; g.c_prev = c_prev; g.c_new = c_new;
+  g.m_out = (__nv_bfloat16*)m_out; g.act = (__nv_bfloat16*)act;
+  g.M = M; g.S = S; g.K = K; g.forget_bias = forget_bias;
+  constexpr int STAGES = 4;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + 128 * BK * 2) + 1024 + 256;
+  static bool set = false;
+  if (!set) {
+    cudaFuncSetAttribute(px_lstm_gates_tc_kernel<STAGES>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    set = true;
+  }
+  dim3 grid(4 * S / 128, M / BM, 1);
+  px_lstm_gates_tc_kernel<STAGES><<<grid, 256, SMEM, stream>>>(ta, tb, g);
   return (int)cudaGetLastError();
 }
 

@@ -22,7 +22,8 @@ from . import lib as _lib, check as _check, register_signatures
 _vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 register_signatures({
     "px_lstm_cell_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
-    "px_lstm_cell_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "px_lstm_cell_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "px_lstm_gates_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "px_sampled_softmax": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
 })
 _DT = {torch.float32: 0, torch.bfloat16: 1}
@@ -60,6 +61,25 @@ def lstm_layer_reference(x, Wx, Wh, bias, W_P, c0, h0, forget_bias=1.0):
     return torch.stack(outs), c, h
 
 
+_perm_cache = {}
+
+
+def gate_interleave_perm(S, device):
+    """perm[n'] = n : column n' = tile·128 + g·32 + j of the gate-interleaved
+    layout holds original column n = g·S + tile·32 + j (g: i, j, f, o)."""
+    key = (S, str(device))
+    if key not in _perm_cache:
+        tiles = S // 32
+        g = torch.arange(4, device=device).view(1, 4, 1)
+        t = torch.arange(tiles, device=device).view(tiles, 1, 1)
+        j = torch.arange(32, device=device).view(1, 1, 32)
+        perm = (g * S + t * 32 + j).reshape(-1)
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(4 * S, device=device)
+        _perm_cache[key] = (perm, inv)
+    return _perm_cache[key]
+
+
 class _LSTMLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, Wx, Wh, bias, W_P, c0, h0, forget_bias):
@@ -69,31 +89,51 @@ class _LSTMLayerFn(torch.autograd.Function):
         dt = x.dtype
         dev = x.device
         x = x.contiguous()
-        xw = torch.addmm(bias, x.view(T * Bsz, E), Wx).view(T, Bsz, 4 * S)
+        # tcgen05 path: recurrent GEMM with the LSTM cell fused into its epilogue
+        # (gate-interleaved column layout, see gemm_tc.cu)
+        tc = (dt == torch.bfloat16 and Bsz % 128 == 0 and P % 64 == 0 and S % 32 == 0)
+        if tc:
+            perm, inv = gate_interleave_perm(S, dev)
+            Wx_l = Wx.index_select(1, perm)
+            Wh_l = Wh.index_select(1, perm)                 # [P, 4S]  (K-contiguous for bwd)
+            WhT = Wh_l.t().contiguous()                     # [4S, P]  (K-contiguous for fwd)
+            bias_l = bias.index_select(0, perm)
+        else:
+            Wx_l, Wh_l, bias_l, WhT = Wx, Wh, bias, None
+        xw = torch.addmm(bias_l, x.view(T * Bsz, E), Wx_l).view(T, Bsz, 4 * S)
         act = torch.empty(T, Bsz, 4 * S, dtype=dt, device=dev)
         c_all = torch.empty(T + 1, Bsz, S, dtype=torch.float32, device=dev)
         m_all = torch.empty(T, Bsz, S, dtype=dt, device=dev)
         h_all = torch.empty(T + 1, Bsz, P, dtype=dt, device=dev)
         c_all[0].copy_(c0)
         h_all[0].copy_(h0)
-        gpre = torch.empty(Bsz, 4 * S, dtype=dt, device=dev)
         st = _stream()
-        for t in range(T):
-            torch.addmm(xw[t], h_all[t], Wh, out=gpre)
-            _check(L.px_lstm_cell_fwd(_p(gpre), _p(c_all[t]), _p(act[t]), _p(c_all[t + 1]),
-                                      _p(m_all[t]), Bsz, S, float(forget_bias), _DT[dt], st),
-                   "lstm_cell_fwd")
-            torch.mm(m_all[t], W_P, out=h_all[t + 1])
+        if tc:
+            for t in range(T):
+                _check(L.px_lstm_gates_tc(_p(h_all[t]), _p(WhT), _p(xw[t]), _p(c_all[t]),
+                                          _p(c_all[t + 1]), _p(m_all[t]), _p(act[t]), Bsz, S, P,
+                                          float(forget_bias), st), "lstm_gates_tc")
+                torch.mm(m_all[t], W_P, out=h_all[t + 1])
+        else:
+            gpre = torch.empty(Bsz, 4 * S, dtype=dt, device=dev)
+            for t in range(T):
+                torch.addmm(xw[t], h_all[t], Wh, out=gpre)
+                _check(L.px_lstm_cell_fwd(_p(gpre), _p(c_all[t]), _p(act[t]),
+                                          _p(c_all[t + 1]), _p(m_all[t]), Bsz, S,
+                                          float(forget_bias), _DT[dt], st), "lstm_cell_fwd")
+                torch.mm(m_all[t], W_P, out=h_all[t + 1])
         _count(T)
-        ctx.save_for_backward(x, Wx, Wh, W_P, act, c_all, m_all, h_all)
+        ctx.save_for_backward(x, Wx_l, Wh_l, W_P, act, c_all, m_all, h_all)
         ctx.dims = (T, Bsz, E, S, P)
+        ctx.tc = tc
         return h_all[1:], c_all[T].clone(), h_all[T].clone()
 
     @staticmethod
     def backward(ctx, dH, dcT, dhT):
         L = _lib()
-        x, Wx, Wh, W_P, act, c_all, m_all, h_all = ctx.saved_tensors
+        x, Wx, Wh, W_P, act, c_all, m_all, h_all = ctx.saved_tensors   # Wx/Wh: layout of `act`
         T, Bsz, E, S, P = ctx.dims
+        tc = ctx.tc
         dt, dev = x.dtype, x.device
         dH = dH.contiguous()
         dgates = torch.empty(T, Bsz, 4 * S, dtype=dt, device=dev)
@@ -119,8 +159,8 @@ class _LSTMLayerFn(torch.autograd.Function):
         for t in range(T - 1, -1, -1):
             torch.mm(dh_tot[t], WPT, out=dm)
             _check(L.px_lstm_cell_bwd(_p(dm), _p(dc), _p(act[t]), _p(c_all[t]),
-                                      _p(c_all[t + 1]), _p(dgates[t]), Bsz, S, _DT[dt], st),
-                   "lstm_cell_bwd")
+                                      _p(c_all[t + 1]), _p(dgates[t]), Bsz, S, _DT[dt],
+                                      1 if tc else 0, st), "lstm_cell_bwd")
             if t > 0:
                 if use_tc:
                     _gemm.gemm_tn(dgates[t], Wh, addend=dH[t - 1], splits=16, bn=64,
@@ -137,6 +177,10 @@ class _LSTMLayerFn(torch.autograd.Function):
         dbias = dg2.sum(0)
         dW_P = m_all.view(T * Bsz, S).t() @ dh_tot.view(T * Bsz, P)
         dx = (dg2 @ Wx.t()).view(T, Bsz, E)
+        if tc:          # back to the caller's (plain) gate-column order
+            _, inv = gate_interleave_perm(S, dev)
+            dWh, dWx, dbias = dWh.index_select(1, inv), dWx.index_select(1, inv), \
+                dbias.index_select(0, inv)
         return dx, dWx, dWh, dbias, dW_P, dc, dh_rec, None
 
 
