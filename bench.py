@@ -301,7 +301,11 @@ def main():
         if world > 1:
             dist.all_reduce(tb, op=dist.ReduceOp.MAX)
         comm_bd = {k: round(float(v), 4) for k, v in zip(sorted(comm_bd), tb)}
-        comm_bd["note"] = "eager (ungraphed) steps; max over ranks"
+        comm_bd["note"] = ("eager (ungraphed) steps, max over ranks; at N>1 eager steps are "
+                           "CPU-launch-bound and the 'exposed' figures are dominated by "
+                           "cross-rank launch skew absorbed in the kernels' start barriers, "
+                           "not by data movement — compare ms_per_step across N for the "
+                           "graph-replayed cost of communication")
     except Exception as e:  # pragma: no cover
         comm_bd = {"error": str(e)}
 

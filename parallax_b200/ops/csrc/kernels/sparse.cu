@@ -514,15 +514,6 @@ px_sparse_apply_kernel(char* ring, uint32_t* hdr, size_t ring_ids_off, int cap, 
   if (threadIdx.x == 0) { ctl->step = step; ctl->apply_done = 0; }
 }
 
-// copy + scale + (optional) cast of a lookup's grad_output into the pending buffer
-template <typename SrcT, typename DstT>
-__global__ void px_rows_copy_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst,
-                                    size_t n_elems, float scale) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems;
-       i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = (DstT)((float)src[i] * scale);
-}
-
 // ---------------------------------------------------------------------------
 extern "C" {
 
