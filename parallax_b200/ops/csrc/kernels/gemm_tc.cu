@@ -357,14 +357,27 @@ px_lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     umma_commit(tmem_full);
   } else if (warp >= 4) {
-    mbar_wait(tmem_full, 0);
-    tcgen05_fence_after();
     const int wq = warp - 4;
     const int row = m_tile * BM + wq * 32 + lane;
-    const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16);
     const size_t gcol0 = (size_t)row * 4 * g.S + (size_t)n_tile * BN;   // permuted column base
     const size_t ccol0 = (size_t)row * g.S + (size_t)n_tile * 32;       // hidden-unit base
-#pragma unroll 1
+    // The addend (xw) and c_{t-1} do not depend on the MMA: fetch this row's
+    // 128 + 32 values while TMA/UMMA are still filling the accumulator.
+    uint4 xv[4][4];      // [q][gate]
+    uint4 cv[4][2];
+    if (row < g.M) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) xv[q][gi] = ld_v4(g.xw + gcol0 + gi * 32 + q * 8);
+        cv[q][0] = ld_v4(g.c_prev + ccol0 + q * 8);
+        cv[q][1] = ld_v4(g.c_prev + ccol0 + q * 8 + 4);
+      }
+    }
+    mbar_wait(tmem_full, 0);
+    tcgen05_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16);
+#pragma unroll
     for (int q = 0; q < 4; ++q) {                                       // 8 hidden units per pass
       uint32_t ri[8], rj[8], rf[8], ro[8];
       tmem_ld8(trow + 0 * 32 + q * 8, ri);
@@ -374,17 +387,16 @@ px_lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tmem_ld_wait();
       if (row < g.M) {
         float xi[8], xj[8], xf[8], xo[8], cp[8];
-        Vec16<__nv_bfloat16>::unpack(ld_v4(g.xw + gcol0 + 0 * 32 + q * 8), xi);
-        Vec16<__nv_bfloat16>::unpack(ld_v4(g.xw + gcol0 + 1 * 32 + q * 8), xj);
-        Vec16<__nv_bfloat16>::unpack(ld_v4(g.xw + gcol0 + 2 * 32 + q * 8), xf);
-        Vec16<__nv_bfloat16>::unpack(ld_v4(g.xw + gcol0 + 3 * 32 + q * 8), xo);
-        Vec16<float>::unpack(ld_v4(g.c_prev + ccol0 + q * 8), cp);
-        Vec16<float>::unpack(ld_v4(g.c_prev + ccol0 + q * 8 + 4), cp + 4);
+        Vec16<__nv_bfloat16>::unpack(xv[q][0], xi);
+        Vec16<__nv_bfloat16>::unpack(xv[q][1], xj);
+        Vec16<__nv_bfloat16>::unpack(xv[q][2], xf);
+        Vec16<__nv_bfloat16>::unpack(xv[q][3], xo);
+        Vec16<float>::unpack(cv[q][0], cp);
+        Vec16<float>::unpack(cv[q][1], cp + 4);
         float si[8], tj[8], sf[8], so[8], cn[8], mo[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          // the reference keeps pre-activations in bf16 between the GEMM and the
-          // non-linearities; here they stay fp32 (TMEM accumulator + bf16 addend)
+          // pre-activations stay fp32 (TMEM accumulator + bf16 addend)
           si[u] = sigm(__uint_as_float(ri[u]) + xi[u]);
           tj[u] = tanh_(__uint_as_float(rj[u]) + xj[u]);
           sf[u] = sigm(__uint_as_float(rf[u]) + xf[u] + g.forget_bias);

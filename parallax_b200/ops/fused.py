@@ -64,6 +64,16 @@ def lstm_layer_reference(x, Wx, Wh, bias, W_P, c0, h0, forget_bias=1.0):
 _perm_cache = {}
 
 
+def _tc_forward_enabled():
+    """The fused tcgen05 forward step is opt-in (`PARALLAX_LSTM_TC_FWD=1`):
+    measured on B200 at the LM1B shape it is numerically equivalent but, with the
+    per-step weight re-layout it needs, slower than cuBLAS + the stand-alone cell
+    kernel (profiles/README.md); the tcgen05 split-K product on the backward path
+    is always on."""
+    import os
+    return os.environ.get("PARALLAX_LSTM_TC_FWD", "0") == "1"
+
+
 def gate_interleave_perm(S, device):
     """perm[n'] = n : column n' = tile·128 + g·32 + j of the gate-interleaved
     layout holds original column n = g·S + tile·32 + j (g: i, j, f, o)."""
@@ -91,7 +101,8 @@ class _LSTMLayerFn(torch.autograd.Function):
         x = x.contiguous()
         # tcgen05 path: recurrent GEMM with the LSTM cell fused into its epilogue
         # (gate-interleaved column layout, see gemm_tc.cu)
-        tc = (dt == torch.bfloat16 and Bsz % 128 == 0 and P % 64 == 0 and S % 32 == 0)
+        tc = (dt == torch.bfloat16 and Bsz % 128 == 0 and P % 64 == 0 and S % 32 == 0 and
+              _tc_forward_enabled())
         if tc:
             perm, inv = gate_interleave_perm(S, dev)
             Wx_l = Wx.index_select(1, perm)

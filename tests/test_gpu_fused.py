@@ -33,9 +33,13 @@ def test_lstm_layer_matches_reference(dtype, tol):
             (float((r - g).abs().max()), scale)
 
 
-def test_lstm_layer_bf16_tcgen05_backward_path():
+@pytest.mark.parametrize("tc_fwd", ["0", "1"])
+def test_lstm_layer_bf16_tcgen05_backward_path(tc_fwd, monkeypatch):
     """B=128, 4S multiple of 1024: the recurrent backward product runs on the
-    tcgen05 split-K kernel with the fused addend."""
+    tcgen05 split-K kernel with the fused addend; with PARALLAX_LSTM_TC_FWD=1 the
+    forward step runs on the tcgen05 kernel with the LSTM cell fused in its
+    epilogue (gate-interleaved layout)."""
+    monkeypatch.setenv("PARALLAX_LSTM_TC_FWD", tc_fwd)
     from parallax_b200.ops.fused import lstm_layer, lstm_layer_reference
     torch.manual_seed(0)
     T, B, E, S, P = 3, 128, 64, 256, 64
