@@ -402,6 +402,48 @@ class TrainEngine(object):
                 with torch.no_grad():
                     bufs[n].copy_(v)
 
+    # ---------------------------------------------------------- re-partition
+    def repartition(self, num_partitions, names=None):
+        """Re-shard sparse tables to `num_partitions` partitions IN PLACE
+        (collective).  The reference's search relaunches the whole job for every
+        candidate P (`common/partitions.py:74-138`); on one box the tables are
+        re-laid out between timing windows instead, keeping weights and optimizer
+        slots."""
+        names = sorted(self.tables) if names is None else names
+        for name in names:
+            old = self.tables[name]
+            if old.layout.P == num_partitions or old.layout.replicated:
+                continue
+            weight, slots = old.full_weight(), old.full_slots()
+            path = name[:-len(".weight")] if name.endswith(".weight") else name
+            holder = None
+            for p_, m_ in self.model.named_modules():
+                if isinstance(m_, ShardedEmbedding) and m_.table is old:
+                    holder, path = m_, p_
+            strategy = old.layout.strategy
+            if self.backend == "host":
+                from .host_backend import HostSparseTable
+                new = _HostTableAdapter(HostSparseTable(
+                    name, weight, num_partitions, strategy, self.graph.sparse_optimizer,
+                    self.comm, self.route, self.graph, self.config))
+            else:
+                from .nvlink_backend import NVSparseTable
+                opts = dict(self.config.sess_config) \
+                    if isinstance(self.config.sess_config, dict) else {}
+                out_dtype, cap = old.out_dtype, old.cap
+                old.release()
+                new = NVSparseTable(name, weight, num_partitions, strategy,
+                                    self.graph.sparse_optimizer, self.fabric, self.route,
+                                    self.graph, self.config, out_dtype=out_dtype, options=opts)
+                if cap:
+                    new.capacity_hint = cap
+            new.load_full(weight, slots)
+            self.tables[name] = new
+            if holder is not None:
+                holder.table = new
+        self._graph_state = None          # captured graphs hold the old tables
+        self.analysis.variables  # (report keeps the build-time partition counts)
+
     # ------------------------------------------------------------ reporting
     def export_report(self, path):
         rep = self.analysis.report()

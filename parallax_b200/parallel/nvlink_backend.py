@@ -780,6 +780,17 @@ class NVSparseTable(object):
         torch.cuda.synchronize(self.device)
         return [self._gather_full(s) for s in self.slots]
 
+    def release(self):
+        """Free this table's symmetric segments (collective)."""
+        torch.cuda.synchronize(self.device)
+        if self.comm.distributed:
+            self.comm.barrier()
+        for b in [self.tab_buf, self.hdr_buf, self.ring_buf] + list(self.slot_bufs):
+            if b is not None:
+                self.heap.free(b)
+        self.table = None
+        self.slots = []
+
     def load_full(self, weight, slots=None):
         g, l = self.layout.global_ids_of_owner(0 if self.replicated else self.rank)
         l = l.to(self.device)

@@ -173,6 +173,18 @@ class SymmetricHeap(object):
             ctypes.c_void_p(self.epoch.data_ptr()), channel, self.rank,
             self.world, 1, ctypes.c_void_p(s.cuda_stream)), "barrier")
 
+    def free(self, buf):
+        """Release one segment (collective: every rank frees the same segment)."""
+        if buf not in self.buffers:
+            return
+        self.buffers.remove(buf)
+        buf._bytes = None
+        if isinstance(self.ex, IpcExchange) and buf.peer_ptrs:
+            for r, p in enumerate(buf.peer_ptrs):
+                if r != self.rank and p:
+                    self.L.px_ipc_close(ctypes.c_void_p(p))
+        self.L.px_symm_free(ctypes.c_void_p(buf.local_ptr))
+
     def close(self):
         for b in self.buffers:
             b._bytes = None

@@ -235,3 +235,41 @@ def send_exec_time(address, exec_time):
 
 def searching():
     return os.environ.get(PARALLAX_SEARCH, "False") == "True"
+
+
+def search_inprocess(sess, next_feed, min_partitions=None, warmup=5, test=10, sync=None):
+    """Online partition search without relaunching the job: for each candidate P
+    the engine re-shards its sparse tables in place, runs `warmup + test` training
+    steps fed by ``next_feed()`` and times the last `test` (device-synchronised);
+    candidates follow the reference's doubling/halving walk and the optimum comes
+    from the same cost-model fit (`SearchState`).  Returns the chosen P, with the
+    tables left partitioned that way.  Collective: every worker must call it."""
+    import time as _time
+    import torch
+    eng = sess.engine
+    if not eng.tables:
+        return None
+    comm = eng.comm
+    cur = max(t.layout.P for t in eng.tables.values())
+    p0 = int(min_partitions or os.environ.get(PARALLAX_MIN_PARTITIONS, cur))
+    state = SearchState(max(p0, 1), p0)
+    keep = True
+    while keep:
+        p = state.p_to_test
+        eng.repartition(p)
+        for i in range(warmup + test):
+            if i == warmup:
+                if comm.is_cuda:
+                    torch.cuda.synchronize(comm.device)
+                comm.barrier()
+                t0 = _time.perf_counter()
+            sess.run(["loss", "train_op"], next_feed())
+        if comm.is_cuda:
+            torch.cuda.synchronize(comm.device)
+        dt = (_time.perf_counter() - t0) / test
+        dts = comm.all_gather_object(dt)
+        keep, nxt = state.report(float(np.mean(dts)))
+        parallax_log.info("partition search: P=%d  %.3f ms/step", p, 1e3 * float(np.mean(dts)))
+    eng.repartition(state.p_to_test)
+    parallax_log.info("optimal partitions: %d", state.p_to_test)
+    return state.p_to_test

@@ -182,3 +182,26 @@ def test_session_feed_fetch_contract():
     with pytest.raises(KeyError):
         sess.run("not_a_tensor", {"ids": [ids], "labels": [labels]})
     sess.close()
+
+
+def test_inprocess_repartition_preserves_state_and_search_runs():
+    from parallax_b200.partitions import search_inprocess
+    cfg = parallax.Config(sess_config={"fabric": "host"})
+    sess, _ = _train(cfg, 3)
+    eng = sess.engine
+    before = eng.state_dict()["sparse"]["emb.weight"]
+    eng.repartition(7)
+    assert eng.tables["emb.weight"].layout.P == 7
+    after = eng.state_dict()["sparse"]["emb.weight"]
+    torch.testing.assert_close(after["weight"], before["weight"])
+    torch.testing.assert_close(after["slots"][0], before["slots"][0])
+    gen = torch.Generator().manual_seed(3)
+
+    def feed():
+        return {"ids": [torch.randint(0, 64, (4, 3), generator=gen)],
+                "labels": [torch.randint(0, 4, (4,), generator=gen)]}
+    l0 = sess.run(["loss", "train_op"], feed())[0][0]
+    p = search_inprocess(sess, feed, min_partitions=2, warmup=1, test=2)
+    assert p >= 2 and eng.tables["emb.weight"].layout.P == p
+    assert np.isfinite(sess.run(["loss", "train_op"], feed())[0][0]) and np.isfinite(l0)
+    sess.close()

@@ -86,3 +86,29 @@ def test_engine_cuda_graph_matches_eager():
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def test_engine_repartition_in_place_nvlink():
+    """Online partition search support: tables are re-sharded in place on the
+    fabric, keeping weights and optimizer slots; training continues."""
+    model = MLPWithEmbedding(64, partitioner=parallax.get_partitioner(3))
+    graph = parallax.Graph(model, optimizer=optim.Adagrad(0.2, 1.0))
+    cfg = parallax.Config(sess_config={"fabric": "nvlink", "cuda_graph": True})
+    sess, *_ = parallax.parallel_run(graph, "localhost:0", parallax_config=cfg)
+    g = torch.Generator().manual_seed(0)
+
+    def feed():
+        return {"ids": [torch.randint(0, 64, (8, 3), generator=g)],
+                "labels": [torch.randint(0, 4, (8,), generator=g)]}
+    for _ in range(5):
+        sess.run(["loss", "train_op"], feed())
+    eng = sess.engine
+    before = eng.state_dict()["sparse"]["emb.weight"]
+    eng.repartition(7)
+    assert eng.tables["emb.weight"].layout.P == 7
+    after = eng.state_dict()["sparse"]["emb.weight"]
+    torch.testing.assert_close(after["weight"], before["weight"])
+    torch.testing.assert_close(after["slots"][0], before["slots"][0])
+    losses = [sess.run(["loss", "train_op"], feed())[0][0] for _ in range(5)]
+    assert np.isfinite(losses).all()
+    sess.close()
