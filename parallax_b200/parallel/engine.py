@@ -329,7 +329,8 @@ class TrainEngine(object):
     def _use_graph(self):
         if self.backend != "nvlink" or not self.config.sess_option("cuda_graph", False):
             return False
-        return self.global_step >= int(self.config.sess_option("graph_warmup", 3))
+        warm = int(self.config.sess_option("graph_warmup", 3))
+        return self.global_step >= max(warm, getattr(self, "_graph_not_before", 0))
 
     @staticmethod
     def _feed_sig(feeds):
@@ -441,8 +442,11 @@ class TrainEngine(object):
             self.tables[name] = new
             if holder is not None:
                 holder.table = new
-        self._graph_state = None          # captured graphs hold the old tables
-        self.analysis.variables  # (report keeps the build-time partition counts)
+        # captured graphs hold the old tables; the new ones allocate their rings
+        # lazily, so run a few eager steps before capturing again
+        self._graph_state = None
+        self._graph_not_before = self.global_step + \
+            int(self.config.sess_option("graph_warmup", 3))
 
     # ------------------------------------------------------------ reporting
     def export_report(self, path):
