@@ -34,6 +34,16 @@ class NVFabric(object):
         self.rank, self.world = comm.rank, comm.world
         self.options = options or {}
         ex = exchange if exchange is not None else IpcExchange(comm)
+        if exchange is None and comm.distributed:
+            import socket
+            hosts = set(comm.all_gather_object(socket.gethostname()))
+            if len(hosts) > 1:
+                raise RuntimeError(
+                    "the NVLink fabric addresses peers through CUDA IPC / NVSwitch "
+                    "multicast and therefore spans ONE NVLink domain (one HGX/DGX box); "
+                    "this job spans hosts %s. Run one job per box, or use "
+                    "sess_config={'fabric': 'host'} (gloo/TCP library path) across boxes."
+                    % sorted(hosts))
         self.heap = SymmetricHeap(self.device, ex)
         self.comm_stream = torch.cuda.Stream(self.device, priority=-1)
         # double-buffered staging for the one-shot all-reduce (norms, scalars)
