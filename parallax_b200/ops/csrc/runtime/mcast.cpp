@@ -17,6 +17,7 @@
 #include <cstring>
 #include <string>
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <sys/un.h>
 #include <unistd.h>
 #include <vector>
@@ -84,6 +85,8 @@ int px_fd_listen(const char* job, int rank) {
   sockaddr_un a; socklen_t len;
   fill_addr(a, len, sock_name(job, rank));
   if (bind(listen_fd, (sockaddr*)&a, len) < 0) FAIL("bind: %s", strerror(errno));
+  timeval tv{60, 0};                       // never block a rank forever on a lost fd
+  setsockopt(listen_fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
   return 0;
 }
 

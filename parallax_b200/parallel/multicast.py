@@ -78,13 +78,24 @@ class MulticastBuffer(object):
         _ck(L.px_fd_listen(job.encode(), rank), "fd_listen")
         comm.barrier()
         ok, err = True, ""
+        # rank 0 creates the multicast object first and tells everybody whether it
+        # worked — peers must never block in recv on an fd that will not come
+        fd0 = _i(-1)
+        if rank == 0:
+            try:
+                _ck(L.px_mc_create_export(seg, W, ctypes.byref(fd0)), "mc_create")
+            except MulticastError as e:
+                ok, err = False, str(e)
+        ok0, err0 = comm.broadcast_object((ok, err), 0)
+        if not ok0:
+            L.px_fd_close_listener()
+            L.px_mc_seg_destroy(seg)
+            raise MulticastError("multicast object creation failed on rank 0: %s" % err0)
         try:
             if rank == 0:
-                fd = _i()
-                _ck(L.px_mc_create_export(seg, W, ctypes.byref(fd)), "mc_create")
                 for r in range(1, W):
-                    _ck(L.px_fd_send(job.encode(), r, fd.value, 0), "fd_send")
-                L.px_fd_close(fd.value)
+                    _ck(L.px_fd_send(job.encode(), r, fd0.value, 0), "fd_send")
+                L.px_fd_close(fd0.value)
             else:
                 fd, tag = _i(), _i()
                 _ck(L.px_fd_recv(ctypes.byref(fd), ctypes.byref(tag)), "fd_recv")
