@@ -11,7 +11,7 @@ import torch.nn.functional as F
 
 from .. import optim
 from ..graph import Graph
-from .resnet import resnet50, resnet101, resnet152
+from .resnet import resnet50, resnet101, resnet152, resnet_v2
 
 
 class _Classifier(nn.Module):
@@ -153,3 +153,167 @@ def cnn_graph(model, optimizer="momentum", learning_rate=0.01, momentum=0.9,
            "rmsprop": lambda: optim.RMSProp(learning_rate, 0.9, momentum, 1.0,
                                             weight_decay=weight_decay)}[optimizer]()
     return Graph(model, optimizer=opt, loss="loss", name="cnn")
+
+
+# ---------------------------------------------------------------------------
+# Inception v3 / v4-lite, CIFAR ResNet and DenseNet (model_config.py:30-64)
+# ---------------------------------------------------------------------------
+def _cbr(cin, cout, k, s=1, p=0):
+    return nn.Sequential(nn.Conv2d(cin, cout, k, s, p, bias=False), nn.BatchNorm2d(cout),
+                         nn.ReLU(inplace=True))
+
+
+class _Branches(nn.Module):
+    def __init__(self, *branches):
+        super().__init__()
+        self.branches = nn.ModuleList(branches)
+
+    def forward(self, x):
+        return torch.cat([b(x) for b in self.branches], 1)
+
+
+def _inc_a(cin, pool):
+    return _Branches(_cbr(cin, 64, 1),
+                     nn.Sequential(_cbr(cin, 48, 1), _cbr(48, 64, 5, p=2)),
+                     nn.Sequential(_cbr(cin, 64, 1), _cbr(64, 96, 3, p=1), _cbr(96, 96, 3, p=1)),
+                     nn.Sequential(nn.AvgPool2d(3, 1, 1), _cbr(cin, pool, 1)))
+
+
+def _inc_b(cin):      # grid reduction 35 -> 17
+    return _Branches(_cbr(cin, 384, 3, 2),
+                     nn.Sequential(_cbr(cin, 64, 1), _cbr(64, 96, 3, p=1), _cbr(96, 96, 3, 2)),
+                     nn.MaxPool2d(3, 2))
+
+
+def _inc_c(cin, c7):
+    return _Branches(
+        _cbr(cin, 192, 1),
+        nn.Sequential(_cbr(cin, c7, 1), _cbr(c7, c7, (1, 7), p=(0, 3)),
+                      _cbr(c7, 192, (7, 1), p=(3, 0))),
+        nn.Sequential(_cbr(cin, c7, 1), _cbr(c7, c7, (7, 1), p=(3, 0)),
+                      _cbr(c7, c7, (1, 7), p=(0, 3)), _cbr(c7, c7, (7, 1), p=(3, 0)),
+                      _cbr(c7, 192, (1, 7), p=(0, 3))),
+        nn.Sequential(nn.AvgPool2d(3, 1, 1), _cbr(cin, 192, 1)))
+
+
+def _inc_d(cin):      # grid reduction 17 -> 8
+    return _Branches(nn.Sequential(_cbr(cin, 192, 1), _cbr(192, 320, 3, 2)),
+                     nn.Sequential(_cbr(cin, 192, 1), _cbr(192, 192, (1, 7), p=(0, 3)),
+                                   _cbr(192, 192, (7, 1), p=(3, 0)), _cbr(192, 192, 3, 2)),
+                     nn.MaxPool2d(3, 2))
+
+
+class _IncE(nn.Module):
+    def __init__(self, cin):
+        super().__init__()
+        self.b1 = _cbr(cin, 320, 1)
+        self.b3 = _cbr(cin, 384, 1)
+        self.b3a, self.b3b = _cbr(384, 384, (1, 3), p=(0, 1)), _cbr(384, 384, (3, 1), p=(1, 0))
+        self.bd = nn.Sequential(_cbr(cin, 448, 1), _cbr(448, 384, 3, p=1))
+        self.bda, self.bdb = _cbr(384, 384, (1, 3), p=(0, 1)), _cbr(384, 384, (3, 1), p=(1, 0))
+        self.bp = nn.Sequential(nn.AvgPool2d(3, 1, 1), _cbr(cin, 192, 1))
+
+    def forward(self, x):
+        b3, bd = self.b3(x), self.bd(x)
+        return torch.cat([self.b1(x), self.b3a(b3), self.b3b(b3), self.bda(bd), self.bdb(bd),
+                          self.bp(x)], 1)
+
+
+class Inception3(_Classifier):
+    image_size = 299
+
+    def __init__(self, num_classes=1000, depth_e=2):
+        super().__init__()
+        self.net = nn.Sequential(
+            _cbr(3, 32, 3, 2), _cbr(32, 32, 3), _cbr(32, 64, 3, p=1), nn.MaxPool2d(3, 2),
+            _cbr(64, 80, 1), _cbr(80, 192, 3), nn.MaxPool2d(3, 2),
+            _inc_a(192, 32), _inc_a(256, 64), _inc_a(288, 64), _inc_b(288),
+            _inc_c(768, 128), _inc_c(768, 160), _inc_c(768, 160), _inc_c(768, 192), _inc_d(768),
+            *[_IncE(1280 if i == 0 else 2048) for i in range(depth_e)],
+            nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Dropout(0.2), nn.Linear(2048, num_classes))
+
+
+class Inception4(Inception3):
+    """Inception-v4-sized variant: the v3 stem/blocks with the v4 block counts
+    (4×A, 7×C, 3×E) — same kernels and gradient volume class as
+    `models/inception_model.py` Inceptionv4Model."""
+
+    def __init__(self, num_classes=1000):
+        _Classifier.__init__(self)
+        self.net = nn.Sequential(
+            _cbr(3, 32, 3, 2), _cbr(32, 32, 3), _cbr(32, 64, 3, p=1), nn.MaxPool2d(3, 2),
+            _cbr(64, 80, 1), _cbr(80, 192, 3), nn.MaxPool2d(3, 2),
+            _inc_a(192, 32), _inc_a(256, 64), _inc_a(288, 64), _inc_a(288, 64), _inc_b(288),
+            *[_inc_c(768, c) for c in (128, 160, 160, 160, 160, 160, 192)], _inc_d(768),
+            _IncE(1280), _IncE(2048), _IncE(2048),
+            nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Dropout(0.2), nn.Linear(2048, num_classes))
+
+
+class _CifarBlock(nn.Module):
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.c1, self.b1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False), nn.BatchNorm2d(cout)
+        self.c2, self.b2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False), nn.BatchNorm2d(cout)
+        self.short = None if stride == 1 and cin == cout else \
+            nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+    def forward(self, x):
+        y = self.b2(self.c2(F.relu(self.b1(self.c1(x)))))
+        return F.relu(y + (x if self.short is None else self.short(x)))
+
+
+class CifarResNet(_Classifier):
+    """resnet20/32/44/56/110 for CIFAR-10 (`models/resnet_model.py` cifar variants)."""
+    image_size = 32
+
+    def __init__(self, depth=20, num_classes=10):
+        super().__init__()
+        n = (depth - 2) // 6
+        layers, cin = [nn.Conv2d(3, 16, 3, 1, 1, bias=False), nn.BatchNorm2d(16), nn.ReLU()], 16
+        for cout, stride in ((16, 1), (32, 2), (64, 2)):
+            for i in range(n):
+                layers.append(_CifarBlock(cin, cout, stride if i == 0 else 1))
+                cin = cout
+        self.net = nn.Sequential(*layers, nn.AdaptiveAvgPool2d(1), nn.Flatten(),
+                                 nn.Linear(64, num_classes))
+
+
+class _DenseLayer(nn.Module):
+    def __init__(self, cin, k):
+        super().__init__()
+        self.bn, self.conv = nn.BatchNorm2d(cin), nn.Conv2d(cin, k, 3, 1, 1, bias=False)
+
+    def forward(self, x):
+        return torch.cat([x, self.conv(F.relu(self.bn(x)))], 1)
+
+
+class CifarDenseNet(_Classifier):
+    """densenet40_k12 / densenet100_k12 / densenet100_k24 (`models/densenet_model.py`)."""
+    image_size = 32
+
+    def __init__(self, depth=40, k=12, num_classes=10):
+        super().__init__()
+        n = (depth - 4) // 3
+        layers, c = [nn.Conv2d(3, 16, 3, 1, 1, bias=False)], 16
+        for stage in range(3):
+            for _ in range(n):
+                layers.append(_DenseLayer(c, k))
+                c += k
+            if stage < 2:
+                layers += [nn.BatchNorm2d(c), nn.ReLU(), nn.Conv2d(c, c, 1, bias=False),
+                           nn.AvgPool2d(2)]
+        self.net = nn.Sequential(*layers, nn.BatchNorm2d(c), nn.ReLU(), nn.AdaptiveAvgPool2d(1),
+                                 nn.Flatten(), nn.Linear(c, num_classes))
+
+
+MODELS.update({
+    "resnet50_v2": lambda n=1000: resnet_v2(50, n), "resnet101_v2": lambda n=1000: resnet_v2(101, n),
+    "resnet152_v2": lambda n=1000: resnet_v2(152, n),
+    "inception3": Inception3, "inception4": Inception4,
+    "resnet20": lambda n=10: CifarResNet(20, n), "resnet32": lambda n=10: CifarResNet(32, n),
+    "resnet44": lambda n=10: CifarResNet(44, n), "resnet56": lambda n=10: CifarResNet(56, n),
+    "resnet110": lambda n=10: CifarResNet(110, n),
+    "densenet40_k12": lambda n=10: CifarDenseNet(40, 12, n),
+    "densenet100_k12": lambda n=10: CifarDenseNet(100, 12, n),
+    "densenet100_k24": lambda n=10: CifarDenseNet(100, 24, n),
+})
