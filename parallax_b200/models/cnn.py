@@ -307,7 +307,8 @@ class CifarDenseNet(_Classifier):
 
 
 MODELS.update({
-    "resnet50_v2": lambda n=1000: resnet_v2(50, n), "resnet101_v2": lambda n=1000: resnet_v2(101, n),
+    "resnet50_v2": lambda n=1000: resnet_v2(50, n),
+    "resnet101_v2": lambda n=1000: resnet_v2(101, n),
     "resnet152_v2": lambda n=1000: resnet_v2(152, n),
     "inception3": Inception3, "inception4": Inception4,
     "resnet20": lambda n=10: CifarResNet(20, n), "resnet32": lambda n=10: CifarResNet(32, n),
