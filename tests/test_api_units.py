@@ -205,3 +205,38 @@ def test_inprocess_repartition_preserves_state_and_search_runs():
     assert p >= 2 and eng.tables["emb.weight"].layout.P == p
     assert np.isfinite(sess.run(["loss", "train_op"], feed())[0][0]) and np.isfinite(l0)
     sess.close()
+
+
+def test_profile_range_and_ckpt_secs(tmp_path):
+    import socket
+    import time
+    pc = parallax.ProfileConfig(profile_dir=str(tmp_path / "prof"), profile_range=(1, 3))
+    ck = parallax.CheckPointConfig(ckpt_dir=str(tmp_path / "ck"), save_ckpt_secs=0.0001)
+    cfg = parallax.Config(profile_config=pc, ckpt_config=ck, sess_config={"fabric": "host"})
+    sess, _ = _train(cfg, 4)
+    sess.close()
+    d = tmp_path / "prof" / socket.gethostname() / "worker:0" / "run_meta"
+    got = sorted(f for f in os.listdir(d) if f.endswith(".json"))
+    assert got == ["run_meta_1.json", "run_meta_2.json"]          # [start, end)
+    saved = [f for f in os.listdir(tmp_path / "ck") if f.startswith("model.ckpt-")]
+    assert len(saved) >= 2                                        # time-based saving fired
+
+
+def test_div_partition_strategy_matches_mod_results():
+    """The two TF partition strategies only differ in row placement."""
+    outs = []
+    for strat in ("mod", "div"):
+        torch.manual_seed(0)
+        model = MLPWithEmbedding(61, partitioner=parallax.get_partitioner(4, strategy=strat))
+        g = parallax.Graph(model, optimizer=optim.Adagrad(0.2, 1.0))
+        cfg = parallax.Config(sess_config={"fabric": "host"})
+        sess, *_ = parallax.parallel_run(g, "localhost", parallax_config=cfg)
+        gen = torch.Generator().manual_seed(5)
+        for _ in range(3):
+            ids = torch.randint(0, 61, (4, 3), generator=gen)
+            sess.run(["loss", "train_op"], {"ids": [ids],
+                                            "labels": [torch.randint(0, 4, (4,), generator=gen)]})
+        outs.append(sess.engine.state_dict()["sparse"]["emb.weight"]["weight"])
+        assert sess.engine.tables["emb.weight"].layout.strategy == strat
+        sess.close()
+    torch.testing.assert_close(outs[0], outs[1])

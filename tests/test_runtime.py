@@ -110,6 +110,22 @@ def _hvd_worker(rank, world):
         out["mismatch_error"] = False
     except hvd.HorovodInternalError:
         out["mismatch_error"] = True
+    # mismatched broadcast root / allgather trailing dims are errors too
+    try:
+        hvd.broadcast(torch.zeros(2), root_rank=rank, name="badroot")
+        out["root_error"] = False
+    except hvd.HorovodInternalError:
+        out["root_error"] = True
+    try:
+        hvd.allgather(torch.zeros(2, 3 + rank), name="badgather")
+        out["gather_error"] = False
+    except hvd.HorovodInternalError:
+        out["gather_error"] = True
+    g = hvd.grouped_allreduce([torch.ones(3) * (rank + 1), torch.ones(2, 2) * rank],
+                              average=False)
+    out["grouped"] = [t.clone() for t in g]
+    out["fp16"] = hvd.allreduce(torch.ones(4) * (rank + 1), average=True,
+                                compression=hvd.Compression.fp16)
     out["stats"] = hvd.registry_stats()
     # DistributedOptimizer averages gradients
     w = torch.nn.Parameter(torch.ones(3))
@@ -134,7 +150,10 @@ def test_collectives_api_host_fabric():
         exp[0] += torch.tensor([1.0, 2.0]); exp[1] += torch.tensor([1.0, 2.0])
         exp[5] += 2 * torch.tensor([1.0, 2.0])
         torch.testing.assert_close(o["sparse"], exp)
-        assert o["dup_error"] and o["mismatch_error"]
+        assert o["dup_error"] and o["mismatch_error"] and o["root_error"] and o["gather_error"]
+        torch.testing.assert_close(o["grouped"][0], torch.full((3,), 3.0))
+        torch.testing.assert_close(o["grouped"][1], torch.full((2, 2), 1.0))
+        torch.testing.assert_close(o["fp16"], torch.full((4,), 1.5))
         assert o["stats"]["hits"] >= 1
         torch.testing.assert_close(o["w"], torch.ones(3) - 1.5)
 
