@@ -533,6 +533,14 @@ class NVSparseTable(object):
         self.anchor_device = self.device
         self.max_blocks = int(opts.get("sparse_blocks", 148 * 4))
         self.capacity_hint = (opts.get("sparse_capacity") or {}).get(name)
+        # push/apply as soon as the table's last gradient of the step has arrived
+        # (softmax tables: right after the loss backward, overlapping the LSTM
+        # backward) instead of after the whole backward pass.  The comm-stream
+        # order stays identical on all ranks because autograd order is.
+        self.early_push = bool(opts.get("sparse_early_push", True))
+        self._fwd_calls = self._bwd_calls = 0
+        self._cur_step = 0
+        self._done_step = -1
         L = self.layout
         rows = L.rows_local
         # table + slots in symmetric memory (async mode updates them remotely)
@@ -598,6 +606,8 @@ class NVSparseTable(object):
         ids = ids.contiguous()
         out = torch.empty((n, self.Dp), dtype=self.out_dtype, device=self.device)
         pend = torch.empty(n, dtype=torch.int32, device=self.device) if record else None
+        if record:
+            self._fwd_calls += 1
         nvops.sparse_lookup(ids, n, self._tdev(), out, pend, self.geom,
                             self.hdr_buf.local_ptr, self.ctl,
                             wait=self.route.sync and self.world > 1)
@@ -627,6 +637,14 @@ class NVSparseTable(object):
         if g.dtype not in (torch.float32, torch.bfloat16):
             g = g.float()
         self.calls.append((token, g.contiguous()))
+        self._bwd_calls += 1
+        if self.early_push and self._bwd_calls == self._fwd_calls and self._cur_step > 0 \
+                and self.ring_ready():
+            self._run_step(self._cur_step)
+
+    def ring_ready(self):
+        """Early push needs every lazy allocation done (first step runs at the end)."""
+        return self.scratch_n > 0 and (not self.route.sync or self.ring_buf is not None)
 
     # ----------------------------------------------------------------- update
     def _ensure_capacity(self, n):
@@ -690,9 +708,17 @@ class NVSparseTable(object):
         for i, v in enumerate(hp):
             self.hp_host[i] = v
         self.hp.copy_(self.hp_host, non_blocking=True)
+        self._cur_step = step
+        self._fwd_calls = self._bwd_calls = 0
 
     def finish_step(self, step, stream=None):
+        if self._done_step == step and not self.calls:
+            return                           # already pushed from the backward pass
+        self._run_step(step, stream)
+
+    def _run_step(self, step, stream=None):
         from ..utils import timeline
+        self._done_step = step
         if timeline.enabled():
             cs = stream if stream is not None else self.fabric.comm_stream
             with timeline.activity(self.name, "SPARSE_PUSH_APPLY", gpu=True, stream=cs,

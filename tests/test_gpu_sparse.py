@@ -26,7 +26,7 @@ def _tables(world, V, D, P, opt, run_option="HYBRID", sync=True, average=False,
     tabs = [NVSparseTable("emb.weight", W0, P, strategy, opt, f, route, graph, cfg,
                           out_dtype=out_dtype,
                           options={"sparse_capacity": {"emb.weight": cap or 4096},
-                                   "sparse_blocks": 4})
+                                   "sparse_blocks": 4, "sparse_early_push": False})
             for f in fabs]
     return fabs, tabs, W0
 

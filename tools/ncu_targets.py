@@ -69,7 +69,8 @@ graph = Graph(torch.nn.Linear(1, 1), optimizer=opt)
 W0 = torch.empty(V, Dm, device="meta")
 t = NVSparseTable("softmax_w.weight", W0, 32, "mod", opt, f, route, graph, cfg,
                   init={"seed": 1, "scale": 0.05}, out_dtype=torch.bfloat16,
-                  options={"sparse_capacity": {"softmax_w.weight": 16384}})
+                  options={"sparse_capacity": {"softmax_w.weight": 16384},
+                           "sparse_early_push": False})
 t.warm(n_ids)
 for step in range(1, REP + 1):
     ids = torch.randint(0, V, (n_ids,), device=dev)
