@@ -81,11 +81,11 @@ class _HostTableAdapter(object):
     def __init__(self, t):
         self.t = t
         self.V, self.D, self.layout = t.V, t.D, t.layout
-        self.anchor_device = torch.device("cpu")
+        self.anchor_device = t.device
         self.name = t.name
 
     def lookup(self, flat_ids, record=True):
-        ids = flat_ids.to(torch.int64).cpu()
+        ids = flat_ids.to(torch.int64).to(self.t.device)
         return self.t.gather_rows(ids).to(self.t.out_dtype), ids
 
     def add_pending(self, token, grad_rows):
@@ -139,11 +139,13 @@ class TrainEngine(object):
 
     def _build(self):
         g, comm, cfg = self.graph, self.comm, self.config
-        if self.backend == "host":
+        if self.backend in ("host", "library"):
             from .host_backend import HostDenseGroup, HostSparseTable
-            self.model.to("cpu") if not any(
-                p.device.type == "meta" for p in self.model.parameters()) \
-                else None
+            # "host": everything on the CPU over gloo (tests, oracle);
+            # "library": same code, tensors on this worker's device, collectives on
+            # NCCL — for jobs spanning several NVLink domains
+            dev = torch.device("cpu") if self.backend == "host" else comm.device
+            self._lib_device = dev
             for path, mod in self.analysis.sparse_modules.items():
                 pname = path + ".weight" if path else "weight"
                 info = self.analysis.variables[pname]
@@ -153,10 +155,11 @@ class TrainEngine(object):
                     part.strategy if part is not None else "mod",
                     g.sparse_optimizer, comm, self.route, g, cfg,
                     init={"seed": getattr(mod, "init_seed", 1234),
-                          "scale": getattr(mod, "init_scale", 0.05)})
+                          "scale": getattr(mod, "init_scale", 0.05)}, device=dev)
                 adapter = _HostTableAdapter(t)
                 self.tables[pname] = adapter
                 _set_submodule(self.model, path, ShardedEmbedding(adapter))
+            self.model.to(dev)
             dense_named = [(n, p) for n, p in self.model.named_parameters()
                            if p.requires_grad and
                            not getattr(p, "_parallax_skip", False)]
@@ -209,7 +212,7 @@ class TrainEngine(object):
 
     # ------------------------------------------------------------------- run
     def _prepare_feeds(self, feeds):
-        dev = self.comm.device if self.backend != "host" else torch.device("cpu")
+        dev = getattr(self, "_lib_device", None) or self.comm.device
         return {k: (v.to(dev, non_blocking=True)
                     if torch.is_tensor(v) and v.device != dev else v)
                 for k, v in feeds.items()}
@@ -422,11 +425,11 @@ class TrainEngine(object):
                 if isinstance(m_, ShardedEmbedding) and m_.table is old:
                     holder, path = m_, p_
             strategy = old.layout.strategy
-            if self.backend == "host":
+            if self.backend in ("host", "library"):
                 from .host_backend import HostSparseTable
                 new = _HostTableAdapter(HostSparseTable(
                     name, weight, num_partitions, strategy, self.graph.sparse_optimizer,
-                    self.comm, self.route, self.graph, self.config))
+                    self.comm, self.route, self.graph, self.config, device=old.t.device))
             else:
                 from .nvlink_backend import NVSparseTable
                 opts = dict(self.config.sess_config) \

@@ -1,5 +1,8 @@
-"""Host fabric: the whole engine expressed with plain torch ops and
-`torch.distributed` library collectives (gloo on CPU).
+"""Host / library fabric: the whole engine expressed with plain torch ops and
+`torch.distributed` library collectives (gloo on CPU; with ``fabric="library"``
+the same code keeps every tensor on the worker's GPU and the collectives run on
+NCCL — the path for jobs that span several NVLink domains, where peer memory
+cannot be addressed).
 
 Purpose: (1) BASELINE config 1 — plumbing and dense/sparse routing tests with
 ``world_size=2`` and no GPU; (2) the semantic oracle the sm_100a kernels are
@@ -75,7 +78,7 @@ class HostDenseGroup(object):
             # mean over workers; one fused buffer, one library all-reduce
             if W > 1:
                 flat = torch.cat([g.reshape(-1) for g in grads]) if grads \
-                    else torch.zeros(0)
+                    else torch.zeros(0, device=self.params[0].device if self.params else "cpu")
                 self.comm.all_reduce_sum_(flat)
                 flat.div_(W)
                 off = 0
@@ -122,10 +125,10 @@ class HostDenseGroup(object):
     def state_dict(self):
         sd = {"master": {}, "slots": {}, "ema": {}}
         for i, n in enumerate(self.names):
-            sd["master"][n] = self.master[i].clone()
-            sd["slots"][n] = [s.clone() for s in self.slots[i]]
+            sd["master"][n] = self.master[i].detach().cpu().clone()
+            sd["slots"][n] = [s.detach().cpu().clone() for s in self.slots[i]]
             if i in self.ema:
-                sd["ema"][n] = self.ema[i].clone()
+                sd["ema"][n] = self.ema[i].detach().cpu().clone()
         return sd
 
     def load_state_dict(self, sd):
@@ -148,8 +151,9 @@ class HostSparseTable(object):
     """One sparse variable (embedding table) on the host fabric."""
 
     def __init__(self, name, weight, num_partitions, strategy, optimizer, comm,
-                 route, graph, config, init=None):
+                 route, graph, config, init=None, device=None):
         self.name = name
+        self.device = torch.device("cpu") if device is None else torch.device(device)
         self.comm = comm
         self.route = route
         self.optimizer = optimizer
@@ -162,15 +166,16 @@ class HostSparseTable(object):
             config.communication_config.ps_config.local_aggregation)
         self.scale = graph.scale_for(name)
         L = self.layout
-        self.shard = torch.zeros(L.rows_local, self.D, dtype=torch.float32)
+        shard = torch.zeros(L.rows_local, self.D, dtype=torch.float32)
         g, l = L.global_ids_of_owner(comm.rank)
         if weight.device.type == "meta":
             gen = torch.Generator().manual_seed(init["seed"])
             full = torch.empty(self.V, self.D).uniform_(
                 -init["scale"], init["scale"], generator=gen)
-            self.shard[l] = full[g]
+            shard[l] = full[g]
         else:
-            self.shard[l] = weight.detach().to(torch.float32)[g]
+            shard[l] = weight.detach().to(torch.float32).cpu()[g]
+        self.shard = shard.to(self.device)
         self.slots = _slots_like(self.shard, optimizer)
         self.pending = []
         self.out_dtype = weight.dtype if weight.device.type != "meta" \
@@ -188,9 +193,9 @@ class HostSparseTable(object):
         for r in range(W):
             mask = L.owner_of(all_ids[r]) == me
             resp.append(self.shard[L.local_row_of(all_ids[r][mask])])
-        resp_cat = torch.cat(resp) if resp else torch.zeros(0, self.D)
+        resp_cat = torch.cat(resp) if resp else torch.zeros(0, self.D, device=self.device)
         all_resp = self.comm.all_gather_varlen(resp_cat)
-        out = torch.zeros(ids.numel(), self.D, dtype=torch.float32)
+        out = torch.zeros(ids.numel(), self.D, dtype=torch.float32, device=self.device)
         owners = L.owner_of(ids)
         for o in range(W):
             # offset of my segment inside owner o's response
@@ -213,15 +218,15 @@ class HostSparseTable(object):
             ids = torch.cat([p[0] for p in self.pending])
             rows = torch.cat([p[1] for p in self.pending])
         else:
-            ids = torch.zeros(0, dtype=torch.int64)
-            rows = torch.zeros(0, self.D)
+            ids = torch.zeros(0, dtype=torch.int64, device=self.device)
+            rows = torch.zeros(0, self.D, device=self.device)
         self.pending = []
         if self.scale != 1.0:
             rows = rows * self.scale
         self.stats["pushed_rows"] += int(ids.numel())
         if self.local_aggregation and ids.numel():
             ids, inv = torch.unique(ids, return_inverse=True)
-            agg = torch.zeros(ids.numel(), self.D)
+            agg = torch.zeros(ids.numel(), self.D, device=self.device)
             agg.index_add_(0, inv, rows)
             rows = agg
         self.stats["unique_rows"] += int(ids.numel())
@@ -235,7 +240,7 @@ class HostSparseTable(object):
                 mask = L.owner_of(ids_c) == me
                 ids_c, rows_c = ids_c[mask], rows_c[mask]
             u, inv = torch.unique(ids_c, return_inverse=True)
-            g = torch.zeros(u.numel(), self.D)
+            g = torch.zeros(u.numel(), self.D, device=self.device)
             g.index_add_(0, inv, rows_c)
             if self.average:
                 g.div_(W)
@@ -248,7 +253,7 @@ class HostSparseTable(object):
             for ids_r, rows_r in zip(all_ids, all_rows):
                 mask = L.owner_of(ids_r) == me
                 u, inv = torch.unique(ids_r[mask], return_inverse=True)
-                g = torch.zeros(u.numel(), self.D)
+                g = torch.zeros(u.numel(), self.D, device=self.device)
                 g.index_add_(0, inv, rows_r[mask])
                 _optim.apply_sparse_rows_(kind, self.shard, L.local_row_of(u),
                                           g, self.slots, hp)
@@ -259,13 +264,13 @@ class HostSparseTable(object):
         if self.replicated or W == 1:
             g, l = L.global_ids_of_owner(0 if self.replicated else self.comm.rank)
             out = torch.zeros(self.V, local.shape[1])
-            out[g] = local[l]
+            out[g] = local.cpu()[l]
             return out
         shards = self.comm.all_gather_tensors(local)
         out = torch.zeros(self.V, local.shape[1])
         for o in range(W):
             g, l = L.global_ids_of_owner(o)
-            out[g] = shards[o][l]
+            out[g] = shards[o].cpu()[l]
         return out
 
     def full_weight(self):
@@ -277,7 +282,8 @@ class HostSparseTable(object):
     def load_full(self, weight, slots=None):
         g, l = self.layout.global_ids_of_owner(
             0 if self.replicated else self.comm.rank)
-        self.shard[l] = weight.to(torch.float32)[g]
+        l = l.to(self.device)
+        self.shard[l] = weight.to(torch.float32)[g].to(self.device)
         if slots is not None:
             for s, full in zip(self.slots, slots):
-                s[l] = full.to(torch.float32)[g]
+                s[l] = full.to(torch.float32)[g].to(self.device)

@@ -42,7 +42,8 @@ class NVFabric(object):
                     "the NVLink fabric addresses peers through CUDA IPC / NVSwitch "
                     "multicast and therefore spans ONE NVLink domain (one HGX/DGX box); "
                     "this job spans hosts %s. Run one job per box, or use "
-                    "sess_config={'fabric': 'host'} (gloo/TCP library path) across boxes."
+                    "sess_config={'fabric': 'library'} (same engine on torch.distributed/"
+                    "NCCL collectives) across boxes."
                     % sorted(hosts))
         self.heap = SymmetricHeap(self.device, ex)
         self.comm_stream = torch.cuda.Stream(self.device, priority=-1)

@@ -57,7 +57,7 @@ def oracle(world, steps, opt, sparse_scale):
 
 
 def worker(rank, world, run_option, average_sparse, opt_name, steps, sync=True,
-           local_agg=True, nparts=None):
+           local_agg=True, nparts=None, fabric=None):
     opt = make_opt(opt_name)
     part = parallax.get_partitioner(nparts) if nparts else None
     model = MLPWithEmbedding(VOCAB, partitioner=part)
@@ -65,6 +65,8 @@ def worker(rank, world, run_option, average_sparse, opt_name, steps, sync=True,
     cfg = parallax.Config()
     cfg.run_option = run_option
     cfg.average_sparse = average_sparse
+    if fabric:
+        cfg.sess_config = {"fabric": fabric}
     cfg.communication_config = parallax.CommunicationConfig(
         parallax.PSConfig(local_aggregation=local_agg))
     sess, nw, wid, nrep = parallax.parallel_run(graph, "localhost", sync=sync,
@@ -122,6 +124,17 @@ def test_local_aggregation_off_and_partitions():
     steps = 3
     res = run_distributed(worker, 2, "HYBRID", True, "adagrad", steps, True,
                           False, 5)
+    _, ref_w = oracle(2, steps, make_opt("adagrad"), sparse_scale=1.0)
+    for _, weights, _ in res:
+        for n, w in ref_w.items():
+            torch.testing.assert_close(weights[n], w, rtol=1e-5, atol=1e-6)
+
+
+def test_library_fabric_same_results():
+    """`fabric="library"`: the device-agnostic library path (NCCL on GPUs, gloo here)."""
+    steps = 3
+    res = run_distributed(worker, 2, "HYBRID", True, "adagrad", steps, True, True, 4,
+                          "library")
     _, ref_w = oracle(2, steps, make_opt("adagrad"), sparse_scale=1.0)
     for _, weights, _ in res:
         for n, w in ref_w.items():
