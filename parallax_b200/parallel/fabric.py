@@ -136,6 +136,25 @@ class Comm(object):
         gathered = self.all_gather_tensors(pad)
         return [g[:s] for g, s in zip(gathered, sizes)]
 
+    def all_to_all_varlen(self, t, send_counts):
+        """Exchange row segments: the first ``send_counts[0]`` rows of `t` go to
+        rank 0, the next ``send_counts[1]`` to rank 1, …  Returns
+        ``(received rows concatenated in source-rank order, recv_counts)`` — the
+        PS-style all-to-all of (index, row) pairs (BASELINE.md "PS-style as
+        all-to-all") used by the library fabric."""
+        if not self.distributed:
+            return t, list(send_counts)
+        W = self.world
+        sc = torch.tensor(list(send_counts), dtype=torch.int64, device=t.device)
+        rc = torch.empty(W, dtype=torch.int64, device=t.device)
+        dist.all_to_all_single(rc, sc, group=self._grp_for(t))
+        recv_counts = [int(x) for x in rc.tolist()]
+        out = torch.empty((sum(recv_counts),) + tuple(t.shape[1:]), dtype=t.dtype,
+                          device=t.device)
+        dist.all_to_all_single(out, t.contiguous(), recv_counts, list(send_counts),
+                               group=self._grp_for(t))
+        return out, recv_counts
+
     def _grp_for(self, t):
         if t.device.type == "cpu":
             return self.host_group()

@@ -188,23 +188,16 @@ class HostSparseTable(object):
         L, W, me = self.layout, self.comm.world, self.comm.rank
         if self.replicated or W == 1:
             return self.shard[L.local_row_of(ids)]
-        all_ids = self.comm.all_gather_varlen(ids)
-        resp = []
-        for r in range(W):
-            mask = L.owner_of(all_ids[r]) == me
-            resp.append(self.shard[L.local_row_of(all_ids[r][mask])])
-        resp_cat = torch.cat(resp) if resp else torch.zeros(0, self.D, device=self.device)
-        all_resp = self.comm.all_gather_varlen(resp_cat)
-        out = torch.zeros(ids.numel(), self.D, dtype=torch.float32, device=self.device)
+        # PS-style request/response all-to-all: ids travel to their owners, rows
+        # travel back; O(n) traffic per rank instead of an all-gather of every id
         owners = L.owner_of(ids)
-        for o in range(W):
-            # offset of my segment inside owner o's response
-            off = 0
-            for r in range(me):
-                off += int((L.owner_of(all_ids[r]) == o).sum())
-            mask = owners == o
-            n = int(mask.sum())
-            out[mask] = all_resp[o][off:off + n]
+        order = torch.argsort(owners, stable=True)
+        counts = torch.bincount(owners, minlength=W).tolist()
+        req, req_counts = self.comm.all_to_all_varlen(ids[order], counts)
+        rows = self.shard[L.local_row_of(req)]
+        resp, _ = self.comm.all_to_all_varlen(rows, req_counts)
+        out = torch.empty(ids.numel(), self.D, dtype=torch.float32, device=self.device)
+        out[order] = resp
         return out
 
     def add_pending(self, ids, grad_rows):
@@ -232,31 +225,35 @@ class HostSparseTable(object):
         self.stats["unique_rows"] += int(ids.numel())
         hp = self.optimizer.hyper(step)
         kind = self.optimizer.kind
-        if self.route.sync:
-            all_ids = self.comm.all_gather_varlen(ids)
-            all_rows = self.comm.all_gather_varlen(rows)
-            ids_c, rows_c = torch.cat(all_ids), torch.cat(all_rows)
-            if not self.replicated:
-                mask = L.owner_of(ids_c) == me
-                ids_c, rows_c = ids_c[mask], rows_c[mask]
-            u, inv = torch.unique(ids_c, return_inverse=True)
+        if self.replicated:
+            # AR run option (Horovod semantics): all-gather of indices and values,
+            # every replica applies the full update
+            ids_c = torch.cat(self.comm.all_gather_varlen(ids))
+            rows_c = torch.cat(self.comm.all_gather_varlen(rows))
+            segs = [(ids_c, rows_c)]
+        else:
+            # PS / HYBRID: all-to-all of (index, row) pairs to the owning rank
+            owners = L.owner_of(ids)
+            order = torch.argsort(owners, stable=True)
+            counts = torch.bincount(owners, minlength=W).tolist()
+            ids_c, rc = self.comm.all_to_all_varlen(ids[order], counts)
+            rows_c, _ = self.comm.all_to_all_varlen(rows[order], counts)
+            if self.route.sync:
+                segs = [(ids_c, rows_c)]
+            else:
+                # async PS: each worker's rows are applied on their own (rank order)
+                segs, off = [], 0
+                for n in rc:
+                    segs.append((ids_c[off:off + n], rows_c[off:off + n]))
+                    off += n
+        for seg_ids, seg_rows in segs:
+            u, inv = torch.unique(seg_ids, return_inverse=True)
             g = torch.zeros(u.numel(), self.D, device=self.device)
-            g.index_add_(0, inv, rows_c)
-            if self.average:
+            g.index_add_(0, inv, seg_rows)
+            if self.average and self.route.sync:
                 g.div_(W)
             _optim.apply_sparse_rows_(kind, self.shard, L.local_row_of(u), g,
                                       self.slots, hp)
-        else:
-            # async PS: each worker's rows are applied on their own
-            all_ids = self.comm.all_gather_varlen(ids)
-            all_rows = self.comm.all_gather_varlen(rows)
-            for ids_r, rows_r in zip(all_ids, all_rows):
-                mask = L.owner_of(ids_r) == me
-                u, inv = torch.unique(ids_r[mask], return_inverse=True)
-                g = torch.zeros(u.numel(), self.D, device=self.device)
-                g.index_add_(0, inv, rows_r[mask])
-                _optim.apply_sparse_rows_(kind, self.shard, L.local_row_of(u),
-                                          g, self.slots, hp)
 
     # -- checkpoint / inspection -------------------------------------------------
     def _gather_full(self, local):
