@@ -235,7 +235,12 @@ def main():
     eng = sess.engine
     dev = eng.comm.device
     gen = torch.Generator().manual_seed(99 + rank)
+    # untimed warm-up: at least 3 steps, and — when the step is graph-captured —
+    # enough to cover the eager steps plus the capture itself (which must never
+    # fall inside the timed region).  The JSON reports the number actually run.
     K, Wm = args.steps, max(args.warmup, 3)
+    if sc["cuda_graph"]:
+        Wm = max(Wm, int(sc.get("graph_warmup", 3)) + 2)
 
     # ---- device-timed arm: inputs resident on the device -------------------
     batches = [{k: v.to(dev) for k, v in make_batch(gen).items()} for _ in range(4)]
