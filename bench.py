@@ -125,7 +125,8 @@ def reference_arm(args):
             why = ("reference `import parallax` fails: %s; it requires the snuspl "
                    "TensorFlow r1.11 fork + Horovod 0.16.3 + mpirun (not in "
                    "/opt/wheelhouse, no sm_100 build)" % last)
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if int(os.environ.get("RANK", "0")) == 0:     # one line per job under torchrun
+        print(json.dumps({"impl": "reference", "unavailable": why}))
     return 0
 
 

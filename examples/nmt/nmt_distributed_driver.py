@@ -1,105 +1,142 @@
-"""NMT driver (reference `examples/nmt/nmt_distributed_driver.py:76-189`):
-GNMT-style seq2seq with partitioned embeddings; the parallel corpus is sharded
-across workers with `parallax.shard.shard` (`utils/iterator_utils.py:103`);
-only worker 0 logs statistics (`:147-163`).
+"""NMT driver (reference `examples/nmt/nmt_distributed_driver.py:76-189`,
+flag set of `examples/nmt/nmt.py:40-290`): vanilla / attention / GNMT
+sequence-to-sequence training with partitioned embeddings; the parallel corpus
+is sharded across workers through `parallax.shard`; only worker 0 logs
+statistics (`:147-163`).  Also runs file inference (`--inference_input_file`).
 
-    python examples/nmt/nmt_distributed_driver.py --synthetic --resource_info_file localhost
+    # synthetic corpus, GNMT, 4 GPUs
+    python examples/nmt/nmt_distributed_driver.py --synthetic \
+        --hparams_path wmt16_gnmt_4_layer --hparams num_units=256,num_train_steps=200 \
+        --resource_info_file localhost:0,1,2,3
+    # real data
+    python examples/nmt/nmt_distributed_driver.py --src vi --tgt en \
+        --vocab_prefix /data/vocab --train_prefix /data/train --dev_prefix /data/tst2012 \
+        --out_dir /tmp/nmt_model --hparams_path iwslt15
 """
 import argparse
 import os
+import random
 import sys
-import time
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-import torch
 
 import parallax_b200 as parallax
-from parallax_b200.models.seq2seq import NMT, nmt_graph
+import parallax_b200.models.nmt as nmt
+from parallax_b200.models.nmt import inference, vocab_utils
 import parallax_config
 
 ap = parallax_config.add_flags(argparse.ArgumentParser())
-ap.add_argument("--src_file", default=None)
-ap.add_argument("--tgt_file", default=None)
-ap.add_argument("--synthetic", action="store_true")
-ap.add_argument("--src_vocab_size", type=int, default=32000)
-ap.add_argument("--tgt_vocab_size", type=int, default=32000)
-ap.add_argument("--num_units", type=int, default=512)
-ap.add_argument("--num_layers", type=int, default=4)
-ap.add_argument("--num_embeddings_partitions", type=int, default=4)
-ap.add_argument("--batch_size", type=int, default=128)
-ap.add_argument("--max_len", type=int, default=50)
-ap.add_argument("--learning_rate", type=float, default=1.0)
-ap.add_argument("--max_gradient_norm", type=float, default=5.0)
-ap.add_argument("--max_steps", type=int, default=200)
-ap.add_argument("--log_frequency", type=int, default=20)
+# data
+ap.add_argument("--src", default="src", help="source language suffix")
+ap.add_argument("--tgt", default="tgt", help="target language suffix")
+ap.add_argument("--train_prefix", default=None)
+ap.add_argument("--dev_prefix", default=None)
+ap.add_argument("--test_prefix", default=None)
+ap.add_argument("--vocab_prefix", default=None)
+ap.add_argument("--embed_prefix", default=None, help="pretrained embeddings <prefix>.<lang>")
+ap.add_argument("--out_dir", default="/tmp/nmt_model")
+ap.add_argument("--synthetic", action="store_true",
+                help="generate a toy reversal corpus under out_dir/synthetic")
+# hyper-parameters: a standard file and/or a comma separated override string
+ap.add_argument("--hparams_path", default=None,
+                help="standard hparams name (%s) or json path" %
+                ", ".join(nmt.hparams.standard_hparams_names()))
+ap.add_argument("--hparams", default="", help="name=value,... overrides")
+ap.add_argument("--num_train_steps", type=int, default=None)
+ap.add_argument("--steps_per_eval", type=int, default=None)
+ap.add_argument("--random_seed", type=int, default=None)
+# inference
+ap.add_argument("--inference_input_file", default=None)
+ap.add_argument("--inference_output_file", default=None)
+ap.add_argument("--inference_ref_file", default=None)
+ap.add_argument("--num_workers", type=int, default=1, help="inference workers")
+ap.add_argument("--jobid", type=int, default=0, help="inference worker id")
 FLAGS = ap.parse_args()
 
 
-def corpus():
-    """(src_ids, tgt_ids) pairs — hashed-token ids when reading real files."""
-    if FLAGS.synthetic or not FLAGS.src_file:
-        g = torch.Generator().manual_seed(0)
-        for _ in range(100000):
-            n = int(torch.randint(5, FLAGS.max_len, (1,), generator=g))
-            yield (torch.randint(3, FLAGS.src_vocab_size, (n,), generator=g),
-                   torch.randint(3, FLAGS.tgt_vocab_size, (n,), generator=g))
+def synthetic_corpus(d, n_train=20000, n_dev=200, vocab=1000, min_len=5, max_len=30):
+    """target = reversed source with renamed words; written once"""
+    if os.path.exists(os.path.join(d, "vocab.tgt")):
+        return d
+    os.makedirs(d, exist_ok=True)
+    rng = random.Random(0)
+    for name, n in (("train", n_train), ("dev", n_dev), ("test", n_dev)):
+        with open(os.path.join(d, name + ".src"), "w") as fs, \
+                open(os.path.join(d, name + ".tgt"), "w") as ft:
+            for _ in range(n):
+                s = [rng.randrange(vocab) for _ in range(rng.randint(min_len, max_len))]
+                fs.write(" ".join("w%d" % i for i in s) + "\n")
+                ft.write(" ".join("t%d" % i for i in reversed(s)) + "\n")
+    for lang, pre in (("src", "w"), ("tgt", "t")):
+        with open(os.path.join(d, "vocab." + lang), "w") as f:
+            f.write("\n".join(["<unk>", "<s>", "</s>"] + [pre + str(i) for i in range(vocab)]) + "\n")
+    return d
+
+
+def build_hparams():
+    hp = nmt.create_hparams(FLAGS.hparams_path)
+    hp.src, hp.tgt, hp.out_dir = FLAGS.src, FLAGS.tgt, FLAGS.out_dir
+    if FLAGS.synthetic:
+        d = synthetic_corpus(os.path.join(FLAGS.out_dir, "synthetic"))
+        hp.train_prefix, hp.dev_prefix = d + "/train", d + "/dev"
+        hp.test_prefix, hp.vocab_prefix = d + "/test", d + "/vocab"
+        hp.subword_option = ""
+    for k in ("train_prefix", "dev_prefix", "test_prefix", "vocab_prefix", "embed_prefix"):
+        if getattr(FLAGS, k):
+            setattr(hp, k, getattr(FLAGS, k))
+    if FLAGS.num_train_steps:
+        hp.num_train_steps = FLAGS.num_train_steps
+    if FLAGS.steps_per_eval:
+        hp.steps_per_eval = FLAGS.steps_per_eval
+    if FLAGS.random_seed is not None:
+        hp.random_seed = FLAGS.random_seed
+    hp.parse(FLAGS.hparams)
+    if not hp.vocab_prefix:
+        raise ValueError("--vocab_prefix (or --synthetic) is required")
+    # a previous run's hparams win unless told otherwise (`nmt.py:476-510`)
+    loaded = nmt.load_hparams(hp.out_dir)
+    if loaded is not None and not hp.override_loaded_hparams:
+        hp = loaded
+    return hp
+
+
+def run_inference(hp):
+    """restore the latest checkpoint of out_dir and translate a file"""
+    nmt.train.prepare_vocab(hp)
+    model = nmt.create_model(hp)
+    cfg = parallax_config.build_config(FLAGS)
+    cfg.ckpt_config = parallax.CheckPointConfig(ckpt_dir=FLAGS.ckpt_dir or hp.out_dir)
+    sess, *_ = parallax.parallel_run(nmt.nmt_graph(model, hp), "localhost", sync=True,
+                                     parallax_config=cfg)
+    sv, tv = vocab_utils.create_vocab_tables(hp.src_vocab_file, hp.tgt_vocab_file, hp.share_vocab)
+    out = FLAGS.inference_output_file or os.path.join(hp.out_dir, "translations")
+    if FLAGS.num_workers > 1:
+        inference.multi_worker_inference(model, hp, FLAGS.inference_input_file, out, sv, tv,
+                                         FLAGS.num_workers, FLAGS.jobid)
     else:
-        with open(FLAGS.src_file) as fs, open(FLAGS.tgt_file) as ft:
-            for s, t in zip(fs, ft):
-                si = [3 + hash(w) % (FLAGS.src_vocab_size - 3) for w in s.split()][:FLAGS.max_len]
-                ti = [3 + hash(w) % (FLAGS.tgt_vocab_size - 3) for w in t.split()][:FLAGS.max_len]
-                if si and ti:
-                    yield torch.tensor(si), torch.tensor(ti)
-
-
-def batches(ds):
-    buf = []
-    for pair in ds:
-        buf.append(pair)
-        if len(buf) == FLAGS.batch_size:
-            L = FLAGS.max_len
-            src = torch.zeros(len(buf), L, dtype=torch.long)
-            tin = torch.zeros(len(buf), L + 1, dtype=torch.long)
-            tout = torch.zeros(len(buf), L + 1, dtype=torch.long)
-            w = torch.zeros(len(buf), L + 1)
-            for i, (s, t) in enumerate(buf):
-                src[i, :len(s)] = s
-                tin[i, 0] = 1
-                tin[i, 1:len(t) + 1] = t
-                tout[i, :len(t)] = t
-                tout[i, len(t)] = 2
-                w[i, :len(t) + 1] = 1
-            yield src, tin, tout, w
-            buf = []
+        inference.single_worker_inference(model, hp, FLAGS.inference_input_file, out, sv, tv)
+    if FLAGS.inference_ref_file and FLAGS.jobid == 0:
+        inference.decode_and_evaluate("infer", model, hp, None, sv, tv, out,
+                                      ref_file=FLAGS.inference_ref_file, decode=False)
+    sess.close()
 
 
 def main():
-    model = NMT(FLAGS.src_vocab_size, FLAGS.tgt_vocab_size, FLAGS.num_units, FLAGS.num_layers,
-                FLAGS.num_embeddings_partitions)
-    graph = nmt_graph(model, FLAGS.learning_rate, FLAGS.max_gradient_norm)
-    ds = parallax.shard.shard(corpus())        # sharded after parallel_run assigns ids
-
-    def run(sess, num_workers, worker_id, num_replicas_per_worker):
-        t0, words = time.time(), 0
-        for step, (src, tin, tout, w) in enumerate(batches(ds)):
-            if step >= FLAGS.max_steps:
-                break
-            loss, gs, _ = sess.run(["loss", "global_step", "train_op"],
-                                   {"src": [src], "tgt_in": [tin], "tgt_out": [tout],
-                                    "tgt_weight": [w]})
-            words += int(w.sum())
-            if worker_id == 0 and (step + 1) % FLAGS.log_frequency == 0:
-                dt = time.time() - t0
-                parallax.log.info("global step %d  loss %.3f  wps %.0f", gs[0], loss[0],
-                                  words * num_workers / dt)
-                t0, words = time.time(), 0
-        sess.close()
-
-    sess, nw, wid, nrep = parallax.parallel_run(
-        graph, FLAGS.resource_info_file, sync=FLAGS.sync,
-        parallax_config=parallax_config.build_config(FLAGS))
-    run(sess, nw, wid, nrep)
+    hp = build_hparams()
+    if FLAGS.inference_input_file:
+        return run_inference(hp)
+    cfg = parallax_config.build_config(FLAGS)
+    if cfg.ckpt_config.ckpt_dir is None:
+        cfg.ckpt_config = parallax.CheckPointConfig(
+            ckpt_dir=hp.out_dir, save_ckpt_steps=FLAGS.save_ckpt_steps or
+            10 * int(hp.steps_per_stats))
+    tr = nmt.train.train(hp, FLAGS.resource_info_file, cfg, sync=FLAGS.sync)
+    if tr.worker_id == 0:
+        parallax.log.info("final: dev/test ppl %s, scores %s", tr.final_ppl, tr.final_scores)
+        if hp.avg_ckpts:
+            nmt.train.avg_checkpoints(cfg.ckpt_config.ckpt_dir, hp.num_keep_ckpts)
+    tr.sess.close()
 
 
 if __name__ == "__main__":
