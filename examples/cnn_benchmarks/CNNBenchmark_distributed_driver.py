@@ -1,67 +1,65 @@
 """CNN benchmark driver (reference
 `examples/tf_cnn_benchmarks/CNNBenchmark_distributed_driver.py:50-91`,
-`benchmark_cnn.py:487-1014`): synthetic images, momentum/sgd/rmsprop, reports
-images/sec and steps/sec.
+`benchmark_cnn.py:487-1014`): every `tf_cnn_benchmarks` flag of the harness
+(`--model`, `--batch_size`, `--optimizer`, `--use_fp16`, `--data_dir`, `--eval`,
+…) plus the Parallax flags; reports images/sec and steps/sec.
 
+    # synthetic ImageNet-shaped data, ResNet-50, AR mode, bf16, 8 GPUs
     python examples/cnn_benchmarks/CNNBenchmark_distributed_driver.py --model resnet50 \
-        --run_option MPI --compute_dtype bf16 --resource_info_file localhost:0,1,2,3
+        --optimizer momentum --use_fp16 --run_option MPI \
+        --resource_info_file localhost:0,1,2,3,4,5,6,7
+    # CIFAR-10 from disk, evaluation of the checkpoint in --ckpt_dir
+    python examples/cnn_benchmarks/CNNBenchmark_distributed_driver.py --model resnet56 \
+        --data_dir /data/cifar-10-batches-py --data_name cifar10 --eval --ckpt_dir /tmp/ck
 """
 import argparse
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-import torch
 
 import parallax_b200 as parallax
-from parallax_b200.models import cnn
+from parallax_b200.models.cnn_benchmarks import benchmark_cnn
 import parallax_config
 
-ap = parallax_config.add_flags(argparse.ArgumentParser())
-ap.add_argument("--model", default="resnet50", choices=sorted(cnn.MODELS))
-ap.add_argument("--batch_size", type=int, default=64)
-ap.add_argument("--optimizer", default="momentum", choices=["momentum", "sgd", "rmsprop"])
-ap.add_argument("--learning_rate", type=float, default=0.01)
-ap.add_argument("--num_classes", type=int, default=1000)
-ap.add_argument("--max_steps", type=int, default=500)
-ap.add_argument("--log_frequency", type=int, default=50)
-ap.add_argument("--params_stat", action="store_true",
-                help="print total parameter/gradient element counts")
+ap = parallax_config.add_flags(argparse.ArgumentParser(conflict_handler="resolve"))
+benchmark_cnn.add_arguments(ap)          # its --cuda_graph (default on) replaces the shared flag
+ap.add_argument("--max_steps", type=int, default=None, help="alias of --num_batches")
+ap.add_argument("--log_frequency", type=int, default=None, help="alias of --display_every")
+ap.set_defaults(run_option="MPI", model="resnet50")
 FLAGS = ap.parse_args()
 
 
 def main():
-    model = cnn.get_model(FLAGS.model, FLAGS.num_classes)
-    graph = cnn.cnn_graph(model, FLAGS.optimizer, FLAGS.learning_rate)
-    hw = cnn.image_size(model)
-
-    def run(sess, num_workers, worker_id, num_replicas_per_worker):
-        if FLAGS.params_stat and worker_id == 0:
-            n = sum(v.numel for v in sess.engine.analysis.variables.values())
-            parallax.log.info("total parameters / gradient elements: %d", n)
-        images = torch.randn(FLAGS.batch_size, 3, hw, hw)
-        labels = torch.randint(0, FLAGS.num_classes, (FLAGS.batch_size,))
-        if torch.cuda.is_available():
-            images, labels = images.pin_memory(), labels.pin_memory()
-        start = time.time()
-        for step in range(FLAGS.max_steps):
-            loss, _ = sess.run(["loss", "train_op"],
-                               feed_dict={"images": [images], "labels": [labels]})
-            if (step + 1) % FLAGS.log_frequency == 0 and worker_id == 0:
-                dt = time.time() - start
-                start = time.time()
-                sps = FLAGS.log_frequency / dt
-                parallax.log.info("step %d  loss %.3f  %.2f steps/sec  %.1f images/sec (total)",
-                                  step + 1, loss[0], sps,
-                                  sps * FLAGS.batch_size * num_workers)
-        sess.close()
-
-    sess, num_workers, worker_id, num_replicas_per_worker = parallax.parallel_run(
-        graph, FLAGS.resource_info_file, sync=FLAGS.sync,
-        parallax_config=parallax_config.build_config(FLAGS))
-    run(sess, num_workers, worker_id, num_replicas_per_worker)
+    if FLAGS.max_steps:
+        FLAGS.num_batches = FLAGS.max_steps
+    if FLAGS.log_frequency:
+        FLAGS.display_every = FLAGS.log_frequency
+    if FLAGS.compute_dtype in ("bf16", "bfloat16"):
+        FLAGS.use_fp16 = True
+    bench = benchmark_cnn.BenchmarkCNN(benchmark_cnn.make_params_from_flags(FLAGS))
+    cfg = parallax_config.build_config(FLAGS)
+    sc = dict(cfg.sess_config or {})
+    sc.update(bench.sess_config())
+    cfg.sess_config = sc
+    if FLAGS.checkpoint_dir and not cfg.ckpt_config.ckpt_dir:
+        cfg.ckpt_config = parallax.CheckPointConfig(ckpt_dir=FLAGS.checkpoint_dir)
+    # the LR schedule of the reference depends on the GLOBAL batch; the resource spec
+    # gives the worker count before parallel_run re-executes this script per worker
+    from parallax_b200.resource import parse_resource_info, worker_layout
+    try:
+        nw = len(worker_layout(parse_resource_info(FLAGS.resource_info_file,
+                                                   cfg.normalized_run_option())))
+    except Exception:
+        nw = int(os.environ.get("WORLD_SIZE", "1"))
+    graph = bench.build_graph(num_workers=nw)
+    sess, num_workers, worker_id, _ = parallax.parallel_run(
+        graph, FLAGS.resource_info_file, sync=FLAGS.sync, parallax_config=cfg)
+    res = bench.run(sess, num_workers, worker_id)
+    if worker_id == 0:
+        parallax.log.info("result: %s", res)
+    sess.close()
 
 
 if __name__ == "__main__":

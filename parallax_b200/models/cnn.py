@@ -262,20 +262,69 @@ class _CifarBlock(nn.Module):
         return F.relu(y + (x if self.short is None else self.short(x)))
 
 
+class _CifarPreActBlock(nn.Module):
+    """v2 (pre-activation) basic block: BN-ReLU-conv ×2, identity added unactivated"""
+
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.b1, self.c1 = nn.BatchNorm2d(cin), nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.b2, self.c2 = nn.BatchNorm2d(cout), nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.short = None if stride == 1 and cin == cout else \
+            nn.Conv2d(cin, cout, 1, stride, bias=False)
+
+    def forward(self, x):
+        pre = F.relu(self.b1(x))
+        y = self.c2(F.relu(self.b2(self.c1(pre))))
+        return y + (x if self.short is None else self.short(pre))
+
+
 class CifarResNet(_Classifier):
-    """resnet20/32/44/56/110 for CIFAR-10 (`models/resnet_model.py` cifar variants)."""
+    """resnet20/32/44/56/110 (+ `_v2` pre-activation variants) for CIFAR-10
+    (`models/resnet_model.py:283-371`)."""
     image_size = 32
 
-    def __init__(self, depth=20, num_classes=10):
+    def __init__(self, depth=20, num_classes=10, v2=False):
         super().__init__()
         n = (depth - 2) // 6
-        layers, cin = [nn.Conv2d(3, 16, 3, 1, 1, bias=False), nn.BatchNorm2d(16), nn.ReLU()], 16
+        block = _CifarPreActBlock if v2 else _CifarBlock
+        layers = [nn.Conv2d(3, 16, 3, 1, 1, bias=False)]
+        if not v2:
+            layers += [nn.BatchNorm2d(16), nn.ReLU()]
+        cin = 16
         for cout, stride in ((16, 1), (32, 2), (64, 2)):
             for i in range(n):
-                layers.append(_CifarBlock(cin, cout, stride if i == 0 else 1))
+                layers.append(block(cin, cout, stride if i == 0 else 1))
                 cin = cout
+        if v2:
+            layers += [nn.BatchNorm2d(64), nn.ReLU()]
         self.net = nn.Sequential(*layers, nn.AdaptiveAvgPool2d(1), nn.Flatten(),
                                  nn.Linear(64, num_classes))
+
+
+class AlexNetCifar(_Classifier):
+    """`models/alexnet_model.py:56-86` AlexnetCifar10Model: two 5×5 conv + LRN + pool
+    stages, fully connected 384 → 192 → classes"""
+    image_size = 32
+
+    def __init__(self, num_classes=10):
+        super().__init__()
+        self.net = nn.Sequential(
+            nn.Conv2d(3, 64, 5, padding=2), nn.ReLU(), nn.MaxPool2d(3, 2, 1),
+            nn.LocalResponseNorm(9, alpha=0.001, beta=0.75, k=1.0),
+            nn.Conv2d(64, 64, 5, padding=2), nn.ReLU(),
+            nn.LocalResponseNorm(9, alpha=0.001, beta=0.75, k=1.0), nn.MaxPool2d(3, 2, 1),
+            nn.Flatten(), nn.Linear(64 * 8 * 8, 384), nn.ReLU(), nn.Linear(384, 192), nn.ReLU(),
+            nn.Linear(192, num_classes))
+
+
+class TrivialCifar(_Classifier):
+    """`models/trivial_model.py:33-45`"""
+    image_size = 32
+
+    def __init__(self, num_classes=10):
+        super().__init__()
+        self.net = nn.Sequential(nn.Flatten(), nn.Linear(3 * 32 * 32, 1), nn.ReLU(),
+                                 nn.Linear(1, 4096), nn.ReLU(), nn.Linear(4096, num_classes))
 
 
 class _DenseLayer(nn.Module):
@@ -314,6 +363,12 @@ MODELS.update({
     "resnet20": lambda n=10: CifarResNet(20, n), "resnet32": lambda n=10: CifarResNet(32, n),
     "resnet44": lambda n=10: CifarResNet(44, n), "resnet56": lambda n=10: CifarResNet(56, n),
     "resnet110": lambda n=10: CifarResNet(110, n),
+    "resnet20_v2": lambda n=10: CifarResNet(20, n, True),
+    "resnet32_v2": lambda n=10: CifarResNet(32, n, True),
+    "resnet44_v2": lambda n=10: CifarResNet(44, n, True),
+    "resnet56_v2": lambda n=10: CifarResNet(56, n, True),
+    "resnet110_v2": lambda n=10: CifarResNet(110, n, True),
+    "alexnet_cifar": AlexNetCifar, "trivial_cifar": TrivialCifar,
     "densenet40_k12": lambda n=10: CifarDenseNet(40, 12, n),
     "densenet100_k12": lambda n=10: CifarDenseNet(100, 12, n),
     "densenet100_k24": lambda n=10: CifarDenseNet(100, 24, n),
