@@ -102,7 +102,8 @@ def get_learning_rate(params, num_examples_per_epoch, model, batch_size):
     base = float(params.learning_rate)
     if params.num_epochs_per_decay > 0 and params.learning_rate_decay_factor > 0:
         every = max(int(steps_per_epoch * params.num_epochs_per_decay), 1)
-        factor, floor = float(params.learning_rate_decay_factor), float(params.minimum_learning_rate)
+        factor = float(params.learning_rate_decay_factor)
+        floor = float(params.minimum_learning_rate)
 
         def lr(step):
             return max(base * factor ** (max(int(step) - 1, 0) // every), floor)

@@ -82,7 +82,8 @@ class RecordLoader(object):
             raise ValueError("Found no input files matching %s" % (files,))
         self.kind, self.num_threads, self.shuffle = kind, int(num_threads), bool(shuffle)
         self.capacity = int(capacity)
-        self.min_after = int(0.6 * capacity) if min_after_dequeue is None else int(min_after_dequeue)
+        self.min_after = int(0.6 * capacity if min_after_dequeue is None
+                             else min_after_dequeue)
         self.seed, self.epochs, self.shard = int(seed), int(epochs or 0), shard
         if shard is not None and num_shards is None:
             num_shards, shard_id = _shard._get_or_create_num_shards_and_shard_id()
