@@ -492,9 +492,18 @@ class DistributedOptimizer(object):
     them with the fabric kernels; sparse gradients are all-gathered unless
     `sparse_as_dense` (`horovod/tensorflow/__init__.py:189-192`)."""
 
-    def __init__(self, optimizer, named_parameters=None, sparse_as_dense=False):
+    def __init__(self, optimizer, named_parameters=None, sparse_as_dense=False,
+                 compression=None, backward_passes_per_step=1):
         self.optimizer = optimizer
         self.sparse_as_dense = sparse_as_dense
+        # `compression`: gradients travel in the compressed dtype
+        # (`horovod/torch/compression.py`); `backward_passes_per_step`: gradients of
+        # that many backward passes accumulate locally in `.grad` and are reduced
+        # once, by the `step()` that follows the last pass
+        self.compression = compression
+        self.backward_passes_per_step = int(backward_passes_per_step)
+        assert self.backward_passes_per_step >= 1
+        self._passes = 0
         params = [p for g in optimizer.param_groups for p in g["params"]]
         if named_parameters is not None:
             names = {id(p): n for n, p in named_parameters}
@@ -513,8 +522,15 @@ class DistributedOptimizer(object):
         by_dtype = {}
         for p in dense:
             by_dtype.setdefault(p.grad.dtype, []).append(p)
+        comp = self.compression if self.compression is not None and \
+            self.compression is not Compression.none else None
         for dt, ps in by_dtype.items():
-            outs = grouped_allreduce([p.grad for p in ps], average=True)
+            if comp is None:
+                outs = grouped_allreduce([p.grad for p in ps], average=True)
+            else:
+                packed = [comp.compress(p.grad) for p in ps]
+                red = grouped_allreduce([c for c, _ in packed], average=True)
+                outs = [comp.decompress(r, ctx) for r, (_, ctx) in zip(red, packed)]
             for p, o in zip(ps, outs):
                 p.grad.copy_(o)
         for p in self._params:
@@ -526,6 +542,12 @@ class DistributedOptimizer(object):
         self._synchronized = True
 
     def step(self, closure=None):
+        """With `backward_passes_per_step` = N only every N-th call reduces and
+        applies; the calls in between return None and keep accumulating."""
+        self._passes += 1
+        if self._passes < self.backward_passes_per_step:
+            return None
+        self._passes = 0
         if not self._synchronized:
             self.synchronize()
         self._synchronized = False
@@ -536,3 +558,100 @@ class DistributedOptimizer(object):
 
     def __getattr__(self, k):
         return getattr(self.optimizer, k)
+
+
+# --------------------------------------------------- more of the Horovod surface
+def mpi_threads_supported():
+    """Horovod reports whether MPI was initialised with MPI_THREAD_MULTIPLE
+    (`horovod/common/operations.cc:1675-1680`).  There is no MPI here: ops are
+    stream-ordered launches that any thread may issue, provided all ranks issue
+    them in the same order."""
+    _st()
+    return True
+
+
+def broadcast_object(obj, root_rank=0):
+    """pickle-able python object from `root_rank` to everyone"""
+    return _st().comm.broadcast_object(obj, root_rank)
+
+
+def broadcast_optimizer_state(optimizer, root_rank=0):
+    """Broadcast a ``torch.optim.Optimizer``'s state (slot tensors, step counters,
+    hyper-parameters in `param_groups`) from `root_rank`
+    (`horovod/torch/__init__.py` `broadcast_optimizer_state`).  State that does not
+    exist yet on a rank (fresh optimizer) is created from the root's layout."""
+    if isinstance(optimizer, DistributedOptimizer):
+        optimizer = optimizer.optimizer
+    st = _st()
+    sd = optimizer.state_dict()
+    # scalars / structure travel as one object; tensors with the tensor broadcast
+    meta = {"param_groups": sd["param_groups"],
+            "state": {k: {n: (("T", tuple(v.shape), str(v.dtype)) if torch.is_tensor(v) else
+                              ("V", v)) for n, v in d.items()}
+                      for k, d in sd["state"].items()}}
+    meta = st.comm.broadcast_object(meta, root_rank)
+    new_state = {}
+    for k, d in sorted(meta["state"].items(), key=lambda kv: str(kv[0])):
+        new_state[k] = {}
+        for n, desc in sorted(d.items()):
+            if desc[0] == "V":
+                new_state[k][n] = desc[1]
+                continue
+            have = sd["state"].get(k, {}).get(n)
+            dtype = getattr(torch, desc[2].split(".")[-1])
+            if have is None or tuple(have.shape) != desc[1]:
+                ref = optimizer.param_groups[0]["params"][0]
+                have = torch.zeros(desc[1], dtype=dtype, device=ref.device)
+            t = have.detach().clone()
+            broadcast_(t, root_rank, name="opt_state.%s.%s" % (k, n))
+            new_state[k][n] = t
+    optimizer.load_state_dict({"state": new_state, "param_groups": meta["param_groups"]})
+
+
+def allreduce_gradients(params, average=True, compression=None, sparse_as_dense=False):
+    """Reduce the `.grad` of `params` in place (fused per dtype).  The building
+    block of `DistributedGradientTape`."""
+    params = [p for p in params if p.grad is not None]
+    dense = [p for p in params if not p.grad.is_sparse]
+    by_dtype = {}
+    for p in dense:
+        by_dtype.setdefault(p.grad.dtype, []).append(p)
+    comp = compression if compression is not None and compression is not Compression.none \
+        else None
+    for ps in by_dtype.values():
+        if comp is None:
+            outs = grouped_allreduce([p.grad for p in ps], average=average)
+        else:
+            packed = [comp.compress(p.grad) for p in ps]
+            red = grouped_allreduce([c for c, _ in packed], average=average)
+            outs = [comp.decompress(r, ctx) for r, (_, ctx) in zip(red, packed)]
+        for p, o in zip(ps, outs):
+            p.grad.copy_(o)
+    for i, p in enumerate(params):
+        if p.grad.is_sparse:
+            p.grad = allreduce(p.grad.to_dense(), average) if sparse_as_dense else \
+                allreduce(p.grad, average, name=None)
+
+
+class DistributedGradientTape(object):
+    """`horovod/tensorflow/__init__.py:242-316`: a gradient "tape" whose
+    `gradient(target, sources)` returns gradients already averaged over the
+    ranks.  The torch counterpart wraps `torch.autograd.grad`."""
+
+    def __init__(self, compression=None, sparse_as_dense=False):
+        self.compression, self.sparse_as_dense = compression, sparse_as_dense
+
+    def gradient(self, target, sources, retain_graph=False):
+        sources = list(sources)
+        grads = torch.autograd.grad(target, sources, retain_graph=retain_graph,
+                                    allow_unused=True)
+        out = []
+        for i, g in enumerate(grads):
+            if g is None:
+                out.append(None)
+            elif g.is_sparse:
+                out.append(allreduce(g.to_dense(), True) if self.sparse_as_dense
+                           else allreduce(g, True))
+            else:
+                out.append(allreduce(g, True, compression=self.compression))
+        return out

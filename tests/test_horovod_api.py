@@ -1,0 +1,141 @@
+"""More of Horovod's user API on the host fabric (gloo, world_size 2):
+`DistributedOptimizer(compression, backward_passes_per_step)`,
+`broadcast_optimizer_state`, `DistributedGradientTape`, `allreduce_gradients`, and the
+Keras-style callbacks (`horovod/test/test_torch.py`, `test_keras.py` — SURVEY §4)."""
+import numpy as np
+import torch
+
+from tests.dist_utils import run_distributed
+
+
+def _worker(rank, world):
+    import torch
+    from parallax_b200 import callbacks as cbs
+    from parallax_b200 import collectives as hvd
+    hvd.init()
+    out = {}
+    assert hvd.mpi_threads_supported() and hvd.broadcast_object({"r": rank}, 1) == {"r": 1}
+
+    # ---- DistributedOptimizer: gradient accumulation + fp16 compression ------------
+    torch.manual_seed(0)
+    model = torch.nn.Linear(4, 2)
+    opt = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9),
+                                   named_parameters=model.named_parameters(),
+                                   compression=hvd.Compression.fp16, backward_passes_per_step=2)
+    w0 = model.weight.detach().clone()
+    xs = [torch.full((3, 4), float(rank + 1)), torch.full((3, 4), float(rank + 3))]
+    model(xs[0]).sum().backward()
+    assert opt.step() is None and torch.equal(model.weight, w0)        # still accumulating
+    model(xs[1]).sum().backward()
+    opt.step()
+    # gradient of sum(Wx+b) wrt W = Σ_rows x; accumulated over 2 passes, averaged over ranks
+    per_rank = [3.0 * ((r + 1) + (r + 3)) for r in range(world)]
+    want = w0 - 0.1 * (sum(per_rank) / world)
+    out["accum_ok"] = bool(torch.allclose(model.weight, want, atol=1e-2))
+    opt.zero_grad()
+
+    # ---- broadcast_optimizer_state: fresh optimizer on rank 1 gets rank 0's state ---
+    torch.manual_seed(rank)
+    m2 = torch.nn.Linear(3, 3)
+    o2 = torch.optim.Adam(m2.parameters(), lr=0.01 * (rank + 1))
+    if rank == 0:
+        for _ in range(3):
+            m2(torch.randn(2, 3)).sum().backward()
+            o2.step()
+            o2.zero_grad()
+    hvd.broadcast_parameters(m2.state_dict(), 0)
+    hvd.broadcast_optimizer_state(o2, 0)
+    sd = o2.state_dict()
+    out["opt_lr"] = sd["param_groups"][0]["lr"]
+    out["opt_step"] = float(sd["state"][0]["step"])
+    out["opt_exp_avg"] = sd["state"][0]["exp_avg"].clone()
+    out["m2_w"] = m2.weight.detach().clone()
+
+    # ---- DistributedGradientTape / allreduce_gradients ---------------------------------
+    w = torch.ones(3, requires_grad=True)
+    unused = torch.ones(2, requires_grad=True)
+    loss = (w * float(rank + 1)).sum()
+    g = hvd.DistributedGradientTape().gradient(loss, [w, unused])
+    out["tape"] = g[0].clone()
+    out["tape_unused_none"] = g[1] is None
+    emb = torch.nn.Embedding(6, 2, sparse=True)
+    emb(torch.tensor([rank, rank + 1])).sum().backward()
+    lin = torch.nn.Linear(2, 1)
+    lin(torch.full((1, 2), float(rank))).sum().backward()
+    hvd.allreduce_gradients(list(emb.parameters()) + list(lin.parameters()), average=False,
+                            sparse_as_dense=True)
+    out["emb_grad_rows"] = emb.weight.grad.sum(1).clone()
+    out["lin_grad"] = lin.weight.grad.clone()
+
+    # ---- callbacks ----------------------------------------------------------------------
+    torch.manual_seed(100 + rank)
+    net = torch.nn.Linear(2, 2)
+    sgd = torch.optim.SGD(net.parameters(), lr=0.4, momentum=0.9)
+    cl = cbs.CallbackList([cbs.BroadcastGlobalVariablesCallback(0), cbs.MetricAverageCallback(),
+                           cbs.LearningRateWarmupCallback(warmup_epochs=2, steps_per_epoch=4),
+                           cbs.LearningRateScheduleCallback(0.1, start_epoch=3)],
+                          model=net, optimizer=sgd)
+    cl.on_train_begin()
+    out["net_w"] = net.weight.detach().clone()
+    lrs = []
+    for epoch in range(5):
+        cl.on_epoch_begin(epoch)
+        for b in range(4):
+            cl.on_batch_begin(b)
+            lrs.append(sgd.param_groups[0]["lr"])
+            net(torch.ones(1, 2)).sum().backward()
+            sgd.step()
+            sgd.zero_grad()
+            cl.on_batch_end(b)
+        logs = {"loss": float(rank), "acc": 10.0 * rank}
+        cl.on_epoch_end(epoch, logs)
+        out["logs%d" % epoch] = dict(logs)
+    out["lrs"] = lrs
+    hvd.shutdown()
+    return out
+
+
+def test_horovod_surface_two_ranks():
+    r0, r1 = run_distributed(_worker, 2)
+    assert r0["accum_ok"] and r1["accum_ok"]
+    # rank 1's fresh Adam now mirrors rank 0's: hyper-parameters, step, slots, weights
+    assert r1["opt_lr"] == r0["opt_lr"] == 0.01 and r1["opt_step"] == r0["opt_step"] == 3.0
+    assert torch.equal(r0["opt_exp_avg"], r1["opt_exp_avg"]) and torch.equal(r0["m2_w"], r1["m2_w"])
+    for r in (r0, r1):
+        assert torch.allclose(r["tape"], torch.full((3,), 1.5)) and r["tape_unused_none"]
+        assert r["emb_grad_rows"].tolist() == [2.0, 4.0, 2.0, 0.0, 0.0, 0.0]   # rows 0,1 | 1,2
+        assert torch.allclose(r["lin_grad"], torch.full((1, 2), 1.0))          # 0 + 1
+    assert torch.equal(r0["net_w"], r1["net_w"])
+    # metrics averaged over the two workers
+    assert r0["logs0"]["loss"] == r1["logs0"]["loss"] == 0.5 and r0["logs4"]["acc"] == 5.0
+    lrs = np.array(r0["lrs"]).reshape(5, 4)
+    # warm-up: 1/size of the target at the start, linear per batch, exact target after it
+    assert abs(lrs[0, 0] - 0.2) < 1e-9 and np.all(np.diff(lrs[:2].reshape(-1)) > 0)
+    assert abs(lrs[1, 3] - 0.4 * 0.5 * (1.75 * 0.5 + 1)) < 1e-9
+    assert np.allclose(lrs[2], 0.4) and np.allclose(lrs[3:], 0.04)
+    assert abs(r0["logs3"]["lr"] - 0.04) < 1e-12
+
+
+def test_schedule_callback_momentum_correction_single_process():
+    from parallax_b200 import callbacks as cbs
+    from parallax_b200 import collectives as hvd
+    hvd.init()
+    try:
+        net = torch.nn.Linear(2, 1)
+        sgd = torch.optim.SGD(net.parameters(), lr=1.0, momentum=0.5)
+        net(torch.ones(1, 2)).sum().backward()
+        sgd.step()
+        buf = sgd.state[net.weight]["momentum_buffer"].clone()
+        cb = cbs.LearningRateScheduleCallback(lambda e: 0.5 ** e, momentum_correction=True)
+        cb.set_context(net, sgd)
+        cb.on_train_begin()
+        cb.on_epoch_begin(2)
+        assert sgd.param_groups[0]["lr"] == 0.25
+        assert torch.allclose(sgd.state[net.weight]["momentum_buffer"], buf * 0.25)
+        import pytest
+        with pytest.raises(ValueError):
+            cbs.LearningRateScheduleCallback(1.0, staircase=False)
+        with pytest.raises(AttributeError):
+            cbs.CallbackList([]).no_such_hook
+    finally:
+        hvd.shutdown()
