@@ -19,7 +19,6 @@ import time
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from ... import optim
 from ...graph import Graph, ScaleGradients

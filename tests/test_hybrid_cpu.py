@@ -1,6 +1,5 @@
 """BASELINE config 1: 2-layer MLP + tiny embedding, CPU/gloo world_size=2 —
 plumbing, dense/sparse routing and aggregation semantics."""
-import copy
 
 import numpy as np
 import pytest

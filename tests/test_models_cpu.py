@@ -1,7 +1,6 @@
 """Model-level checks on the host fabric: the LM1B training graph (clip, scale,
 EMA, sampled softmax, partitioned tables) learns; every example model builds and
 takes a step; the unique log-uniform sampler has the right law."""
-import math
 
 import numpy as np
 import pytest

@@ -11,7 +11,6 @@ encoder/attention/architecture combination builds and steps),
 import math
 import os
 
-import numpy as np
 import pytest
 import torch
 
