@@ -136,12 +136,14 @@ class NVDenseGroup(object):
         # NVLS: bucket buffers bound to an NVSwitch multicast object, the fused
         # kernel then reduces with multimem.ld_reduce and broadcasts parameters
         # with multimem.st.  Measured (profiles/allreduce_sweep_8gpu.json): wins
-        # from 256 KB up at 8 GPUs, loses at 2 — "auto" enables it for world >= 4.
+        # from 256 KB up at 8 GPUs, loses at 2.  "auto" enables it on the
+        # configuration it was validated and measured on (a full 8-GPU box; the
+        # end-to-end gain there is ~1 %); `dense_nvls=True` forces it for 4..7.
         want = self.options.get("dense_nvls", "auto")
         self.nvls = False
         if W > 1 and self.update == "sharded" and not self.pull_mirrors and want:
             from . import multicast
-            if want is True or (want == "auto" and W >= 4):
+            if want is True or (want == "auto" and W >= 8):
                 try:
                     self.nvls = multicast.supported(self.fabric.comm)
                 except Exception:
