@@ -96,11 +96,19 @@ class _HostTableAdapter(object):
 
 
 def _set_submodule(root, path, new):
+    """Replace the module at `path` — and every other attribute that refers to the
+    same module object (tied embeddings, e.g. NMT `share_vocab`) — by `new`."""
     parts = path.split(".")
     parent = root
     for p in parts[:-1]:
         parent = getattr(parent, p)
+    old = getattr(parent, parts[-1])
     setattr(parent, parts[-1], new)
+    if isinstance(old, tnn.Module):
+        for m in root.modules():
+            for name, child in list(m._modules.items()):
+                if child is old:
+                    m._modules[name] = new
 
 
 class TrainEngine(object):

@@ -474,3 +474,33 @@ def test_gnmt_trains_through_parallax_and_averages_checkpoints(tmp_path):
         assert nmt.train.avg_checkpoints(ck, 5) is None
     finally:
         tr.sess.close()
+
+
+def test_shared_vocabulary_is_one_table_in_the_engine():
+    """`share_vocab`: encoder and decoder use ONE embedding module; the engine must
+    replace every alias by the same sharded table and train it from both uses."""
+    torch.manual_seed(0)
+    hp = _hp(share_vocab=True, attention="luong", encoder_type="uni", num_layers=1,
+             num_embeddings_partitions=2, learning_rate=0.5)
+    m = nmt.create_model(hp)
+    sess, *_ = parallax.parallel_run(nmt.nmt_graph(m, hp), "localhost",
+                                     parallax_config=parallax.Config(
+                                         search_partitions=False, sess_config={"fabric": "host"}))
+    try:
+        assert sorted(sess.engine.tables) == ["embedding_encoder.weight"]
+        assert m.embedding_encoder is m.embedding_decoder
+        assert type(m.embedding_encoder).__name__ == "ShardedEmbedding"
+        src, tin, tout, sl, tl = _batch()
+        feed = {"source": [src], "target_input": [tin], "target_output": [tout],
+                "source_sequence_length": [sl], "target_sequence_length": [tl]}
+        w0 = sess.engine.tables["embedding_encoder.weight"].full_weight().clone()
+        losses = [sess.run(["loss", "train_op"], feed)[0][0] for _ in range(25)]
+        assert losses[-1] < losses[0] - 1.0
+        w1 = sess.engine.tables["embedding_encoder.weight"].full_weight()
+        moved = (w1 - w0).abs().sum(1) > 0
+        # rows used only by the source side and rows used only by the target side both moved
+        only_src = set(src.reshape(-1).tolist()) - set(tin.reshape(-1).tolist())
+        only_tgt = set(tin[:, :2].reshape(-1).tolist()) - set(src.reshape(-1).tolist())
+        assert all(moved[i] for i in only_tgt) and any(moved[i] for i in only_src)
+    finally:
+        sess.close()
