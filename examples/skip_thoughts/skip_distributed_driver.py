@@ -40,6 +40,8 @@ ap.add_argument("--learning_rate", type=float, default=0.0008)
 ap.add_argument("--learning_rate_decay_factor", type=float, default=0.5)
 ap.add_argument("--learning_rate_decay_steps", type=int, default=400000)
 ap.add_argument("--clip_gradient_norm", type=float, default=5.0)
+ap.add_argument("--max_len", type=int, default=31,
+                help="longest sentence incl. <eos> (preprocess_dataset --max_sentence_length+1)")
 ap.add_argument("--max_steps", type=int, default=500000)
 ap.add_argument("--log_frequency", type=int, default=100)
 FLAGS = ap.parse_args()
@@ -85,6 +87,11 @@ def main():
     if cfg.ckpt_config.ckpt_dir is None:
         cfg.ckpt_config = parallax.CheckPointConfig(ckpt_dir=FLAGS.train_dir,
                                                     save_ckpt_secs=tc.save_model_secs)
+    # three lookups per step (encode, previous, next) of at most max_len ids each; the
+    # NVLink fabric sizes a table's receive rings once, at the first step
+    sc = dict(cfg.sess_config or {})
+    sc.setdefault("sparse_capacity", {"word_embedding.weight": 3 * mc.batch_size * FLAGS.max_len})
+    cfg.sess_config = sc
     sess, num_workers, worker_id, _ = parallax.parallel_run(
         graph, FLAGS.resource_info_file, sync=FLAGS.sync, parallax_config=cfg)
     t0 = time.time()

@@ -85,6 +85,28 @@ def avg_checkpoints(ckpt_dir, num_last_checkpoints, out_dir=None):
     return os.path.join(out_dir, name)
 
 
+def sparse_capacity(hp):
+    """Upper bound of gradient rows per step for each embedding table — on the
+    NVLink fabric the receive rings of a sparse table are sized once, at the first
+    step, and NMT batches vary in length (`sess_config["sparse_capacity"]`)."""
+    src = hp.batch_size * int(hp.src_max_len or 100)
+    tgt = hp.batch_size * (int(hp.tgt_max_len or 100) + 1)
+    if hp.share_vocab:
+        return {"embedding_encoder.weight": src + tgt}
+    return {"embedding_encoder.weight": src, "embedding_decoder.weight": tgt}
+
+
+def with_sparse_capacity(config, hp):
+    """copy of `config` whose sess_config carries `sparse_capacity(hp)` unless the
+    user set one"""
+    import copy
+    cfg = copy.copy(config)
+    sc = dict(cfg.sess_config) if isinstance(cfg.sess_config, dict) else {}
+    sc.setdefault("sparse_capacity", sparse_capacity(hp))
+    cfg.sess_config = sc
+    return cfg
+
+
 class Trainer(object):
     """Drives one worker's session; see `train()`."""
 
@@ -267,6 +289,7 @@ def train(hp, resource_info="localhost", parallax_config=None, sync=True,
     graph = nmt_graph(model, hp)
     src_vocab, tgt_vocab = vocab_utils.create_vocab_tables(
         hp.src_vocab_file, hp.tgt_vocab_file, hp.share_vocab)
+    parallax_config = with_sparse_capacity(parallax_config or parallax.Config(), hp)
     sess, num_workers, worker_id, _ = parallax.parallel_run(
         graph, resource_info, sync=sync, parallax_config=parallax_config)
     tr = Trainer(hp, sess, num_workers, worker_id, model, src_vocab, tgt_vocab)
