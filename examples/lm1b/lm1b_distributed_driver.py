@@ -22,6 +22,13 @@ from data_utils import Vocabulary, Dataset
 
 ap = parallax_config.add_flags(argparse.ArgumentParser())
 ap.add_argument("--datadir", default=None)
+ap.add_argument("--logdir", default="/tmp/lm1b", help="logging directory (analysis reports)")
+ap.add_argument("--hpconfig", default="",
+                help="override hyper-parameters: name=value,... (batch_size, num_steps, "
+                     "learning_rate, max_grad_norm, keep_prob, num_sampled, emb_size, state_size, "
+                     "projected_size, vocab_size, num_variable_shards)")
+ap.add_argument("--save_n_ckpts_per_epoch", type=int, default=-1,
+                help="checkpoints per epoch of the 1B-word corpus (overrides save_ckpt_steps)")
 ap.add_argument("--use_synthetic", action="store_true")
 ap.add_argument("--batch_size", type=int, default=128)
 ap.add_argument("--num_steps", type=int, default=20)
@@ -34,10 +41,32 @@ ap.add_argument("--vocab_size", type=int, default=793470)
 ap.add_argument("--tiny", action="store_true", help="small model for smoke runs")
 FLAGS = ap.parse_args()
 
+NUM_TRAIN_WORDS = 798945280          # words in the 1B-word training shards
+
+MODEL_HP = {"keep_prob": float, "num_sampled": int, "emb_size": int, "state_size": int,
+            "projected_size": int}
+
+
+def apply_hpconfig():
+    """`--hpconfig a=1,b=2` (reference `language_model_graph.py` hps.parse)"""
+    model_kw = {}
+    for item in filter(None, (x.strip() for x in FLAGS.hpconfig.split(","))):
+        k, _, v = item.partition("=")
+        if k in MODEL_HP:
+            model_kw[k] = MODEL_HP[k](v)
+        elif hasattr(FLAGS, k):
+            cur = getattr(FLAGS, k)
+            setattr(FLAGS, k, type(cur)(v) if cur is not None else v)
+        else:
+            raise ValueError("unknown hyper-parameter %r in --hpconfig" % k)
+    return model_kw
+
 
 def main():
+    model_kw = apply_hpconfig()
     kw = dict(vocab_size=FLAGS.vocab_size, num_steps=FLAGS.num_steps,
               num_shards=FLAGS.num_variable_shards, lazy=True)
+    kw.update(model_kw)
     if FLAGS.tiny:
         kw.update(vocab_size=min(FLAGS.vocab_size, 10000), emb_size=32, state_size=64,
                   projected_size=32, num_sampled=64, lazy=False)
@@ -76,15 +105,27 @@ def main():
             if local_step % FLAGS.log_frequency == 0:
                 now = time.time()
                 gs = fetched["global_step"][0]
-                wps = (gs - prev_step) * B * T * num_workers / max(now - prev_time, 1e-9)
+                elapsed = max(now - prev_time, 1e-9)
+                wps = (gs - prev_step) * B * T * num_workers / elapsed
                 prev_step, prev_time = gs, now
                 parallax.log.info("Iteration %d, time = %.2fs, wps = %.0f, train loss = %.4f",
-                                  gs, now - prev_time, wps, fetched["loss"][0])
+                                  gs, elapsed, wps, fetched["loss"][0])
         sess.close()
 
+    cfg = parallax_config.build_config(FLAGS)
+    if cfg.export_graph_path is None:
+        cfg.export_graph_path = FLAGS.logdir
+    if FLAGS.save_n_ckpts_per_epoch > 0 and FLAGS.ckpt_dir:
+        # steps per epoch depend on the number of workers, known from the resource spec
+        from parallax_b200.resource import parse_resource_info, worker_layout
+        nw = len(worker_layout(parse_resource_info(FLAGS.resource_info_file,
+                                                   cfg.normalized_run_option())))
+        per_epoch = NUM_TRAIN_WORDS // (FLAGS.batch_size * FLAGS.num_steps * nw)
+        cfg.ckpt_config = parallax.CheckPointConfig(
+            ckpt_dir=FLAGS.ckpt_dir,
+            save_ckpt_steps=max(per_epoch // FLAGS.save_n_ckpts_per_epoch, 1))
     sess, num_workers, worker_id, num_replicas_per_worker = parallax.parallel_run(
-        single_gpu_graph, FLAGS.resource_info_file, sync=FLAGS.sync,
-        parallax_config=parallax_config.build_config(FLAGS))
+        single_gpu_graph, FLAGS.resource_info_file, sync=FLAGS.sync, parallax_config=cfg)
     run(sess, num_workers, worker_id, num_replicas_per_worker)
 
 

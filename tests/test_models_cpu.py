@@ -88,3 +88,34 @@ def test_ncf_and_bert_shapes_run():
     l = [sess.run(["loss", "train_op"], f)[0][0] for _ in range(10)]
     assert l[-1] < l[0] and sess.engine.run_option == "HYBRID"
     sess.close()
+
+
+def test_lm1b_vocabulary_and_dataset(tmp_path):
+    from parallax_b200.models.lm1b_data import Dataset, Vocabulary
+    (tmp_path / "vocab.txt").write_text("<S> 100\n<UNK> 50\nthe 40\ncat 30\nsat 20\nmat 10\n")
+    v = Vocabulary.from_file(str(tmp_path / "vocab.txt"))
+    assert (v.num_tokens, v.s_id, v.unk_id) == (6, 0, 1) and v.get_count("cat") == 30
+    assert v.get_id("dog") == 1 and v.get_token(3) == "cat"
+    assert Vocabulary.from_file(str(tmp_path / "vocab.txt"), num_tokens_limit=4).num_tokens == 4
+    # native and python tokenisation agree
+    line = "the  cat\tsat on the mat"
+    assert v.encode_line(line) == v.encode_line(line, native=False) == [0, 2, 3, 4, 1, 2, 5, 0]
+    for i, text in enumerate(["the cat sat\nthe mat\n", "cat sat\nmat the cat sat the\n"]):
+        (tmp_path / ("news-%05d" % i)).write_text(text)
+    ds = Dataset(v, str(tmp_path / "news-*"), deterministic=True)
+    batches = list(ds.iterate_once(2, 4))
+    x, y, w = batches[0]
+    # row 0 streams sentence 1 then continues with the next unread sentence
+    assert x[0].tolist() == [0, 2, 3, 4] and y[0].tolist() == [2, 3, 4, 0] and w[0].tolist() == [1] * 4
+    assert x[1].tolist() == [0, 2, 5, 0] and y[1].tolist() == [2, 5, 0, 3]
+    total = sum(int(b[2].sum()) for b in batches)
+    assert total == sum(len(s.split()) + 1 for s in
+                        ["the cat sat", "the mat", "cat sat", "mat the cat sat the"])
+    # files are split over workers; an empty share is an error, not a silent hang
+    assert [len(ds.files(2, k)) for k in (0, 1)] == [1, 1]
+    one = list(Dataset(v, str(tmp_path / "news-*"), deterministic=True).iterate_once(2, 4, 2, 1))
+    assert sum(int(b[2].sum()) for b in one) == 3 + 6
+    with pytest.raises(ValueError):
+        next(Dataset(v, str(tmp_path / "nothing-*")).iterate_forever(2, 4))
+    it = Dataset(v, str(tmp_path / "news-*"), seed=1).iterate_forever(2, 4)
+    assert all(next(it)[0].shape == (2, 4) for _ in range(12))      # wraps around epochs
