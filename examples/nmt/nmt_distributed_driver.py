@@ -46,6 +46,9 @@ ap.add_argument("--hparams", default="", help="name=value,... overrides")
 ap.add_argument("--num_train_steps", type=int, default=None)
 ap.add_argument("--steps_per_eval", type=int, default=None)
 ap.add_argument("--random_seed", type=int, default=None)
+ap.add_argument("--eval_only", action="store_true",
+                help="restore the latest checkpoint of out_dir / --ckpt_dir and run the internal "
+                     "(perplexity) and external (BLEU, …) evaluations — the reference's nmt_eval.py")
 # inference
 ap.add_argument("--inference_input_file", default=None)
 ap.add_argument("--inference_output_file", default=None)
@@ -122,10 +125,23 @@ def run_inference(hp):
     sess.close()
 
 
+def run_eval(hp):
+    """`nmt_eval.py:571-630` eval_fn: latest checkpoint → dev/test perplexity + scores"""
+    cfg = parallax_config.build_config(FLAGS)
+    cfg.ckpt_config = parallax.CheckPointConfig(ckpt_dir=FLAGS.ckpt_dir or hp.out_dir)
+    tr = nmt.train.train(hp, "localhost", cfg, num_train_steps=0, final_eval=True)
+    parallax.log.info("global step %d: dev/test ppl %s, scores %s", tr.sess.engine.global_step,
+                      tr.final_ppl, tr.final_scores)
+    tr.sess.close()
+    return tr
+
+
 def main():
     hp = build_hparams()
     if FLAGS.inference_input_file:
         return run_inference(hp)
+    if FLAGS.eval_only:
+        return run_eval(hp)
     cfg = parallax_config.build_config(FLAGS)
     if cfg.ckpt_config.ckpt_dir is None:
         cfg.ckpt_config = parallax.CheckPointConfig(

@@ -219,7 +219,7 @@ class Trainer(object):
     # -- training ---------------------------------------------------------------
     def train(self, num_train_steps=None, steps_per_eval=None):
         hp = self.hp
-        total = int(num_train_steps or hp.num_train_steps)
+        total = int(hp.num_train_steps if num_train_steps is None else num_train_steps)
         steps_per_stats = int(hp.steps_per_stats)
         steps_per_eval = int(steps_per_eval or hp.get("steps_per_eval") or 10 * steps_per_stats)
         steps_per_external = int(hp.get("steps_per_external_eval") or 5 * steps_per_eval)

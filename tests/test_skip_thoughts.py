@@ -258,3 +258,65 @@ def test_fit_linear_map_recovers_affine_map():
     assert np.allclose(w2, w, atol=1e-4) and np.allclose(b2, b, atol=1e-4)
     with pytest.raises(ValueError):
         st.vocabulary_expansion.expand_vocabulary(np.zeros((3, 2)), {"a": 0}, {"zzz": [1.0]})
+
+
+class _BagEncoder(object):
+    """deterministic stand-in for a trained encoder: hashed bag of words"""
+
+    def encode(self, data, use_norm=True, verbose=False, batch_size=128, use_eos=False):
+        out = np.zeros((len(data), 64), np.float32)
+        for i, s in enumerate(data):
+            for w in s.lower().split():
+                out[i, sum(map(ord, w)) % 64] += 1.0
+        return out / np.maximum(np.linalg.norm(out, axis=1, keepdims=True), 1e-9)
+
+
+def test_downstream_evaluation_protocols(tmp_path):
+    from parallax_b200.models.skip_thoughts import evaluate as ev
+    rng = np.random.RandomState(0)
+    good, bad = ["great", "fine", "lovely", "superb"], ["awful", "poor", "boring", "bad"]
+    filler = ["movie", "plot", "actor", "scene", "the", "a"]
+
+    def sent(words):
+        return " ".join(rng.choice(filler, 3).tolist() + rng.choice(words, 2).tolist())
+    (tmp_path / "custrev.pos").write_text("\n".join(sent(good) for _ in range(60)))
+    (tmp_path / "custrev.neg").write_text("\n".join(sent(bad) for _ in range(60)))
+    enc = _BagEncoder()
+    acc = ev.eval_nested_kfold(enc, "CR", str(tmp_path), k=3, scan=[1, 16])
+    assert acc > 0.9 and ev.evaluate(enc, "CR", str(tmp_path))["accuracy"] > 0.9
+    # TREC: coarse label = text before ':'
+    kinds = {"NUM": ["how", "many", "count"], "LOC": ["where", "city", "country"],
+             "HUM": ["who", "person", "name"]}
+    def trec(n):
+        return "\n".join("%s:x %s" % (k, " ".join(rng.choice(w, 3).tolist()))
+                         for _ in range(n) for k, w in kinds.items())
+    (tmp_path / "train_5500.label").write_text(trec(30))
+    (tmp_path / "TREC_10.label").write_text(trec(8))
+    assert ev.eval_trec(enc, str(tmp_path), k=3, scan=[1, 16]) > 0.9
+    # MSRP: paraphrase = same words reordered
+    def pair(same):
+        a = rng.choice(filler + good + bad, 5).tolist()
+        b = list(rng.permutation(a)) if same else rng.choice(filler + good + bad, 5).tolist()
+        return "%d\t1\t2\t%s\t%s" % (int(same), " ".join(a), " ".join(b))
+    for fn, n in (("msr_paraphrase_train.txt", 80), ("msr_paraphrase_test.txt", 30)):
+        (tmp_path / fn).write_text("Quality\tid1\tid2\ts1\ts2\n" +
+                                   "\n".join(pair(i % 2 == 0) for i in range(n)))
+    acc, f1 = ev.eval_msrp(enc, str(tmp_path), k=3, scan=[1, 16])
+    assert acc > 0.8 and f1 > 0.8
+    # SICK: relatedness grows with word overlap
+    def sick(i):
+        a = rng.choice(filler + good + bad, 6, replace=False).tolist()
+        keep = i % 6
+        b = a[:keep] + rng.choice(["zz1", "zz2", "zz3", "zz4", "zz5", "zz6"], 6 - keep,
+                                  replace=False).tolist()
+        return "%d\t%s\t%s\t%.1f\tNEUTRAL" % (i, " ".join(a), " ".join(b), 1 + 4 * keep / 5.0)
+    for fn, n in (("SICK_train.txt", 120), ("SICK_test_annotated.txt", 40)):
+        (tmp_path / fn).write_text("pair_ID\tA\tB\tscore\tjudgment\n" +
+                                   "\n".join(sick(i) for i in range(n)))
+    p, sp, mse = ev.eval_sick(enc, str(tmp_path))
+    assert p > 0.8 and sp > 0.8 and mse < 1.0
+    y = ev.encode_score_labels([1.0, 3.6, 5.0])
+    assert y[0].tolist() == [1, 0, 0, 0, 0] and np.allclose(y[1], [0, 0, 0.4, 0.6, 0])
+    assert y[2].tolist() == [0, 0, 0, 0, 1]
+    with pytest.raises(ValueError):
+        ev.evaluate(enc, "SST", str(tmp_path))
