@@ -1,0 +1,67 @@
+"""The example drivers as a user runs them: the script is the launcher AND the
+worker; two CPU workers (host fabric) are spawned from a two-line resource file."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(tmp_path, script, args, timeout=420):
+    res = tmp_path / "resource_info"
+    res.write_text("localhost\nlocalhost\n")
+    env = {k: v for k, v in os.environ.items()
+           if not k.startswith("PARALLAX_") and k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env.update(PARALLAX_FABRIC="host", CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    cmd = [sys.executable, os.path.join(ROOT, "examples", script), "--resource_info_file", str(res),
+           "--redirect_path", str(tmp_path / "logs")] + args
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout,
+                       cwd=str(tmp_path))
+    logs = {}
+    for i in (0, 1):
+        p = tmp_path / "logs" / ("log_worker%d_stderr" % i)
+        logs[i] = p.read_text() if p.exists() else ""
+    assert r.returncode == 0, (r.stderr[-1500:], logs[0][-1500:], logs[1][-1500:])
+    return logs
+
+
+def test_nmt_driver_two_workers(tmp_path):
+    logs = _run(tmp_path, "nmt/nmt_distributed_driver.py", [
+        "--synthetic", "--out_dir", str(tmp_path / "nmt"), "--num_train_steps", "24",
+        "--steps_per_eval", "12", "--save_ckpt_steps", "12", "--hparams",
+        "num_units=16,num_layers=2,batch_size=16,steps_per_stats=6,infer_batch_size=100,"
+        "num_embeddings_partitions=2,beam_width=2"])
+    assert "step 24" in logs[0] and "final: dev/test ppl" in logs[0]
+    assert "final: dev/test ppl" not in logs[1]             # only worker 0 reports
+    assert (tmp_path / "nmt" / "model.ckpt-24.pt").exists()
+    assert (tmp_path / "nmt" / "output_dev").read_text().count("\n") == 200
+
+
+def test_skip_thoughts_driver_two_workers(tmp_path):
+    logs = _run(tmp_path, "skip_thoughts/skip_distributed_driver.py", [
+        "--synthetic", "--train_dir", str(tmp_path / "st"), "--vocab_size", "100",
+        "--word_embedding_dim", "8", "--encoder_dim", "16", "--batch_size", "16",
+        "--num_embedding_partitions", "2", "--max_steps", "20", "--log_frequency", "10",
+        "--learning_rate", "0.01"])
+    assert "global step 20" in logs[0] and "global step" not in logs[1]
+
+
+@pytest.mark.parametrize("extra", [["--model", "lenet", "--optimizer", "momentum"],
+                                   ["--model", "trivial", "--forward_only"]])
+def test_cnn_driver_two_workers(tmp_path, extra):
+    logs = _run(tmp_path, "cnn_benchmarks/CNNBenchmark_distributed_driver.py", extra + [
+        "--batch_size", "4", "--num_batches", "6", "--num_warmup_batches", "2",
+        "--display_every", "3"])
+    assert "total images/sec" in logs[0] and "Batch size:  8 global / 4 per device" in logs[0]
+    assert "total images/sec" not in logs[1]
+
+
+def test_lm1b_and_simple_drivers_two_workers(tmp_path):
+    logs = _run(tmp_path, "lm1b/lm1b_distributed_driver.py", [
+        "--use_synthetic", "--tiny", "--max_steps", "11", "--log_frequency", "5", "--hpconfig",
+        "batch_size=8,num_steps=4,keep_prob=1.0", "--logdir", str(tmp_path / "lm1b")])
+    assert "Iteration 11" in logs[0] and (tmp_path / "lm1b" / "analysis_worker_1.json").exists()
+    logs = _run(tmp_path, "simple/simple_driver.py", [])
+    assert "learned" in logs[0] or "step" in logs[0]
