@@ -240,3 +240,40 @@ def test_div_partition_strategy_matches_mod_results():
         assert sess.engine.tables["emb.weight"].layout.strategy == strat
         sess.close()
     torch.testing.assert_close(outs[0], outs[1])
+
+
+def test_inspect_checkpoint_tool(tmp_path, capsys):
+    import io
+    from parallax_b200.models.lm1b import LM1B, lm1b_graph
+    from parallax_b200.tools import inspect_checkpoint as ic
+    torch.manual_seed(0)
+    m = LM1B(vocab_size=50, emb_size=8, state_size=16, projected_size=8, num_sampled=8,
+             num_steps=3, num_shards=2, keep_prob=1.0)
+    cfg = parallax.Config(sess_config={"fabric": "host"},
+                          ckpt_config=parallax.CheckPointConfig(ckpt_dir=str(tmp_path),
+                                                                save_ckpt_steps=2))
+    sess, *_ = parallax.parallel_run(lm1b_graph(m, batch_size=4), "localhost", parallax_config=cfg)
+    x = torch.randint(0, 50, (4, 3))
+    for _ in range(2):
+        sess.run(["loss", "train_op"], {"x": [x], "y": [x]})
+    sess.close()
+    path, sd = ic.load(str(tmp_path))
+    assert path.endswith("model.ckpt-2.pt")
+    kinds = {(k, n) for k, n, _ in ic.entries(sd)}
+    assert ("dense", "W") in kinds and ("dense-ema", "W_P") in kinds
+    assert ("sparse", "emb.weight") in kinds and ("sparse-slot0", "softmax_w.weight") in kinds
+    buf = io.StringIO()
+    total = ic.summarize(sd, buf)
+    assert "global_step: 2" in buf.getvalue() and total > 0
+    plain, ema = ic.to_state_dict(sd), ic.to_state_dict(sd, use_ema=True)
+    assert plain["emb.weight"].shape == (50, 8) and not torch.equal(plain["W"], ema["W"])
+    fresh = LM1B(vocab_size=50, emb_size=8, state_size=16, projected_size=8, num_sampled=8,
+                 num_steps=3, num_shards=2, keep_prob=1.0)
+    missing, unexpected = fresh.load_state_dict(plain, strict=False)
+    assert not missing and not unexpected
+    assert ic.main([str(tmp_path), "--tensor", "B"]) == 0 and "dense B" in capsys.readouterr().out
+    out = str(tmp_path / "plain.pt")
+    assert ic.main([str(tmp_path), "--to_state_dict", out, "--ema"]) == 0
+    assert torch.equal(torch.load(out)["W_P"], ema["W_P"])
+    with pytest.raises(FileNotFoundError):
+        ic.load(str(tmp_path / "empty_dir_that_does_not_exist"))
