@@ -39,6 +39,8 @@ class Comm(object):
         world = int(os.environ.get("WORLD_SIZE", "1"))
         rank = int(os.environ.get("RANK", "0"))
         local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+        # `run --start-timeout`: how long ranks wait for each other at start-up
+        timeout_s = int(os.environ.get("PARALLAX_START_TIMEOUT", timeout_s))
         if device is None:
             if torch.cuda.is_available():
                 device = torch.device("cuda", local_rank % torch.cuda.device_count())

@@ -34,11 +34,24 @@ def _pump(stream, prefix):
 
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="parallax_b200.run")
-    ap.add_argument("-np", "--num-proc", type=int, required=True)
-    ap.add_argument("-H", "--hosts", default=None, help="host:slots[,host:slots...]")
+    ap.add_argument("-v", "--version", action="store_true", help="print the version and exit")
+    ap.add_argument("-np", "--num-proc", type=int, default=None)
+    ap.add_argument("-H", "--hosts", "--host", default=None, help="host:slots[,host:slots...]")
+    ap.add_argument("-p", "--ssh-port", type=int, default=22, help="ssh port of remote hosts")
     ap.add_argument("--master-port", type=int, default=None)
+    ap.add_argument("--start-timeout", type=int, default=None,
+                    help="seconds the ranks wait for each other at start-up (default 600)")
+    ap.add_argument("--disable-cache", action="store_true",
+                    help="accepted for horovodrun compatibility (there are no cached host checks)")
+    ap.add_argument("--verbose", action="store_true", help="log the launch commands")
     ap.add_argument("command", nargs=argparse.REMAINDER)
     a = ap.parse_args(argv)
+    if a.version:
+        from . import __version__
+        print(__version__)
+        return 0
+    if a.num_proc is None:
+        ap.error("-np is required")
     if not a.command:
         ap.error("no command given")
     hosts = parse_hosts(a.hosts, a.num_proc)
@@ -56,6 +69,10 @@ def main(argv=None):
                 break
             env = {"RANK": rank, "WORLD_SIZE": a.num_proc, "LOCAL_RANK": local,
                    "LOCAL_WORLD_SIZE": slots, "MASTER_ADDR": master, "MASTER_PORT": port}
+            if a.start_timeout:
+                env["PARALLAX_START_TIMEOUT"] = a.start_timeout
+            if a.verbose:
+                sys.stderr.write("[run] rank %d on %s: %s\n" % (rank, host, " ".join(cmd)))
             if is_local_host(host):
                 penv = dict(os.environ)
                 penv.update({k: str(v) for k, v in env.items()})
@@ -63,7 +80,8 @@ def main(argv=None):
                                      stderr=subprocess.STDOUT, preexec_fn=os.setsid)
             else:
                 p = remote_exec("cd %s; %s" % (os.getcwd(), " ".join(cmd)), host,
-                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)
+                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env,
+                                port=a.ssh_port)
             t = threading.Thread(target=_pump, args=(p.stdout, str(rank)), daemon=True)
             t.start()
             procs.append(p)

@@ -65,3 +65,35 @@ def test_partition_search_relaunches_and_converges(tmp_path):
     assert "optimal partitions" in r.stderr
     for i in final:
         assert i["tableP"] == i["partitions"]
+
+
+def test_run_cli_like_horovodrun(tmp_path):
+    """`python -m parallax_b200.run -np 2 script.py`: rank-prefixed output, rendezvous env,
+    failure of one rank fails the job (horovodrun, `horovod/run/run.py`)."""
+    script = tmp_path / "job.py"
+    script.write_text(
+        "import os, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import torch\n"
+        "from parallax_b200 import collectives as hvd\n"
+        "hvd.init()\n"
+        "s = hvd.allreduce(torch.tensor([float(hvd.rank() + 1)]), average=False)\n"
+        "r = hvd.rank()\n"
+        "print('rank', r, 'sum', s.item(), os.environ.get('PARALLAX_START_TIMEOUT'))\n"
+        "hvd.shutdown()\n"
+        "sys.exit(3 if '--fail' in sys.argv and r == 1 else 0)\n" % ROOT)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    base = [sys.executable, "-m", "parallax_b200.run"]
+    r = subprocess.run(base + ["-np", "2", "--start-timeout", "90", "--verbose", str(script)],
+                       env=env, cwd=ROOT, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "[0] rank 0 sum 3.0 90" in r.stdout and "[1] rank 1 sum 3.0 90" in r.stdout
+    assert "[run] rank 1 on localhost" in r.stderr
+    r = subprocess.run(base + ["-np", "2", str(script), "--fail"], env=env, cwd=ROOT,
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 3
+    r = subprocess.run(base + ["--version"], env=env, cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "0.1.0"
+    r = subprocess.run(base + ["-np", "3", "-H", "localhost:2", str(script)], env=env, cwd=ROOT,
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "not enough slots" in r.stderr
