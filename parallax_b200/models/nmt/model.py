@@ -151,8 +151,37 @@ class RNNLayer(nn.Module):
         return out, self._from_rnn(st)
 
     def step(self, x, state):
-        out, st = self.forward(x[:, None, :], state)
-        return out[:, 0], st
+        """One time step as explicit GEMMs + gate math (fp32) on the layer's own
+        weights.  A length-1 cuDNN call would re-pack the weights on every step:
+        on the NVLink fabric parameters are views into the symmetric buckets, never
+        one flat cuDNN buffer."""
+        if self.unit_type == "layer_norm_lstm":
+            out, st = self.forward(x[:, None, :], state)
+            return out[:, 0], st
+        inp = F.dropout(x, self.dropout, True) if (self.training and self.dropout > 0) else x
+        r = self.rnn
+        n = self.num_units
+        if self.unit_type == "lstm":
+            h, c = state
+            gates = (F.linear(inp, r.weight_ih_l0, r.bias_ih_l0) +
+                     F.linear(h, r.weight_hh_l0, r.bias_hh_l0)).float()
+            i, f, g, o = gates[:, :n], gates[:, n:2 * n], gates[:, 2 * n:3 * n], gates[:, 3 * n:]
+            c2 = torch.sigmoid(f) * c.float() + torch.sigmoid(i) * torch.tanh(g)
+            h2 = (torch.sigmoid(o) * torch.tanh(c2)).to(x.dtype)
+            st = (h2, c2.to(c.dtype))
+        else:                                   # torch / cuDNN GRU equations
+            h = state
+            gi = F.linear(inp, r.weight_ih_l0, r.bias_ih_l0).float()
+            gh = F.linear(h, r.weight_hh_l0, r.bias_hh_l0).float()
+            rg = torch.sigmoid(gi[:, :n] + gh[:, :n])
+            z = torch.sigmoid(gi[:, n:2 * n] + gh[:, n:2 * n])
+            cand = torch.tanh(gi[:, 2 * n:] + rg * gh[:, 2 * n:])
+            h2 = ((1.0 - z) * cand + z * h.float()).to(x.dtype)
+            st = h2
+        out = h2
+        if self.residual:
+            out = out + x[..., :self.num_units]
+        return out, st
 
 
 def build_stack(unit_type, num_layers, num_residual_layers, input_size, num_units, hp,

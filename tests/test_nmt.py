@@ -504,3 +504,37 @@ def test_shared_vocabulary_is_one_table_in_the_engine():
         assert all(moved[i] for i in only_tgt) and any(moved[i] for i in only_src)
     finally:
         sess.close()
+
+
+@pytest.mark.parametrize("unit_type", ["lstm", "gru", "layer_norm_lstm"])
+def test_rnn_layer_step_equals_sequence_call(unit_type):
+    """the explicit-GEMM step used by the decoders = the (cuDNN / native) sequence kernel"""
+    from parallax_b200.models.nmt.model import RNNLayer
+    torch.manual_seed(0)
+    layer = RNNLayer(unit_type, 12, 10, forget_bias=1.0, dropout=0.0, residual=True,
+                     init_weight=0.5).eval()
+    x = torch.randn(3, 5, 12)
+    seq, st_seq = layer(x)
+    st, outs = layer.zero_state(3, x.device, x.dtype), []
+    for t in range(5):
+        o, st = layer.step(x[:, t], st)
+        outs.append(o)
+    assert torch.allclose(torch.stack(outs, 1), seq, atol=1e-5)
+    for a, b in zip(st if isinstance(st, tuple) else (st,),
+                    st_seq if isinstance(st_seq, tuple) else (st_seq,)):
+        assert torch.allclose(a, b, atol=1e-5)
+    # gradients agree too
+    layer.train()
+    x1 = x.clone().requires_grad_(True)
+    layer(x1)[0].sum().backward()
+    g_seq = [p.grad.clone() for p in layer.parameters()]
+    layer.zero_grad()
+    x2 = x.clone().requires_grad_(True)
+    st, tot = layer.zero_state(3, x.device, x.dtype), 0.0
+    for t in range(5):
+        o, st = layer.step(x2[:, t], st)
+        tot = tot + o.sum()
+    tot.backward()
+    for a, p in zip(g_seq, layer.parameters()):
+        assert torch.allclose(a, p.grad, atol=1e-4)
+    assert torch.allclose(x1.grad, x2.grad, atol=1e-5)
