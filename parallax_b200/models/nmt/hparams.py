@@ -2,8 +2,8 @@
 
 Parity: the reference's flag set and defaults (`examples/nmt/nmt.py:40-290`
 `add_arguments`, `:293-372` `create_hparams`, `:375-474` `extend_hparams`),
-the standard hyper-parameter files (`examples/nmt/standard_hparams/*.json`,
-loaded by `utils/misc_utils.py:maybe_parse_standard_hparams`) and
+the four standard configurations (`examples/nmt/standard_hparams/*.json`, loaded by
+`utils/misc_utils.py:maybe_parse_standard_hparams`; here `STANDARD_HPARAMS`) and
 `utils/standard_hparams_utils.py:27-104`.
 
 `HParams` is a plain attribute bag with JSON round-trip and
@@ -15,7 +15,30 @@ import os
 
 UNK, SOS, EOS = "<unk>", "<s>", "</s>"
 
-_STD_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "standard_hparams")
+# The reference ships four "standard" hyper-parameter files
+# (`examples/nmt/standard_hparams/{iwslt15,wmt16,wmt16_gnmt_4_layer,wmt16_gnmt_8_layer}.json`).
+# The same settings, written as what they share plus what distinguishes them:
+_STD_SHARED = dict(
+    batch_size=128, infer_batch_size=32, beam_width=10, num_buckets=5,
+    src_max_len=50, tgt_max_len=50, src_max_len_infer=None, tgt_max_len_infer=None,
+    optimizer="sgd", learning_rate=1.0, init_weight=0.1, max_gradient_norm=5.0,
+    dropout=0.2, forget_bias=1.0, unit_type="lstm", time_major=True,
+    sos=SOS, eos=EOS, share_vocab=False, metrics=["bleu"],
+    colocate_gradients_with_ops=True, steps_per_external_eval=None)
+_WMT = dict(num_units=1024, num_train_steps=340000, decay_scheme="luong10",
+            attention="normed_bahdanau", subword_option="bpe")
+_GNMT = dict(_WMT, encoder_type="gnmt", attention_architecture="gnmt_v2", residual=True,
+             length_penalty_weight=1.0)
+STANDARD_HPARAMS = {
+    "iwslt15": dict(_STD_SHARED, num_units=512, num_layers=2, num_train_steps=12000,
+                    decay_scheme="luong234", encoder_type="bi", attention="scaled_luong",
+                    attention_architecture="standard", residual=False, subword_option="",
+                    steps_per_stats=100),
+    "wmt16": dict(_STD_SHARED, num_layers=4, encoder_type="bi", residual=False,
+                  attention_architecture="standard", steps_per_stats=100, **_WMT),
+    "wmt16_gnmt_4_layer": dict(_STD_SHARED, num_layers=4, steps_per_stats=100, **_GNMT),
+    "wmt16_gnmt_8_layer": dict(_STD_SHARED, num_layers=8, steps_per_stats=50, **_GNMT),
+}
 
 
 class HParams(object):
@@ -136,25 +159,30 @@ def create_standard_hparams():
 
 
 def standard_hparams_names():
-    return sorted(f[:-5] for f in os.listdir(_STD_DIR) if f.endswith(".json"))
+    return sorted(STANDARD_HPARAMS)
 
 
-def standard_hparams_path(name):
-    path = name if os.path.exists(name) else os.path.join(_STD_DIR, name + ".json")
-    if not os.path.exists(path):
-        raise ValueError("unknown standard hparams %r (have: %s)" %
-                         (name, ", ".join(standard_hparams_names())))
-    return path
+def standard_hparams(name_or_path):
+    """settings of a bundled standard configuration, or of a JSON file"""
+    if name_or_path in STANDARD_HPARAMS:
+        return dict(STANDARD_HPARAMS[name_or_path])
+    base = os.path.basename(name_or_path)
+    if base.endswith(".json") and base[:-5] in STANDARD_HPARAMS and \
+            not os.path.exists(name_or_path):
+        return dict(STANDARD_HPARAMS[base[:-5]])          # reference-style "…/wmt16.json"
+    if os.path.exists(name_or_path):
+        with open(name_or_path) as f:
+            return json.load(f)
+    raise ValueError("unknown standard hparams %r (have: %s)" %
+                     (name_or_path, ", ".join(standard_hparams_names())))
 
 
 def maybe_parse_standard_hparams(hparams, hparams_path):
-    """Override `hparams` with a standard hyper-parameter file (name of one of
-    the bundled files, or a path)."""
+    """Override `hparams` with a standard configuration (name of a bundled one, or
+    the path of a JSON file)."""
     if not hparams_path:
         return hparams
-    with open(standard_hparams_path(hparams_path)) as f:
-        hparams.parse_json(f.read())
-    return hparams
+    return hparams.parse_json(standard_hparams(hparams_path))
 
 
 def load_hparams(model_dir):
