@@ -83,8 +83,8 @@ def analyze(model, world=1):
             sparse_modules[path] = m
         elif isinstance(m, tnn.EmbeddingBag) and m.sparse:
             raise NotImplementedError(
-                "nn.EmbeddingBag(sparse=True) at %r: use parallax.nn.Embedding "
-                "followed by a reduction" % path)
+                "nn.EmbeddingBag(sparse=True) at %r: use parallax.nn.EmbeddingBag (same "
+                "semantics on a shardable table)" % path)
     variables = OrderedDict()
     for name, p in model.named_parameters():
         if id(p) in sparse_param_ids:

@@ -43,6 +43,70 @@ class Embedding(tnn.Embedding):
                 self.weight.uniform_(-self.init_scale, self.init_scale)
 
 
+class EmbeddingBag(tnn.Module):
+    """``nn.EmbeddingBag`` semantics (sum / mean / max over bags of ids, optional
+    per-sample weights) on top of a sparse `Embedding`, so the table is an ordinary
+    sparse variable: partitionable, looked up over the fabric, updated by its row
+    owners.  Accepts 2-D input (fixed-size bags) or 1-D input + `offsets`."""
+
+    def __init__(self, num_embeddings, embedding_dim, mode="sum", partitioner=None,
+                 lazy=False, init_scale=None, seed=1234, include_last_offset=False,
+                 padding_idx=None):
+        super().__init__()
+        if mode not in ("sum", "mean", "max"):
+            raise ValueError("mode must be sum, mean or max")
+        self.mode, self.include_last_offset, self.padding_idx = mode, include_last_offset, \
+            padding_idx
+        self.table = Embedding(num_embeddings, embedding_dim, partitioner=partitioner, lazy=lazy,
+                               init_scale=init_scale, seed=seed)
+
+    @property
+    def weight(self):
+        return self.table.weight
+
+    def forward(self, input, offsets=None, per_sample_weights=None):
+        if per_sample_weights is not None and self.mode != "sum":
+            raise NotImplementedError("per_sample_weights needs mode='sum'")
+        if input.dim() == 2:
+            if offsets is not None:
+                raise ValueError("offsets must be None for 2-D input")
+            B, L = input.shape
+            flat = input.reshape(-1)
+            bag = torch.arange(B, device=input.device).repeat_interleave(L)
+            psw = per_sample_weights.reshape(-1) if per_sample_weights is not None else None
+        else:
+            if offsets is None:
+                raise ValueError("offsets are required for 1-D input")
+            flat, psw = input, per_sample_weights
+            off = offsets.to(input.device)
+            B = off.numel() - (1 if self.include_last_offset else 0)
+            ends = off[1:] if self.include_last_offset else \
+                torch.cat([off[1:], off.new_tensor([flat.numel()])])
+            lens = ends - off[:B]
+            bag = torch.arange(B, device=input.device).repeat_interleave(lens)
+        rows = self.table(flat)                               # [N, D] — the sparse lookup
+        keep = None
+        if self.padding_idx is not None:
+            keep = (flat != self.padding_idx)
+            rows = rows * keep[:, None].to(rows.dtype)
+        if psw is not None:
+            rows = rows * psw[:, None].to(rows.dtype)
+        bag = bag.to(rows.device)
+        D = rows.shape[1]
+        if self.mode == "max":
+            out = torch.full((B, D), float("-inf"), dtype=rows.dtype, device=rows.device)
+            out = out.scatter_reduce(0, bag[:, None].expand(-1, D), rows, "amax",
+                                     include_self=True)
+            return torch.where(torch.isinf(out), torch.zeros_like(out), out)   # empty bags → 0
+        out = torch.zeros(B, D, dtype=rows.dtype, device=rows.device).index_add_(0, bag, rows)
+        if self.mode == "mean":
+            ones = torch.ones(flat.numel(), device=rows.device, dtype=rows.dtype) if keep is None \
+                else keep.to(rows.dtype)
+            cnt = torch.zeros(B, dtype=rows.dtype, device=rows.device).index_add_(0, bag, ones)
+            out = out / cnt.clamp(min=1.0)[:, None]
+        return out
+
+
 def partition(module, partitioner):
     """Attach a partitioner to an existing ``nn.Embedding(sparse=True)``."""
     assert isinstance(module, tnn.Embedding), "only nn.Embedding is partitionable"

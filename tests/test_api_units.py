@@ -277,3 +277,53 @@ def test_inspect_checkpoint_tool(tmp_path, capsys):
     assert torch.equal(torch.load(out)["W_P"], ema["W_P"])
     with pytest.raises(FileNotFoundError):
         ic.load(str(tmp_path / "empty_dir_that_does_not_exist"))
+
+
+@pytest.mark.parametrize("mode", ["sum", "mean", "max"])
+def test_embedding_bag_matches_torch_and_trains_sharded(mode):
+    torch.manual_seed(0)
+    bag = parallax.nn.EmbeddingBag(30, 6, mode=mode, partitioner=parallax.get_partitioner(3))
+    ref = torch.nn.EmbeddingBag(30, 6, mode=mode)
+    with torch.no_grad():
+        ref.weight.copy_(bag.weight)
+    flat = torch.tensor([1, 2, 4, 5, 4, 3, 2, 9, 7])
+    offsets = torch.tensor([0, 4, 4, 7])                       # the second bag is empty
+    torch.testing.assert_close(bag(flat, offsets), ref(flat, offsets))
+    two_d = torch.tensor([[1, 2, 3], [4, 4, 9]])
+    torch.testing.assert_close(bag(two_d), ref(two_d))
+    if mode == "sum":
+        w = torch.rand(9)
+        torch.testing.assert_close(bag(flat, offsets, per_sample_weights=w),
+                                   ref(flat, offsets, per_sample_weights=w))
+    else:
+        with pytest.raises(NotImplementedError):
+            bag(flat, offsets, per_sample_weights=torch.rand(9))
+    with pytest.raises(ValueError):
+        bag(flat)
+    # under the engine the bag's table is a partitioned sparse variable
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.bag = parallax.nn.EmbeddingBag(30, 6, mode=mode,
+                                                partitioner=parallax.get_partitioner(3))
+            self.fc = torch.nn.Linear(6, 2)
+
+        def forward(self, ids, labels):
+            return {"loss": torch.nn.functional.cross_entropy(self.fc(self.bag(ids)), labels)}
+    net = Net()
+    sess, *_ = parallax.parallel_run(
+        parallax.Graph(net, optimizer=parallax.optim.Adagrad(0.5, 0.1)), "localhost",
+        parallax_config=parallax.Config(sess_config={"fabric": "host"}, search_partitions=False))
+    try:
+        assert list(sess.engine.tables) == ["bag.table.weight"]
+        assert sess.engine.tables["bag.table.weight"].layout.P == 3
+        ids = torch.randint(0, 30, (16, 4))
+        labels = (ids.sum(1) % 2).long()
+        losses = [sess.run(["loss", "train_op"], {"ids": [ids], "labels": [labels]})[0][0]
+                  for _ in range(40)]
+        assert losses[-1] < 0.7 * losses[0]
+    finally:
+        sess.close()
+    with pytest.raises(NotImplementedError, match="parallax.nn.EmbeddingBag"):
+        from parallax_b200.analyzer import analyze
+        analyze(torch.nn.Sequential(torch.nn.EmbeddingBag(5, 2, sparse=True)))
