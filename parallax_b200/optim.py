@@ -29,14 +29,34 @@ import math
 
 import torch
 
-KINDS = ("sgd", "momentum", "adagrad", "adam", "rmsprop")
+KINDS = ("sgd", "momentum", "adagrad", "adam", "rmsprop")        # fused sm_100a kernels
 KIND_ID = {k: i for i, k in enumerate(KINDS)}
+# The rest of the reference's recognised update ops (`graph_transform_lib.py:56-75`:
+# ApplyAdadelta, ApplyFtrl, ApplyProximalGradientDescent, ApplyProximalAdagrad,
+# ApplyAdagradDA, ApplyCenteredRMSProp) run on the host / library fabrics; the NVLink
+# fabric rejects them until their cases are added to `px_update` (they need three
+# more hyper-parameters and, for centered RMSProp, a third slot).
+HOST_KINDS = ("adadelta", "ftrl", "proximal_sgd", "proximal_adagrad", "adagrad_da",
+              "centered_rmsprop")
 # number of fp32 state slots per kind
-NUM_SLOTS = {"sgd": 0, "momentum": 1, "adagrad": 1, "adam": 2, "rmsprop": 2}
+NUM_SLOTS = {"sgd": 0, "momentum": 1, "adagrad": 1, "adam": 2, "rmsprop": 2,
+             "adadelta": 2, "ftrl": 2, "proximal_sgd": 0, "proximal_adagrad": 1,
+             "adagrad_da": 2, "centered_rmsprop": 3}
 SLOT_NAMES = {
     "sgd": (), "momentum": ("momentum",), "adagrad": ("accumulator",),
     "adam": ("m", "v"), "rmsprop": ("ms", "mom"),
+    "adadelta": ("accum", "accum_update"), "ftrl": ("accum", "linear"), "proximal_sgd": (),
+    "proximal_adagrad": ("accumulator",),
+    "adagrad_da": ("gradient_accumulator", "gradient_squared_accumulator"),
+    "centered_rmsprop": ("ms", "mg", "mom"),
 }
+
+
+def require_fused(kind, where):
+    if kind not in KINDS:
+        raise NotImplementedError(
+            "optimizer kind %r has no fused kernel yet (%s); it runs on fabric='host' or "
+            "'library'.  Fused kinds: %s" % (kind, where, ", ".join(KINDS)))
 
 # layout of the device-side hyper-parameter vector read by the kernels
 HP_LR, HP_A, HP_B, HP_EPS, HP_WD, HP_STEP, HP_GSCALE, HP_FLAGS = range(8)
@@ -139,7 +159,87 @@ class RMSProp(Optimizer):
         hp[HP_A], hp[HP_B], hp[HP_EPS] = self.decay, self.momentum, self.epsilon
 
 
+class Adadelta(Optimizer):
+    """`tf.train.AdadeltaOptimizer` (ApplyAdadelta)"""
+    kind = "adadelta"
+
+    def __init__(self, learning_rate=0.001, rho=0.95, epsilon=1e-8, **kw):
+        super().__init__(learning_rate, **kw)
+        self.rho, self.epsilon = float(rho), float(epsilon)
+
+    def _fill(self, hp, step):
+        hp[HP_A], hp[HP_EPS] = self.rho, self.epsilon
+
+
+class Ftrl(Optimizer):
+    """`tf.train.FtrlOptimizer` (ApplyFtrl): FTRL-proximal with L1/L2"""
+    kind = "ftrl"
+
+    def __init__(self, learning_rate, learning_rate_power=-0.5, initial_accumulator_value=0.1,
+                 l1_regularization_strength=0.0, l2_regularization_strength=0.0, **kw):
+        super().__init__(learning_rate, **kw)
+        if learning_rate_power > 0:
+            raise ValueError("learning_rate_power must be <= 0")
+        self.learning_rate_power = float(learning_rate_power)
+        self.initial_accumulator_value = float(initial_accumulator_value)
+        self.l1, self.l2 = float(l1_regularization_strength), float(l2_regularization_strength)
+
+    def slot_init(self):
+        return (self.initial_accumulator_value, 0.0)
+
+    def _fill(self, hp, step):
+        hp[HP_A], hp[HP_B], hp[HP_EPS] = self.learning_rate_power, self.l1, self.l2
+
+
+class ProximalGradientDescent(Optimizer):
+    """`tf.train.ProximalGradientDescentOptimizer` (ApplyProximalGradientDescent)"""
+    kind = "proximal_sgd"
+
+    def __init__(self, learning_rate, l1_regularization_strength=0.0,
+                 l2_regularization_strength=0.0, **kw):
+        super().__init__(learning_rate, **kw)
+        self.l1, self.l2 = float(l1_regularization_strength), float(l2_regularization_strength)
+
+    def _fill(self, hp, step):
+        hp[HP_A], hp[HP_B] = self.l1, self.l2
+
+
+class ProximalAdagrad(ProximalGradientDescent):
+    """`tf.train.ProximalAdagradOptimizer` (ApplyProximalAdagrad)"""
+    kind = "proximal_adagrad"
+
+    def __init__(self, learning_rate, initial_accumulator_value=0.1, **kw):
+        super().__init__(learning_rate, **kw)
+        self.initial_accumulator_value = float(initial_accumulator_value)
+
+    def slot_init(self):
+        return (self.initial_accumulator_value,)
+
+
+class AdagradDA(ProximalGradientDescent):
+    """`tf.train.AdagradDAOptimizer` (ApplyAdagradDA): dual averaging, needs the step"""
+    kind = "adagrad_da"
+
+    def __init__(self, learning_rate, initial_gradient_squared_accumulator_value=0.1, **kw):
+        super().__init__(learning_rate, **kw)
+        self.initial_gradient_squared_accumulator_value = \
+            float(initial_gradient_squared_accumulator_value)
+
+    def slot_init(self):
+        return (0.0, self.initial_gradient_squared_accumulator_value)
+
+
+class CenteredRMSProp(RMSProp):
+    """`tf.train.RMSPropOptimizer(centered=True)` (ApplyCenteredRMSProp)"""
+    kind = "centered_rmsprop"
+
+
 # TF-style aliases
+AdadeltaOptimizer = Adadelta
+FtrlOptimizer = Ftrl
+ProximalGradientDescentOptimizer = ProximalGradientDescent
+ProximalAdagradOptimizer = ProximalAdagrad
+AdagradDAOptimizer = AdagradDA
 GradientDescentOptimizer = GradientDescent
 MomentumOptimizer = Momentum
 AdagradOptimizer = Adagrad
@@ -180,6 +280,44 @@ def apply_dense_(kind, w, g, slots, hp):
         ms.mul_(a).addcmul_(g, g, value=1.0 - a)
         mom.mul_(b).add_(g / (ms + eps).sqrt(), alpha=lr)
         w.sub_(mom)
+    elif kind == "centered_rmsprop":
+        ms, mg, mom = slots
+        ms.mul_(a).addcmul_(g, g, value=1.0 - a)
+        mg.mul_(a).add_(g, alpha=1.0 - a)
+        mom.mul_(b).add_(g / (ms - mg * mg + eps).sqrt(), alpha=lr)
+        w.sub_(mom)
+    elif kind == "adadelta":
+        accum, accum_update = slots
+        accum.mul_(a).addcmul_(g, g, value=1.0 - a)
+        update = (accum_update + eps).sqrt() / (accum + eps).sqrt() * g
+        accum_update.mul_(a).addcmul_(update, update, value=1.0 - a)
+        w.add_(update, alpha=-lr)
+    elif kind == "ftrl":                  # a = lr_power (<= 0), b = l1, eps = l2
+        accum, linear = slots
+        new_accum = accum + g * g
+        p_new, p_old = new_accum.pow(-a), accum.pow(-a)
+        linear.add_(g - (p_new - p_old) / lr * w)
+        quadratic = p_new / lr + 2.0 * eps
+        w.copy_(torch.where(linear.abs() > b,
+                            (torch.sign(linear) * b - linear) / quadratic,
+                            torch.zeros_like(w)))
+        accum.copy_(new_accum)
+    elif kind in ("proximal_sgd", "proximal_adagrad"):       # a = l1, b = l2
+        if kind == "proximal_adagrad":
+            (accum,) = slots
+            accum.addcmul_(g, g)
+            lr_t = lr / accum.sqrt()
+        else:
+            lr_t = torch.full_like(w, lr)
+        prox = w - lr_t * g
+        w.copy_(torch.sign(prox) * (prox.abs() - lr_t * a).clamp(min=0.0) / (1.0 + lr_t * b))
+    elif kind == "adagrad_da":            # a = l1, b = l2, hp[HP_STEP] = global step
+        g_acc, gg_acc = slots
+        t = float(hp[HP_STEP])
+        g_acc.add_(g)
+        gg_acc.addcmul_(g, g)
+        tmp = torch.sign(g_acc) * (g_acc.abs() - a * t).clamp(min=0.0) if a > 0 else g_acc
+        w.copy_(-lr * tmp / (b * t * lr + gg_acc.sqrt()))
     else:  # pragma: no cover
         raise ValueError(kind)
     return w

@@ -93,6 +93,7 @@ class NVDenseGroup(object):
                              self.update == "sharded" and self.world > 1)
         self.names = [n for n, _ in named_params]
         self.params = [p for _, p in named_params]
+        _optim.require_fused(optimizer.kind, "NVLink fabric")
         self.kind = optimizer.kind
         self.nslots = _optim.NUM_SLOTS[self.kind]
         self.clip_rules = graph.clip_rules()
@@ -512,6 +513,7 @@ class NVSparseTable(object):
         self.comm = fabric.comm
         self.rank, self.world, self.device = fabric.rank, fabric.world, fabric.device
         self.route, self.optimizer = route, optimizer
+        _optim.require_fused(optimizer.kind, "NVLink fabric")
         self.kind = optimizer.kind
         self.nslots = _optim.NUM_SLOTS[self.kind]
         self.V, self.D = int(weight.shape[0]), int(weight.shape[1])

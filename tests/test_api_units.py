@@ -327,3 +327,105 @@ def test_embedding_bag_matches_torch_and_trains_sharded(mode):
     with pytest.raises(NotImplementedError, match="parallax.nn.EmbeddingBag"):
         from parallax_b200.analyzer import analyze
         analyze(torch.nn.Sequential(torch.nn.EmbeddingBag(5, 2, sparse=True)))
+
+
+def test_remaining_tf_optimizers_math():
+    """Adadelta / FTRL / proximal SGD+Adagrad / AdagradDA / centered RMSProp follow TF's
+    Apply* kernels (`tensorflow/core/kernels/training_ops.cc`)."""
+    from parallax_b200 import optim
+    g = torch.tensor([0.5, -2.0, 0.01])
+    # Adadelta = torch.optim.Adadelta (same recurrences)
+    w = torch.tensor([1.0, -1.0, 0.3])
+    ref = w.clone().requires_grad_(True)
+    topt = torch.optim.Adadelta([ref], lr=0.7, rho=0.9, eps=1e-6)
+    spec = optim.Adadelta(0.7, rho=0.9, epsilon=1e-6)
+    slots = tuple(torch.full_like(w, v) for v in spec.slot_init())
+    for step in (1, 2, 3):
+        ref.grad = g.clone()
+        topt.step()
+        optim.apply_dense_("adadelta", w, g, slots, spec.hyper(step))
+    torch.testing.assert_close(w, ref.detach())
+    # proximal SGD: soft threshold then L2 shrink
+    w = torch.tensor([1.0, -1.0, 0.001])
+    spec = optim.ProximalGradientDescent(0.1, l1_regularization_strength=0.5,
+                                         l2_regularization_strength=2.0)
+    optim.apply_dense_("proximal_sgd", w, g, (), spec.hyper(1))
+    prox = torch.tensor([1.0 - 0.05, -1.0 + 0.2, 0.001 - 0.001])
+    want = torch.sign(prox) * (prox.abs() - 0.05).clamp(min=0) / 1.2
+    torch.testing.assert_close(w, want)
+    assert w[2] == 0.0                                   # L1 produces exact zeros
+    # proximal Adagrad with l1 = l2 = 0 is Adagrad
+    w1, w2 = torch.tensor([1.0, -1.0, 0.3]), torch.tensor([1.0, -1.0, 0.3])
+    a1, a2 = torch.full_like(w1, 0.1), torch.full_like(w2, 0.1)
+    optim.apply_dense_("proximal_adagrad", w1, g, (a1,), optim.ProximalAdagrad(0.2).hyper(1))
+    optim.apply_dense_("adagrad", w2, g, (a2,), optim.Adagrad(0.2, 0.1).hyper(1))
+    torch.testing.assert_close(w1, w2)
+    # FTRL, first step from w = 0 with lr_power -0.5: closed form
+    spec = optim.Ftrl(0.5, initial_accumulator_value=0.1, l1_regularization_strength=0.1,
+                      l2_regularization_strength=0.01)
+    w = torch.zeros(3)
+    slots = tuple(torch.full_like(w, v) for v in spec.slot_init())
+    optim.apply_dense_("ftrl", w, g, slots, spec.hyper(1))
+    n = 0.1 + g * g
+    want = torch.where(g.abs() > 0.1, (torch.sign(g) * 0.1 - g) / (n.sqrt() / 0.5 + 0.02),
+                       torch.zeros(3))
+    torch.testing.assert_close(w, want)
+    assert w[2] == 0.0 and torch.equal(slots[0], n) and torch.equal(slots[1], g)
+    with pytest.raises(ValueError):
+        optim.Ftrl(0.1, learning_rate_power=0.5)
+    # AdagradDA: w = -lr·shrink(Σg) / (l2·t·lr + sqrt(Σg²))
+    spec = optim.AdagradDA(0.3, initial_gradient_squared_accumulator_value=0.1,
+                           l1_regularization_strength=0.2, l2_regularization_strength=0.5)
+    w = torch.tensor([9.0, 9.0, 9.0])
+    slots = tuple(torch.full_like(w, v) for v in spec.slot_init())
+    for step in (1, 2):
+        optim.apply_dense_("adagrad_da", w, g, slots, spec.hyper(step))
+    gs, gg = 2 * g, 0.1 + 2 * g * g
+    want = -0.3 * torch.sign(gs) * (gs.abs() - 0.2 * 2).clamp(min=0) / (0.5 * 2 * 0.3 + gg.sqrt())
+    torch.testing.assert_close(w, want)
+    # centered RMSProp subtracts the squared running mean
+    spec = optim.CenteredRMSProp(0.01, decay=0.9, momentum=0.5, epsilon=1e-3)
+    w = torch.tensor([1.0, -1.0, 0.3])
+    slots = tuple(torch.zeros(3) for _ in spec.slot_init())
+    optim.apply_dense_("centered_rmsprop", w, g, slots, spec.hyper(1))
+    ms, mg = 0.1 * g * g, 0.1 * g
+    torch.testing.assert_close(w, torch.tensor([1.0, -1.0, 0.3]) -
+                               0.01 * g / (ms - mg * mg + 1e-3).sqrt())
+    assert len(spec.slot_init()) == 3
+    with pytest.raises(NotImplementedError, match="no fused kernel"):
+        optim.require_fused("ftrl", "NVLink fabric")
+    optim.require_fused("adam", "NVLink fabric")
+
+
+@pytest.mark.parametrize("name", ["adadelta", "ftrl", "proximal_sgd", "proximal_adagrad",
+                                  "adagrad_da", "centered_rmsprop"])
+def test_remaining_tf_optimizers_train_dense_and_sparse(name):
+    from parallax_b200 import optim
+    from parallax_b200.models.simple import MLPWithEmbedding
+    mk = {"adadelta": lambda: optim.Adadelta(1.0, epsilon=1e-2), "ftrl": lambda: optim.Ftrl(0.5),
+          "proximal_sgd": lambda: optim.ProximalGradientDescent(0.5, 1e-4, 1e-4),
+          "proximal_adagrad": lambda: optim.ProximalAdagrad(0.5, 0.1,
+                                                            l1_regularization_strength=1e-4),
+          "adagrad_da": lambda: optim.AdagradDA(0.5),
+          "centered_rmsprop": lambda: optim.CenteredRMSProp(0.01, momentum=0.5, epsilon=1e-3)}[name]
+    torch.manual_seed(0)
+    model = MLPWithEmbedding(32, partitioner=parallax.get_partitioner(2))
+    sess, *_ = parallax.parallel_run(
+        parallax.Graph(model, optimizer=mk()), "localhost",
+        parallax_config=parallax.Config(sess_config={"fabric": "host"}, search_partitions=False))
+    try:
+        g = torch.Generator().manual_seed(0)
+        ids = torch.randint(0, 32, (16, 3), generator=g)
+        labels = torch.randint(0, 4, (16,), generator=g)
+        losses = [sess.run(["loss", "train_op"], {"ids": [ids], "labels": [labels]})[0][0]
+                  for _ in range(60)]
+        # (FTRL and dual averaging rebuild the weights from accumulated gradients, i.e. they
+        # forget a non-zero initialisation at their first step — TF's kernels do too)
+        bound = 0.95 if name in ("ftrl", "adagrad_da") else 0.9
+        assert np.isfinite(losses).all() and losses[-1] < bound * losses[0], (name, losses[::10])
+        sd = sess.engine.state_dict()
+        nslots = optim.NUM_SLOTS[name]
+        assert len(sd["dense"]["slots"]["fc1.weight"]) == nslots
+        assert len(sd["sparse"]["emb.weight"]["slots"]) == nslots
+    finally:
+        sess.close()
