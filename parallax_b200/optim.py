@@ -335,3 +335,85 @@ def apply_sparse_rows_(kind, w, rows, g, slots, hp):
     for s, sr in zip(slots, s_r):
         s.index_copy_(0, rows, sr)
     return w
+
+
+# ---------------------------------------------------------------------------
+# learning-rate schedules (`tf.train.*_decay`) — callables for `learning_rate=`
+# ---------------------------------------------------------------------------
+class schedules(object):
+    """Every function returns ``lr(step)``; `step` is the 1-based index of the update
+    being applied, and — like TF, which evaluates a schedule with the number of
+    *completed* steps — the formulas use ``global_step = step − 1``."""
+
+    @staticmethod
+    def _gs(step):
+        return max(int(step) - 1, 0)
+
+    @staticmethod
+    def exponential_decay(learning_rate, decay_steps, decay_rate, staircase=False):
+        def lr(step):
+            p = schedules._gs(step) / float(decay_steps)
+            return learning_rate * decay_rate ** (math.floor(p) if staircase else p)
+        return lr
+
+    @staticmethod
+    def natural_exp_decay(learning_rate, decay_steps, decay_rate, staircase=False):
+        def lr(step):
+            p = schedules._gs(step) / float(decay_steps)
+            return learning_rate * math.exp(-decay_rate * (math.floor(p) if staircase else p))
+        return lr
+
+    @staticmethod
+    def inverse_time_decay(learning_rate, decay_steps, decay_rate, staircase=False):
+        def lr(step):
+            p = schedules._gs(step) / float(decay_steps)
+            return learning_rate / (1.0 + decay_rate * (math.floor(p) if staircase else p))
+        return lr
+
+    @staticmethod
+    def piecewise_constant(boundaries, values):
+        """values[i] while global_step ≤ boundaries[i]; values[-1] afterwards"""
+        if len(values) != len(boundaries) + 1:
+            raise ValueError("The length of boundaries should be 1 less than the length of values")
+
+        def lr(step):
+            gs = schedules._gs(step)
+            for b, v in zip(boundaries, values):
+                if gs <= b:
+                    return v
+            return values[-1]
+        return lr
+
+    @staticmethod
+    def polynomial_decay(learning_rate, decay_steps, end_learning_rate=0.0001, power=1.0,
+                         cycle=False):
+        def lr(step):
+            gs, ds = schedules._gs(step), float(decay_steps)
+            if cycle:
+                ds *= max(1.0, math.ceil(gs / ds))
+            else:
+                gs = min(gs, decay_steps)
+            return (learning_rate - end_learning_rate) * (1.0 - gs / ds) ** power + \
+                end_learning_rate
+        return lr
+
+    @staticmethod
+    def cosine_decay(learning_rate, decay_steps, alpha=0.0):
+        def lr(step):
+            gs = min(schedules._gs(step), decay_steps)
+            cos = 0.5 * (1.0 + math.cos(math.pi * gs / float(decay_steps)))
+            return learning_rate * ((1.0 - alpha) * cos + alpha)
+        return lr
+
+    @staticmethod
+    def warmup(schedule, warmup_steps, start_factor=0.0):
+        """linear ramp from start_factor·lr to the schedule's value over `warmup_steps`"""
+        base = schedule if callable(schedule) else (lambda step: schedule)
+
+        def lr(step):
+            gs = schedules._gs(step)
+            v = base(step)
+            if gs >= warmup_steps:
+                return v
+            return v * (start_factor + (1.0 - start_factor) * gs / float(warmup_steps))
+        return lr

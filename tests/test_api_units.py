@@ -429,3 +429,28 @@ def test_remaining_tf_optimizers_train_dense_and_sparse(name):
         assert len(sd["sparse"]["emb.weight"]["slots"]) == nslots
     finally:
         sess.close()
+
+
+def test_learning_rate_schedules_follow_tf_formulas():
+    S = parallax.optim.schedules
+    f = S.exponential_decay(0.1, 100, 0.5, staircase=True)
+    assert [f(1), f(100), f(101), f(201)] == [0.1, 0.1, 0.05, 0.025]
+    assert abs(S.exponential_decay(0.1, 100, 0.5)(51) - 0.1 * 0.5 ** 0.5) < 1e-12
+    assert abs(S.natural_exp_decay(1.0, 10, 0.5)(11) - np.exp(-0.5)) < 1e-12
+    assert abs(S.inverse_time_decay(1.0, 10, 0.5, staircase=True)(26) - 0.5) < 1e-12
+    p = S.piecewise_constant([10, 20], [1.0, 0.5, 0.1])
+    assert [p(1), p(11), p(12), p(21), p(22), p(999)] == [1.0, 1.0, 0.5, 0.5, 0.1, 0.1]
+    with pytest.raises(ValueError):
+        S.piecewise_constant([10], [1.0])
+    q = S.polynomial_decay(1.0, 100, end_learning_rate=0.1, power=2.0)
+    assert abs(q(51) - (0.9 * 0.25 + 0.1)) < 1e-12 and q(1000) == 0.1
+    c = S.polynomial_decay(1.0, 100, end_learning_rate=0.0, cycle=True)
+    assert abs(c(151) - (1 - 150 / 200.0)) < 1e-12
+    cos = S.cosine_decay(2.0, 100, alpha=0.1)
+    assert abs(cos(1) - 2.0) < 1e-12 and abs(cos(51) - 2.0 * (0.9 * 0.5 + 0.1)) < 1e-12
+    assert abs(cos(500) - 0.2) < 1e-12
+    w = S.warmup(S.piecewise_constant([100], [1.0, 0.1]), 10, start_factor=0.1)
+    assert abs(w(1) - 0.1) < 1e-12 and abs(w(6) - 0.55) < 1e-12 and w(11) == 1.0 and w(200) == 0.1
+    # a schedule is accepted wherever a learning rate is
+    opt = parallax.optim.Momentum(S.exponential_decay(0.1, 10, 0.5, staircase=True), 0.9)
+    assert opt.hyper(1)[0] == 0.1 and opt.hyper(11)[0] == 0.05
