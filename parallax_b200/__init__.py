@@ -18,7 +18,7 @@ from .config import CommunicationConfig
 from .config import CheckPointConfig
 from .config import ProfileConfig
 
-from .graph import (Graph, ClipByGlobalNorm, ScaleGradients,
+from .graph import (Graph, ClipByGlobalNorm, ClipByValue, ScaleGradients,
                     ExponentialMovingAverage)
 from . import optim
 from . import nn
@@ -28,6 +28,6 @@ __version__ = "0.1.0"
 __all__ = [
     "get_partitioner", "parallel_run", "shard", "log", "Config", "PSConfig",
     "MPIConfig", "CommunicationConfig", "CheckPointConfig", "ProfileConfig",
-    "Graph", "ClipByGlobalNorm", "ScaleGradients", "ExponentialMovingAverage",
+    "Graph", "ClipByGlobalNorm", "ClipByValue", "ScaleGradients", "ExponentialMovingAverage",
     "optim", "nn",
 ]

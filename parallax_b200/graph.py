@@ -10,6 +10,7 @@ lives in the user graph between `tf.gradients` and `apply_gradients`
 
 * `ClipByGlobalNorm(max_norm, params)`  — `tf.clip_by_global_norm`
 * `ScaleGradients(factor, params)`      — e.g. embedding grads × batch_size
+* `ClipByValue(clip, params)`            — `tf.clip_by_value`
 * `ExponentialMovingAverage(decay, params)` — `ema.apply(lstm_vars)`
 
 Fetch/feed names: placeholders are the forward argument names; fetchable
@@ -63,6 +64,19 @@ class ScaleGradients(GradRule):
         self.factor = float(factor)
 
 
+class ClipByValue(GradRule):
+    """Clamp every element of the dense gradients of `params` to
+    ``[-clip_value, clip_value]`` (`tf.clip_by_value`, e.g. tf_cnn_benchmarks'
+    `--gradient_clip`, `benchmark_cnn.py:797-802`).  Applied to each worker's
+    gradient as it is produced (a tensor hook), i.e. before aggregation — with one
+    process per GPU there is no per-worker aggregated tensor to clamp afterwards."""
+
+    def __init__(self, clip_value, params=None):
+        super().__init__(params)
+        self.clip_value = float(clip_value)
+        assert self.clip_value > 0
+
+
 class ExponentialMovingAverage(GradRule):
     """Maintain ``shadow -= (1-decay)·(shadow - var)`` after every update for
     dense `params` (`tf.train.ExponentialMovingAverage.apply`)."""
@@ -82,7 +96,7 @@ class Graph(object):
       optimizer: a `parallax.optim` spec applied to every trainable variable.
       sparse_optimizer: optional different spec for sparse variables.
       loss: key of the scalar to differentiate.
-      grad_rules: list of `ClipByGlobalNorm` / `ScaleGradients`.
+      grad_rules: list of `ClipByGlobalNorm` / `ClipByValue` / `ScaleGradients`.
       ema: optional `ExponentialMovingAverage`.
       loss_scale: the backward pass differentiates ``loss * loss_scale``
         (LM1B uses ``loss * num_steps``).
@@ -105,6 +119,16 @@ class Graph(object):
         self.placeholders = [
             p.name for p in sig.parameters.values()
             if p.kind in (p.POSITIONAL_OR_KEYWORD, p.KEYWORD_ONLY)]
+        self._install_value_clips()
+
+    def _install_value_clips(self):
+        for rule in self.grad_rules:
+            if not isinstance(rule, ClipByValue):
+                continue
+            c = rule.clip_value
+            for name, p in self.model.named_parameters():
+                if p.requires_grad and rule.applies_to(name):
+                    p.register_hook(lambda g, c=c: g if g.is_sparse else g.clamp(-c, c))
 
     # -- helpers used by the engine -------------------------------------------
     def clip_rules(self):

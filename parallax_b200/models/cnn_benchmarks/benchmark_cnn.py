@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from ... import optim
-from ...graph import Graph, ScaleGradients
+from ...graph import ClipByValue, Graph, ScaleGradients
 from ...log import parallax_log as log
 from . import datasets, model_config
 
@@ -158,12 +158,6 @@ class BenchmarkCNN(object):
         net = self.model_conf.build(nclass)
         self.model = _WithAccuracy(net, self.params.data_format == "NHWC",
                                    self.params.print_training_accuracy)
-        if self.params.gradient_clip:
-            c = float(self.params.gradient_clip)
-            # the reference clips the aggregated gradient; with one process per GPU the
-            # clamp is applied to each worker's gradient before aggregation
-            for q in self.model.parameters():
-                q.register_hook(lambda g, c=c: g.clamp(-c, c))
         return self.model
 
     def build_graph(self, num_workers=1):
@@ -182,6 +176,8 @@ class BenchmarkCNN(object):
             opt = optim.RMSProp(lr, p.rmsprop_decay, p.rmsprop_momentum, p.rmsprop_epsilon,
                                 weight_decay=wd)
         rules = [ScaleGradients(1.0 / self.loss_scale)] if self.loss_scale != 1.0 else []
+        if p.gradient_clip:
+            rules.append(ClipByValue(float(p.gradient_clip)))
         return Graph(model, optimizer=opt, loss="loss", loss_scale=self.loss_scale,
                      grad_rules=rules, name="cnn")
 

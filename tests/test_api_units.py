@@ -454,3 +454,26 @@ def test_learning_rate_schedules_follow_tf_formulas():
     # a schedule is accepted wherever a learning rate is
     opt = parallax.optim.Momentum(S.exponential_decay(0.1, 10, 0.5, staircase=True), 0.9)
     assert opt.hyper(1)[0] == 0.1 and opt.hyper(11)[0] == 0.05
+
+
+def test_clip_by_value_rule():
+    from parallax_b200.models.simple import LinearRegression
+    torch.manual_seed(0)
+    m = LinearRegression(2)
+    with torch.no_grad():
+        m.linear.weight.fill_(0.0)
+        m.linear.bias.fill_(0.0)
+    g = parallax.Graph(m, optimizer=parallax.optim.GradientDescent(1.0),
+                       grad_rules=[parallax.ClipByValue(0.25, params=["linear.weight"])])
+    sess, *_ = parallax.parallel_run(g, "localhost",
+                                     parallax_config=parallax.Config(sess_config={"fabric": "host"}))
+    try:
+        x = torch.tensor([[10.0, 0.01], [10.0, 0.01]])
+        y = torch.tensor([100.0, 100.0])
+        sess.run(["loss", "train_op"], {"x": [x], "y": [y]})
+        sd = sess.engine.state_dict()["dense"]["master"]
+        # d loss/d w = 2·mean((0-100)·x) = [-2000, -2]: both clamp to -0.25 ⇒ w = +0.25
+        torch.testing.assert_close(sd["linear.weight"].view(-1), torch.tensor([0.25, 0.25]))
+        assert abs(float(sd["linear.bias"]) - 200.0) < 1e-3        # bias is not clipped
+    finally:
+        sess.close()
