@@ -24,6 +24,7 @@ import os
 import subprocess
 import sys
 import threading
+import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -52,19 +53,25 @@ def parse():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks/throttle reasons DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region.
+
+    The query process is started before the warm-up so it is already streaming when
+    the timed region begins (its start-up alone can exceed a short timed region);
+    every line is stamped on arrival and `stop(t0, t1)` reports the samples that fall
+    inside the timed window (median SM clock under load)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, gpu_index=0):
-        self.proc, self.lines, self.gpu = None, [], gpu_index
+    def __init__(self, gpu_index=0, period_ms=50):
+        self.proc, self.lines, self.gpu, self.period_ms = None, [], gpu_index, period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-i", str(self.gpu), "-lms", "100"],
+                 "-i", str(self.gpu), "-lms", str(self.period_ms)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -73,9 +80,24 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    @classmethod
+    def _parse(cls, stamped):
+        out = []
+        for ts, ln in stamped:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                rec = (ts, float(f[1]), float(f[2]), float(f[3]))
+            except ValueError:
+                continue
+            out.append(rec + ([nm for nm, v in zip(cls.NAMES, f[5:9])
+                               if v.lower().startswith("active")],))
+        return out
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -83,24 +105,21 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
+        recs = self._parse(list(self.lines))
+        inside = [r for r in recs if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)]
+        window = "timed region"
+        if not inside:
+            # a very short timed region can fall between two samples: use the samples
+            # taken under the same load just before it (the warm-up steps)
+            inside, window = ([r for r in recs if t1 is None or r[0] <= t1][-5:] or recs), \
+                "last warm-up samples (timed region shorter than the sampling period)"
+        sm = sorted(r[1] for r in inside)
+        reasons = sorted({nm for r in inside for nm in r[4]})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "sm_max_mhz": max((r[2] for r in inside), default=None),
+                "power_w_max": max((r[3] for r in inside), default=None),
+                "samples": len(inside), "samples_total": len(recs), "window": window,
+                "period_ms": self.period_ms, "reasons": reasons}
 
 
 def reference_arm(args):
@@ -244,14 +263,15 @@ def main():
 
     # ---- device-timed arm: inputs resident on the device -------------------
     batches = [{k: v.to(dev) for k, v in make_batch(gen).items()} for _ in range(4)]
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()          # streaming by the time the timed region starts
     for i in range(Wm):
         eng.train_step(batches[i % 4])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(dev.index or 0)
-    if rank == 0:
-        sampler.start()
+    t_window0 = time.time()
     l0 = nvops.launches["n"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -297,7 +317,7 @@ def main():
         e2e = {"value": desc["items_per_step"] * world * K / (ms2 / 1e3), "unit": unit,
                "ms_per_step": ms2 / K, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "last_loss": float(loss[0])}
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_window0, time.time()) if rank == 0 else None
     # exposed (non-overlapped) comm per step, dense vs sparse — eager steps, device events
     comm_bd = None
     try:
