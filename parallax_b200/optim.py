@@ -67,6 +67,7 @@ class Optimizer(object):
     kind = None
 
     def __init__(self, learning_rate, weight_decay=0.0, name=None):
+        # weight_decay: L2 term added to the gradient of DENSE variables (g + wd·w)
         self.learning_rate = learning_rate
         self.weight_decay = float(weight_decay)
         self.name = name or type(self).__name__
@@ -325,9 +326,14 @@ def apply_dense_(kind, w, g, slots, hp):
 
 def apply_sparse_rows_(kind, w, rows, g, slots, hp):
     """Row-sparse update: `rows` (int64, unique) index dim 0 of `w`/`slots`;
-    `g` is [len(rows), D] — the *summed* gradient of each row."""
+    `g` is [len(rows), D] — the *summed* gradient of each row.  `weight_decay` is a
+    dense-variable setting: sparse rows are not decayed (TF's SparseApply* ops have no
+    L2 term either, and the fused `sparse_update4` kernel takes none)."""
     if rows.numel() == 0:
         return w
+    if hp[HP_WD] != 0.0:
+        hp = list(hp)
+        hp[HP_WD] = 0.0
     w_r = w.index_select(0, rows)
     s_r = tuple(s.index_select(0, rows) for s in slots)
     apply_dense_(kind, w_r, g, s_r, hp)
