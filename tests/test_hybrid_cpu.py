@@ -165,3 +165,51 @@ def test_mpi_and_hybrid_require_sync():
         with pytest.raises(ValueError):
             parallax.parallel_run(graph, "localhost", sync=False,
                                   parallax_config=cfg)
+
+
+def _ckpt_worker(rank, world, ckpt_dir, run_option, nparts, steps, start_step):
+    """train `steps` steps from whatever checkpoint `ckpt_dir` holds; save at the end"""
+    part = parallax.get_partitioner(nparts)
+    model = MLPWithEmbedding(VOCAB, partitioner=part)
+    graph = parallax.Graph(model, optimizer=make_opt("adam"),
+                           ema=parallax.ExponentialMovingAverage(0.9, ["fc2.*"]))
+    # average_sparse: with the default SUM semantics the sparse update depends on the number
+    # of workers (each contributes the gradient of its own mean loss)
+    cfg = parallax.Config(run_option=run_option, search_partitions=False, average_sparse=True,
+                          ckpt_config=parallax.CheckPointConfig(ckpt_dir=ckpt_dir,
+                                                                save_ckpt_steps=10 ** 6))
+    sess, nw, wid, _ = parallax.parallel_run(graph, "localhost", parallax_config=cfg)
+    assert sess.engine.global_step == start_step            # restore-on-start
+    for s in range(start_step, start_step + steps):
+        # every world size consumes the same global batch, split evenly
+        ids, labels = make_batch(s, 2)
+        n = ids.shape[0] // world
+        sess.run(["loss", "train_op"], {"ids": [ids[rank * n:(rank + 1) * n]],
+                                        "labels": [labels[rank * n:(rank + 1) * n]]})
+    sess.save_checkpoint()
+    sd = sess.engine.state_dict()
+    sess.close()
+    return sd
+
+
+def test_checkpoint_resumes_under_other_world_size_mode_and_partitioning(tmp_path):
+    """2 workers HYBRID P=3 for 3 steps → save → ONE worker PS P=5 for 3 more steps equals an
+    uninterrupted 2-worker run: checkpoints hold logical tensors, not a layout."""
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    run_distributed(_ckpt_worker, 2, a, "HYBRID", 3, 3, 0)
+    resumed = run_distributed(_ckpt_worker, 1, a, "PS", 5, 3, 3)[0]
+    straight = run_distributed(_ckpt_worker, 2, b, "HYBRID", 3, 6, 0)[0]
+    assert resumed["global_step"] == straight["global_step"] == 6
+    for n, w in straight["dense"]["master"].items():
+        # the mean over 2 half-batches equals the full-batch mean, for dense and (with
+        # average_sparse) sparse variables alike
+        torch.testing.assert_close(resumed["dense"]["master"][n], w, rtol=2e-4, atol=2e-5)
+        for s_r, s_s in zip(resumed["dense"]["slots"][n], straight["dense"]["slots"][n]):
+            torch.testing.assert_close(s_r, s_s, rtol=2e-4, atol=2e-5)
+    torch.testing.assert_close(resumed["dense"]["ema"]["fc2.weight"],
+                               straight["dense"]["ema"]["fc2.weight"], rtol=2e-4, atol=2e-5)
+    torch.testing.assert_close(resumed["sparse"]["emb.weight"]["weight"],
+                               straight["sparse"]["emb.weight"]["weight"], rtol=2e-4, atol=2e-5)
+    for s_r, s_s in zip(resumed["sparse"]["emb.weight"]["slots"],
+                        straight["sparse"]["emb.weight"]["slots"]):
+        torch.testing.assert_close(s_r, s_s, rtol=2e-4, atol=2e-5)
