@@ -263,7 +263,7 @@ def search_inprocess(sess, next_feed, min_partitions=None, warmup=5, test=10, sy
                     torch.cuda.synchronize(comm.device)
                 comm.barrier()
                 t0 = _time.perf_counter()
-            sess.run(["loss", "train_op"], next_feed())
+            sess.run([eng.graph.loss, "train_op"], next_feed())
         if comm.is_cuda:
             torch.cuda.synchronize(comm.device)
         dt = (_time.perf_counter() - t0) / test
