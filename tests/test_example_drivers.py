@@ -65,3 +65,25 @@ def test_lm1b_and_simple_drivers_two_workers(tmp_path):
     assert "Iteration 11" in logs[0] and (tmp_path / "lm1b" / "analysis_worker_1.json").exists()
     logs = _run(tmp_path, "simple/simple_driver.py", [])
     assert "learned" in logs[0] or "step" in logs[0]
+
+
+def test_horovod_style_examples_under_run_cli(tmp_path):
+    env = {k: v for k, v in os.environ.items()
+           if not k.startswith("PARALLAX_") and k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env.update(CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    base = [sys.executable, "-m", "parallax_b200.run", "-np", "2"]
+    r = subprocess.run(base + [os.path.join(ROOT, "examples/horovod/pytorch_mnist.py"),
+                               "--epochs", "4", "--no-cuda", "--lr", "0.05", "--num-synthetic",
+                               "2048"], env=env, cwd=ROOT, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "finished gradual learning rate warmup to 0.1" in r.stdout
+    last = [l for l in r.stdout.splitlines() if "Epoch 4:" in l][-1]
+    assert float(last.split("accuracy")[1].split()[0]) > 0.5
+    r = subprocess.run(base + [os.path.join(ROOT, "examples/horovod/pytorch_synthetic_benchmark.py"),
+                               "--model", "lenet", "--batch-size", "4", "--num-iters", "2",
+                               "--num-batches-per-iter", "2", "--num-warmup-batches", "1",
+                               "--fp16-allreduce", "--no-cuda"], env=env, cwd=ROOT,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "Total img/sec on 2 worker(s)" in r.stdout
