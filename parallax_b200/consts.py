@@ -30,6 +30,7 @@ PARALLAX_MIN_PARTITIONS = "PARALLAX_MIN_PARTITIONS"
 PARALLAX_PARTITIONS = "PARALLAX_PARTITIONS"
 PARALLAX_SEARCH = "PARALLAX_SEARCH"
 PARALLAX_SEARCH_ADDR = "PARALLAX_SEARCH_ADDR"
+PARALLAX_SEARCH_AUTHKEY = "PARALLAX_SEARCH_AUTHKEY"    # per-job secret of the stats queue
 
 # --- misc -------------------------------------------------------------------
 PARALLAX_LOG_LEVEL = "PARALLAX_LOG_LEVEL"

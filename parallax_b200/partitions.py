@@ -24,7 +24,7 @@ from multiprocessing.managers import BaseManager
 import numpy as np
 
 from .consts import (PARALLAX_MIN_PARTITIONS, PARALLAX_PARTITIONS,
-                     PARALLAX_SEARCH)
+                     PARALLAX_SEARCH, PARALLAX_SEARCH_AUTHKEY)
 from .log import parallax_log
 
 
@@ -158,13 +158,20 @@ class _QueueManager(BaseManager):
     pass
 
 
+def _authkey():
+    """the job's queue secret: generated by the launcher, handed to the workers through
+    the environment"""
+    return os.environ.get(PARALLAX_SEARCH_AUTHKEY, "parallax").encode()
+
+
 class PartitionStatCollector(object):
     """Master-side collector: workers push their window-mean step time to a
     `BaseManager` queue (reference `partitions.py:53-138`)."""
 
-    def __init__(self, p_to_test, address, min_partitions=None):
+    def __init__(self, p_to_test, address, min_partitions=None, authkey=None):
         self.state = SearchState(p_to_test, min_partitions)
         self.address = address
+        self.authkey = (authkey.encode() if isinstance(authkey, str) else authkey) or _authkey()
         self.start = None
         self.m = None
         self._q = None
@@ -182,7 +189,7 @@ class PartitionStatCollector(object):
         host, port = self.address.rsplit(":", 1)
         self.m = _QueueManager(address=("127.0.0.1" if host in ("", "localhost")
                                         else host, int(port)),
-                               authkey=b"parallax")
+                               authkey=self.authkey)
         self.m.start()
         return self.m
 
@@ -228,7 +235,7 @@ def send_exec_time(address, exec_time):
     (reference `common/session_context.py:64-71`)."""
     host, port = address.rsplit(":", 1)
     _QueueManager.register("queue")
-    m = _QueueManager(address=(host, int(port)), authkey=b"parallax")
+    m = _QueueManager(address=(host, int(port)), authkey=_authkey())
     m.connect()
     m.queue().put(float(exec_time))
 

@@ -80,9 +80,11 @@ def _parallax_run_master(graph, config, resource_info):
     if search:
         min_p = int(os.environ[consts.PARALLAX_MIN_PARTITIONS])
         addr = "127.0.0.1:%d" % get_empty_port(1)[0]
-        collector = PartitionStatCollector(max(min_p, n_machines), addr, min_p)
+        secret = os.urandom(16).hex()
+        collector = PartitionStatCollector(max(min_p, n_machines), addr, min_p, authkey=secret)
         collector.setup_manager()
         extra_env[consts.PARALLAX_SEARCH_ADDR] = addr
+        extra_env[consts.PARALLAX_SEARCH_AUTHKEY] = secret
 
     procs = []
 
