@@ -49,6 +49,8 @@ def parse():
                     help="tiny config for plumbing checks (NOT a valid number)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dense-nvls", default="auto", choices=["auto", "on", "off"],
+                    help="NVLS multicast dense step: auto = on a full 8-GPU box")
     return ap.parse_args()
 
 
@@ -247,6 +249,8 @@ def main():
                "bert": build_bert}[args.model]
     graph, make_batch, desc, metric, unit, baseline = builder(args, parallax, torch)
     sc = {"compute_dtype": args.dtype, "cuda_graph": not args.no_graph}
+    if args.dense_nvls != "auto":
+        sc["dense_nvls"] = args.dense_nvls == "on"
     cfg = parallax.Config(run_option=args.run_option, search_partitions=False,
                           sess_config=sc)
     sess, nw, wid, _ = parallax.parallel_run(graph, "localhost:0", sync=True,

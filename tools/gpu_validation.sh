@@ -35,6 +35,10 @@ if [ "$MODE" = single ]; then
 else
   run mp_worker_$N 240 $TR --master-port 29541 tests/mp_nvlink_worker.py
   run bench_lm1b_$N 240 $TR --master-port 29542 bench.py --gpus "$N" --steps 30 --warmup 5
+  if [ "$N" -ge 4 ]; then
+    run bench_lm1b_nvls_$N 240 $TR --master-port 29546 bench.py --gpus "$N" --steps 30 --warmup 5 \
+        --dense-nvls on
+  fi
   run bench_resnet_$N 300 $TR --master-port 29543 bench.py --gpus "$N" --steps 20 --warmup 5 \
       --model resnet50
   run sweep_$N 300 $TR --master-port 29544 tools/allreduce_sweep.py
