@@ -6,6 +6,9 @@ Public surface (parity with `parallax/parallax/__init__.py:16-26`):
 `CheckPointConfig`, `ProfileConfig`, `get_partitioner`, `shard`, `log`; plus
 the torch-side pieces a TF graph provided implicitly: `Graph`, `optim`, `nn`.
 """
+from . import consts as _consts
+_consts.adopt_horovod_env()          # HOROVOD_TIMELINE & co. work under their own names
+
 from .partitions import get_partitioner
 from .runner import parallel_run
 from . import shard

@@ -44,6 +44,32 @@ PARALLAX_AUTOTUNE_LOG = "PARALLAX_AUTOTUNE_LOG"
 PARALLAX_DEBUG_CONSISTENCY = "PARALLAX_DEBUG_CONSISTENCY"
 
 
+# Horovod's knobs (`horovod/common/operations.h:33-46`) are honoured under their own names
+# too, so a job script written for horovodrun keeps working: HOROVOD_X seeds PARALLAX_X.
+HOROVOD_ENV_ALIASES = {
+    "HOROVOD_TIMELINE": PARALLAX_TIMELINE,
+    "HOROVOD_STALL_CHECK_TIME_SECONDS": PARALLAX_STALL_CHECK_TIME_SECONDS,
+    "HOROVOD_STALL_SHUTDOWN_TIME_SECONDS": PARALLAX_STALL_SHUTDOWN_TIME_SECONDS,
+    "HOROVOD_FUSION_THRESHOLD": PARALLAX_FUSION_THRESHOLD,
+    "HOROVOD_AUTOTUNE": PARALLAX_AUTOTUNE,
+    "HOROVOD_AUTOTUNE_LOG": PARALLAX_AUTOTUNE_LOG,
+    "HOROVOD_CACHE_CAPACITY": "PARALLAX_CACHE_CAPACITY",
+    "HOROVOD_LOG_LEVEL": PARALLAX_LOG_LEVEL,
+}
+
+
+def adopt_horovod_env(environ=None):
+    """copy HOROVOD_* settings to their PARALLAX_* names where the latter are unset;
+    returns the names adopted"""
+    env = os.environ if environ is None else environ
+    adopted = []
+    for src, dst in HOROVOD_ENV_ALIASES.items():
+        if src in env and dst not in env:
+            env[dst] = env[src]
+            adopted.append(dst)
+    return adopted
+
+
 def _user():
     try:
         return getpass.getuser()

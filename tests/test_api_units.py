@@ -477,3 +477,13 @@ def test_clip_by_value_rule():
         assert abs(float(sd["linear.bias"]) - 200.0) < 1e-3        # bias is not clipped
     finally:
         sess.close()
+
+
+def test_horovod_environment_names_are_honoured():
+    from parallax_b200 import consts
+    env = {"HOROVOD_TIMELINE": "/tmp/t.json", "HOROVOD_STALL_CHECK_TIME_SECONDS": "5",
+           "PARALLAX_STALL_CHECK_TIME_SECONDS": "9", "HOROVOD_CACHE_CAPACITY": "64"}
+    adopted = consts.adopt_horovod_env(env)
+    assert env["PARALLAX_TIMELINE"] == "/tmp/t.json" and env["PARALLAX_CACHE_CAPACITY"] == "64"
+    assert env["PARALLAX_STALL_CHECK_TIME_SECONDS"] == "9"        # an explicit setting wins
+    assert sorted(adopted) == ["PARALLAX_CACHE_CAPACITY", "PARALLAX_TIMELINE"]
