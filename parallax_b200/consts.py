@@ -41,7 +41,6 @@ PARALLAX_STALL_SHUTDOWN_TIME_SECONDS = "PARALLAX_STALL_SHUTDOWN_TIME_SECONDS"
 PARALLAX_FUSION_THRESHOLD = "PARALLAX_FUSION_THRESHOLD"
 PARALLAX_AUTOTUNE = "PARALLAX_AUTOTUNE"
 PARALLAX_AUTOTUNE_LOG = "PARALLAX_AUTOTUNE_LOG"
-PARALLAX_DEBUG_CONSISTENCY = "PARALLAX_DEBUG_CONSISTENCY"
 
 
 # Horovod's knobs (`horovod/common/operations.h:33-46`) are honoured under their own names

@@ -76,7 +76,12 @@ class NVDenseGroup(object):
         self.device = fabric.device
         opts = options or {}
         self.options = opts
-        self.bucket_bytes = int(opts.get("bucket_bytes", 32 << 20))
+        # bucket size: sess_config["bucket_bytes"], else PARALLAX_FUSION_THRESHOLD (Horovod's
+        # HOROVOD_FUSION_THRESHOLD, `operations.cc:1030`), else 32 MiB
+        import os
+        from .. import consts
+        self.bucket_bytes = int(opts.get("bucket_bytes") or
+                                os.environ.get(consts.PARALLAX_FUSION_THRESHOLD) or (32 << 20))
         self.update = opts.get("dense_update", "sharded")   # or "replicated"
         if not route.sync:
             self.update = "async"
