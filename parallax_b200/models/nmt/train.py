@@ -103,6 +103,10 @@ def with_sparse_capacity(config, hp):
     cfg = copy.copy(config)
     sc = dict(cfg.sess_config) if isinstance(cfg.sess_config, dict) else {}
     sc.setdefault("sparse_capacity", sparse_capacity(hp))
+    if sc.get("cuda_graph"):
+        # the encoders pack by length (a host read of the lengths) and batch shapes vary
+        log.warning("cuda_graph is not supported for the NMT models; running eagerly")
+        sc["cuda_graph"] = False
     cfg.sess_config = sc
     return cfg
 
