@@ -64,8 +64,13 @@ class MPIConfig(object):
     user scripts relied on.
     """
 
-    def __init__(self, mpirun_options=''):
+    def __init__(self, mpirun_options='', use_allgatherv=None):
         self.mpirun_options = self.parse_mpirun_options(mpirun_options)
+        # The reference's docs still show `MPIConfig(use_allgatherv=…)` although the
+        # option was removed from its code (`doc/parallax_api.md:62,81` vs
+        # `common/config.py:51-53`).  Accepted so scripts written from the docs run;
+        # the AR route's sparse aggregation is always a variable-length all-gather.
+        self.use_allgatherv = use_allgatherv
 
     def parse_mpirun_options(self, mpirun_options):
         if isinstance(mpirun_options, str):
