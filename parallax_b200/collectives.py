@@ -283,6 +283,8 @@ class Compression(object):
 
 
 def allreduce(tensor, average=True, name=None, out=None, compression=None):
+    if out is None and compression is None and _wants_grad(tensor):
+        return _AllreduceFn.apply(tensor, average, name)
     if compression is not None and compression is not Compression.none:
         c, ctx = compression.compress(tensor)
         r = compression.decompress(allreduce(c, average, name), ctx)
@@ -349,6 +351,12 @@ def grouped_allreduce(tensors, average=True, name=None):
 
 def allgather(tensor, name=None):
     """Concatenate `tensor` from all ranks along dim 0 (first dims may differ)."""
+    if _wants_grad(tensor):
+        return _AllgatherFn.apply(tensor, name)
+    return _allgather_impl(tensor, name)
+
+
+def _allgather_impl(tensor, name=None):
     st = _st()
     _validate(name, "allgather", tensor)
     W = st.comm.world
@@ -380,6 +388,12 @@ def allgather(tensor, name=None):
 
 
 def broadcast(tensor, root_rank, name=None, out=None):
+    if out is None and _wants_grad(tensor):
+        return _BroadcastFn.apply(tensor, root_rank, name)
+    return _broadcast_impl(tensor, root_rank, name, out)
+
+
+def _broadcast_impl(tensor, root_rank, name=None, out=None):
     st = _st()
     _validate(name, "broadcast", tensor, extra=(root_rank,))
     W = st.comm.world
@@ -424,6 +438,60 @@ def broadcast_parameters(params, root_rank=0):
             with torch.no_grad():
                 broadcast_(p.data if hasattr(p, "data") else p, root_rank,
                            name="broadcast." + name)
+
+
+# ---------------------------------------------------------------- autograd
+# Horovod registers gradients for its collective ops
+# (`horovod/tensorflow/mpi_ops.py:82-173`, `horovod/torch/mpi_ops.py` autograd Functions):
+# d(allreduce) = allreduce of the upstream gradient; d(allgather) = this rank's rows of the
+# summed gradient; d(broadcast) = the summed gradient on the root, zero elsewhere.
+def _wants_grad(t):
+    return torch.is_grad_enabled() and torch.is_tensor(t) and t.requires_grad and \
+        not t.is_sparse
+
+
+def _gname(name):
+    return None if name is None else name + ".grad"
+
+
+class _AllreduceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tensor, average, name):
+        ctx.average, ctx.name = average, name
+        return _allreduce_impl(tensor.detach(), average, name)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return _allreduce_impl(grad.contiguous(), ctx.average, _gname(ctx.name)), None, None
+
+
+class _AllgatherFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tensor, name):
+        st = _st()
+        ctx.name, ctx.n = name, int(tensor.shape[0])
+        sizes = st.comm.all_gather_object(ctx.n) if st.comm.world > 1 else [ctx.n]
+        ctx.offset = sum(sizes[:st.comm.rank])
+        return _allgather_impl(tensor.detach(), name)
+
+    @staticmethod
+    def backward(ctx, grad):
+        summed = _allreduce_impl(grad.contiguous(), False, _gname(ctx.name))
+        return summed[ctx.offset:ctx.offset + ctx.n], None
+
+
+class _BroadcastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tensor, root_rank, name):
+        ctx.root, ctx.name = root_rank, name
+        return _broadcast_impl(tensor.detach(), root_rank, name)
+
+    @staticmethod
+    def backward(ctx, grad):
+        summed = _allreduce_impl(grad.contiguous(), False, _gname(ctx.name))
+        if _st().comm.rank != ctx.root:
+            summed = torch.zeros_like(summed)
+        return summed, None, None
 
 
 # ------------------------------------------------------------- handle API

@@ -139,3 +139,81 @@ def test_schedule_callback_momentum_correction_single_process():
             cbs.CallbackList([]).no_such_hook
     finally:
         hvd.shutdown()
+
+
+def _sweep_worker(rank, world):
+    import itertools
+    import torch
+    from parallax_b200 import collectives as hvd
+    hvd.init()
+    out = {"ok": True, "msgs": []}
+
+    def check(cond, msg):
+        if not cond:
+            out["ok"] = False
+            out["msgs"].append(msg)
+    # allreduce / allgather / broadcast over dtypes × ranks-of-tensor (test_torch.py sweeps)
+    dtypes = [torch.int32, torch.int64, torch.float16, torch.float32, torch.float64]
+    for dt, dim in itertools.product(dtypes, (1, 2, 3)):
+        torch.manual_seed(1234)
+        shape = (5,) * dim
+        base = (torch.rand(shape) * 20 - 10).to(dt)
+        x = base * (rank + 1) if dt.is_floating_point else base * (rank + 1)
+        tag = "%s.%d" % (str(dt).split(".")[1], dim)
+        s = hvd.allreduce(x, average=False, name="ar." + tag)
+        want = base * sum(r + 1 for r in range(world))
+        tol = 1e-2 if dt == torch.float16 else 1e-5
+        check(s.dtype == dt and torch.allclose(s.double(), want.double(), atol=tol * 40),
+              "allreduce sum " + tag)
+        y = x.clone()
+        hvd.allreduce_(y, average=False, name="ari." + tag)
+        check(torch.equal(y, s), "allreduce_ in place " + tag)
+        if dt.is_floating_point:
+            a = hvd.allreduce(x, average=True, name="av." + tag)
+            check(torch.allclose(a.double(), want.double() / world, atol=tol * 40), "avg " + tag)
+        h = hvd.allreduce_async(x, average=False, name="as." + tag)
+        while not hvd.poll(h):
+            pass
+        check(torch.equal(hvd.synchronize(h), s), "async " + tag)
+        g = hvd.allgather(torch.full((rank + 1,) + shape[1:], rank, dtype=dt), name="ag." + tag)
+        check(g.shape[0] == sum(r + 1 for r in range(world)) and g.dtype == dt and
+              float(g[0].double().max()) == 0 and float(g[-1].double().min()) == world - 1,
+              "allgather variable " + tag)
+        b = hvd.broadcast(torch.full(shape, rank, dtype=dt), root_rank=world - 1, name="bc." + tag)
+        check(b.dtype == dt and float(b.double().min()) == world - 1, "broadcast " + tag)
+        z = torch.full(shape, rank, dtype=dt)
+        hvd.broadcast_(z, root_rank=0, name="bci." + tag)
+        check(float(z.double().max()) == 0, "broadcast_ " + tag)
+    # dtype mismatch across ranks is an error on every rank
+    try:
+        hvd.allreduce(torch.zeros(3, dtype=torch.float32 if rank == 0 else torch.float64),
+                      name="bad.dtype")
+        check(False, "dtype mismatch not detected")
+    except hvd.HorovodInternalError:
+        pass
+    # gradients of the collectives (horovod registers them for its ops)
+    w = torch.arange(4, dtype=torch.float64, requires_grad=True)
+    y = hvd.allreduce(w * (rank + 1), average=False, name="grad.ar")
+    (y * torch.tensor([1.0, 2.0, 3.0, 4.0], dtype=torch.float64) * (rank + 2)).sum().backward()
+    # dL_r/dy = (r+2)·c ; dy/dw_r = (r+1) ⇒ grad = (r+1)·Σ_r'(r'+2)·c
+    c = torch.tensor([1.0, 2.0, 3.0, 4.0], dtype=torch.float64)
+    check(torch.allclose(w.grad, (rank + 1) * sum(r + 2 for r in range(world)) * c), "grad ar")
+    v = torch.ones(rank + 1, 2, dtype=torch.float64, requires_grad=True)
+    g = hvd.allgather(v, name="grad.ag")
+    (g * torch.arange(g.numel(), dtype=torch.float64).view_as(g)).sum().backward()
+    off = sum(r + 1 for r in range(rank)) * 2
+    want = world * torch.arange(off, off + v.numel(), dtype=torch.float64).view_as(v)
+    check(torch.allclose(v.grad, want), "grad allgather")
+    u = torch.full((3,), float(rank + 1), dtype=torch.float64, requires_grad=True)
+    b = hvd.broadcast(u, root_rank=1, name="grad.bc")
+    (b * (rank + 1)).sum().backward()
+    want = torch.full((3,), float(sum(r + 1 for r in range(world)))) if rank == 1 \
+        else torch.zeros(3)
+    check(torch.allclose(u.grad, want.double()), "grad broadcast")
+    hvd.shutdown()
+    return out
+
+
+def test_dtype_dim_sweep_and_gradients_two_ranks():
+    for r in run_distributed(_sweep_worker, 2, timeout=400):
+        assert r["ok"], r["msgs"]
