@@ -82,6 +82,10 @@ def log_uniform_logq_unique(ids, num_tries, range_max):
 
 
 class LM1B(nn.Module):
+    # softmax_w and softmax_b are always looked up with the same ids: one lookup / push /
+    # owner kernel serves both on the NVLink fabric (`parallax.nn.lookup_many`)
+    co_lookup_groups = [("softmax_w", "softmax_b")]
+
     def __init__(self, vocab_size=793470, emb_size=512, state_size=2048,
                  projected_size=512, num_sampled=8192, num_steps=20,
                  num_shards=32, keep_prob=0.9, lazy=False):
@@ -106,10 +110,10 @@ class LM1B(nn.Module):
     def lstm(self, x, c, h):
         """x: [B, T, E] -> outputs [B*T, P] (rows ordered like y.reshape(-1)),
         final c, h.  One fused autograd node (`ops.fused.lstm_layer`)."""
-        from ..ops.fused import lstm_layer
+        from ..ops.fused import lstm_layer_stacked
         Bsz, T, E = x.shape
-        H, c, h = lstm_layer(x.transpose(0, 1), self.W[:E], self.W[E:], self.B,
-                             self.W_P, c, h, forget_bias=1.0)
+        H, c, h = lstm_layer_stacked(x.transpose(0, 1), self.W, self.B, self.W_P, c, h,
+                                     forget_bias=1.0)
         out = H.transpose(0, 1)                      # [B, T, P]
         if self.training and self.keep_prob < 1.0:
             out = F.dropout(out, 1.0 - self.keep_prob)
@@ -128,10 +132,14 @@ class LM1B(nn.Module):
             torch.zeros(Bsz, self.state_size, device=dev, dtype=dt)
         h = initial_state_h if initial_state_h is not None else \
             torch.zeros(Bsz, self.projected_size, device=dev, dtype=dt)
-        inputs, c, h = self.lstm(e, c.float(), h.to(dt))
         targets = y.reshape(-1)
-        if self.training and self.num_sampled > 0:
-            loss = self.sampled_softmax_loss(inputs, targets)
+        sampled_mode = self.training and self.num_sampled > 0
+        # the sampler and the softmax-table lookups do not depend on the LSTM: issue them
+        # on a side stream so they run underneath the (latency-bound) recurrent chain
+        pre = self.prefetch_softmax(targets) if sampled_mode else None
+        inputs, c, h = self.lstm(e, c.float(), h.to(dt))
+        if sampled_mode:
+            loss = self.sampled_softmax_loss(inputs, targets, pre)
         else:
             loss = self.full_softmax_loss(inputs, targets)
         if w is not None:
@@ -139,21 +147,45 @@ class LM1B(nn.Module):
         return {"loss": loss.mean(), "final_state_c": c.detach(),
                 "final_state_h": h.detach()}
 
-    def sampled_softmax_loss(self, inputs, targets):
-        from ..ops.fused import sampled_softmax_loss
+    def prefetch_softmax(self, targets):
+        """Negative sampling + one fused lookup of (softmax_w, softmax_b) rows for
+        targets ∪ samples; on CUDA it runs on the side stream."""
         N, S, V = targets.numel(), self.num_sampled, self.vocab_size
-        sampled, tries = log_uniform_sample_unique(S, V, inputs.device)
-        ids = torch.cat([targets.to(torch.int64), sampled])
-        w_all = self.softmax_w(ids)                 # [N+S, P]  one lookup per table
-        b_all = self.softmax_b(ids).squeeze(-1)     # [N+S]
-        logq = log_uniform_logq_unique(ids, tries, V)
+        dev = self.W.device
+
+        def work():
+            sampled, tries = log_uniform_sample_unique(S, V, dev)
+            ids = torch.cat([targets.to(torch.int64), sampled])
+            w_all, b_all = pnn.lookup_many([self.softmax_w, self.softmax_b], ids)
+            logq = log_uniform_logq_unique(ids, tries, V)
+            return sampled, w_all, b_all.squeeze(-1), logq
+        if dev.type != "cuda":
+            return work() + (None,)
+        from ..ops import sinks
+        cur = torch.cuda.current_stream(dev)
+        side = sinks.side_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            out = work()
+        return out + (side,)
+
+    def sampled_softmax_loss(self, inputs, targets, pre=None):
+        from ..ops.fused import sampled_softmax_loss
+        N = targets.numel()
+        sampled, w_all, b_all, logq, side = pre if pre is not None \
+            else self.prefetch_softmax(targets)
+        if side is not None:
+            cur = torch.cuda.current_stream(inputs.device)
+            cur.wait_stream(side)
+            for t in (sampled, w_all, b_all, logq):
+                t.record_stream(cur)
         return sampled_softmax_loss(inputs, w_all[:N], w_all[N:], b_all[:N], b_all[N:],
                                     logq[:N], logq[N:], targets, sampled)
 
     def full_softmax_loss(self, inputs, targets):
         ids = torch.arange(self.vocab_size, device=inputs.device)
-        w = self.softmax_w(ids).to(inputs.dtype)
-        b = self.softmax_b(ids).squeeze(-1).float()
+        w, b = pnn.lookup_many([self.softmax_w, self.softmax_b], ids)
+        w, b = w.to(inputs.dtype), b.squeeze(-1).float()
         logits = (inputs @ w.t()).float() + b
         return F.cross_entropy(logits, targets, reduction="none")
 

@@ -113,3 +113,12 @@ def partition(module, partitioner):
     module.sparse = True
     module.partitioner = partitioner
     return module
+
+
+def lookup_many(modules, ids):
+    """Rows of several embedding modules for the SAME ids (e.g. a softmax weight table
+    and its bias table).  Declare the modules as a group on the model
+    (``co_lookup_groups = [("softmax_w", "softmax_b")]``) and the NVLink fabric serves
+    them with one lookup kernel, one push kernel and one owner kernel per step."""
+    from .parallel.engine import lookup_many as _lm
+    return _lm(list(modules), ids)

@@ -17,9 +17,29 @@ c_void_p, c_int, c_size_t, c_float = \
 PP = ctypes.POINTER(ctypes.c_void_p)
 
 
-class PxTableGeom(ctypes.Structure):
-    _fields_ = [(n, c_int) for n in ("V", "P", "W", "rows_per_part", "D4",
-                                     "strategy", "replicated", "extras", "base")]
+class PxGroupGeom(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in ("V", "P", "W", "rows_per_part", "strategy",
+                                     "replicated", "extras", "base")] + \
+        [("part_owner", c_void_p), ("part_slot", c_void_p)]
+
+
+class PxLookupTable(ctypes.Structure):
+    _fields_ = [("srcs", c_void_p), ("out", c_void_p), ("D4", c_int),
+                ("src_bf16", c_int), ("out_bf16", c_int), ("pad", c_int)]
+
+
+class PxPushTable(ctypes.Structure):
+    _fields_ = [("grads", c_void_p), ("staging", c_void_p), ("rings", c_void_p),
+                ("tables", c_void_p), ("slot0s", c_void_p), ("slot1s", c_void_p),
+                ("slot2s", c_void_p), ("shadows", c_void_p), ("hp", c_void_p),
+                ("D4", c_int), ("kind", c_int), ("scale", c_float), ("pad", c_int)]
+
+
+class PxOwnerTable(ctypes.Structure):
+    _fields_ = [("ring", c_void_p), ("table", c_void_p), ("slot0", c_void_p),
+                ("slot1", c_void_p), ("slot2", c_void_p), ("shadow", c_void_p),
+                ("hp", c_void_p), ("D4", c_int), ("kind", c_int), ("avg", c_float),
+                ("pad", c_int)]
 
 
 _SIGS = {
@@ -46,41 +66,34 @@ _SIGS = {
                              c_int, c_int, c_int, c_void_p]),
     "px_allgather": (c_int, [PP, c_void_p, c_void_p, c_int, c_int, c_size_t, c_int,
                              c_int, c_int, c_void_p]),
-    "px_dense_step": (c_int, [PP, PP, c_void_p, c_void_p, c_void_p, c_void_p,
+    "px_dense_step": (c_int, [PP, PP, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                               c_float, c_float, c_int, c_int, c_int, c_void_p,
                               c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p]),
     "px_clip_scale": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                               c_void_p]),
-    "px_dense_async": (c_int, [c_void_p, c_void_p, PP, PP, PP, c_void_p, c_void_p,
+    "px_dense_async": (c_int, [c_void_p, c_void_p, PP, PP, PP, PP, c_void_p, c_void_p,
                                c_size_t, c_int, c_int, c_int, c_int, c_int,
                                c_void_p]),
     "px_sumsq": (c_int, [c_void_p, c_size_t, c_int, c_float, c_void_p, c_void_p]),
     "px_sparse_ctl_bytes": (c_size_t, []),
     "px_sparse_hdr_words": (c_int, []),
-    "px_sparse_lookup": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int,
-                                 c_void_p, ctypes.POINTER(PxTableGeom), c_void_p,
+    "px_sparse_group_max": (c_int, []),
+    "px_sparse_ctl_time_offset": (c_int, []),
+    "px_sparse_ctl_overflow_offset": (c_int, []),
+    "px_sparse_lookup": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(PxLookupTable),
+                                 c_int, c_void_p, ctypes.POINTER(PxGroupGeom), c_void_p,
                                  c_void_p, c_int, c_void_p]),
-    "px_sparse_dedup": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                ctypes.POINTER(PxTableGeom), c_int, c_int, c_void_p]),
-    "px_sparse_push": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                               c_size_t, c_int, ctypes.POINTER(PxTableGeom), c_float,
-                               c_int, c_int, c_void_p]),
-    "px_sparse_claim": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p,
-                                c_void_p, ctypes.POINTER(PxTableGeom), c_int,
+    "px_sparse_push": (c_int, [c_void_p, c_int, ctypes.POINTER(PxPushTable), c_int, c_int,
+                               c_int, c_int, c_void_p, c_void_p, c_int,
+                               ctypes.POINTER(PxGroupGeom), c_void_p, c_int, c_int, c_int,
+                               c_void_p]),
+    "px_sparse_owner": (c_int, [ctypes.POINTER(PxOwnerTable), c_int, c_int, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                ctypes.POINTER(PxGroupGeom), c_void_p, c_int, c_int, c_int,
                                 c_void_p]),
-    "px_sparse_apply": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_float,
-                                c_int, c_void_p, c_void_p,
-                                ctypes.POINTER(PxTableGeom), c_int, c_int, c_int,
-                                c_void_p]),
-    "px_sparse_async_apply": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p,
-                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                      c_void_p, c_void_p, c_void_p, c_float, c_int,
-                                      ctypes.POINTER(PxTableGeom), c_int, c_void_p]),
+    "px_stamp": (c_int, [c_void_p, c_void_p]),
 }
 
 

@@ -22,9 +22,7 @@
 // local update after a plain all-reduce in "replicated" AR mode).
 #include "common.cuh"
 #include "launch.h"
-
-enum { PX_SGD = 0, PX_MOMENTUM = 1, PX_ADAGRAD = 2, PX_ADAM = 3, PX_RMSPROP = 4 };
-enum { HP_LR = 0, HP_A, HP_B, HP_EPS, HP_WD, HP_STEP, HP_GSCALE, HP_FLAGS };
+#include "optim_rules.cuh"
 
 struct DenseStepArgs {
   PeerPtrs grads;    // rotated, element type T
@@ -32,6 +30,7 @@ struct DenseStepArgs {
   float* master;     // [slice] fp32 master weights of the owned slice
   float* slot0;      // [slice] or null
   float* slot1;      // [slice] or null
+  float* slot2;      // [slice] or null (centered RMSProp)
   float* ema;        // [slice] or null
   float* red;        // [slice] fp32 scratch (modes 1/2) or null
   const float* hp;   // device hyper-parameters (8 floats)
@@ -61,33 +60,6 @@ __device__ __forceinline__ void ds_mm_st(void* p, const uint4& r) {
                ::"l"(p), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w) : "memory");
 }
 
-__device__ __forceinline__ void px_update(int kind, float lr, float a, float b, float eps,
-                                          float wd, float nesterov, float g, float& w, float& s0,
-                                          float& s1) {
-  if (wd != 0.f) g = fmaf(wd, w, g);
-  switch (kind) {
-    case PX_SGD: w = fmaf(-lr, g, w); break;
-    case PX_MOMENTUM:
-      s0 = fmaf(a, s0, g);
-      w = nesterov != 0.f ? fmaf(-lr, fmaf(a, s0, g), w) : fmaf(-lr, s0, w);
-      break;
-    case PX_ADAGRAD:
-      s0 = fmaf(g, g, s0);
-      w = fmaf(-lr * g, rsqrtf(s0), w);
-      break;
-    case PX_ADAM:
-      s0 = fmaf(a, s0, (1.f - a) * g);
-      s1 = fmaf(b, s1, (1.f - b) * g * g);
-      w -= lr * s0 / (sqrtf(s1) + eps);
-      break;
-    case PX_RMSPROP:
-      s0 = fmaf(a, s0, (1.f - a) * g * g);
-      s1 = fmaf(b, s1, lr * g * rsqrtf(s0 + eps));
-      w -= s1;
-      break;
-  }
-}
-
 template <int VN>
 __device__ __forceinline__ void ld_f32(const float* p, float* f) {
 #pragma unroll
@@ -105,7 +77,7 @@ __device__ __forceinline__ void st_f32(float* p, const float* f) {
                                 __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3])));
 }
 
-template <typename T, int W>
+template <typename T, int W, int FAM>
 __global__ void __launch_bounds__(512)
 px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr) {
   constexpr int VN = Vec16<T>::N;
@@ -115,8 +87,7 @@ px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr
   const size_t nvec = slice / VN;
   const size_t base = (size_t)a.rank * slice;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const float lr = a.hp[HP_LR], ha = a.hp[HP_A], hb = a.hp[HP_B], eps = a.hp[HP_EPS],
-              wd = a.hp[HP_WD], nesterov = a.hp[HP_FLAGS];
+  const PxHP h = px_load_hp(a.hp);
   float gmul = a.avg * a.hp[HP_GSCALE];
   if (mode == 2) gmul = 1.f;                       // already applied in REDUCE
   if (mode != 1 && a.clip != nullptr) gmul *= *a.clip;
@@ -152,15 +123,20 @@ px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr
       st_f32<VN>(a.red + e, g);
       continue;
     }
-    float w[VN], s0[VN], s1[VN];
+    float w[VN], s0[VN], s1[VN], s2[FAM == 1 ? VN : 1];
     ld_f32<VN>(a.master + e, w);
     if (a.slot0) ld_f32<VN>(a.slot0 + e, s0);
     if (a.slot1) ld_f32<VN>(a.slot1 + e, s1);
+    if (FAM == 1 && a.slot2) ld_f32<VN>(a.slot2 + e, s2);
 #pragma unroll
-    for (int i = 0; i < VN; ++i) px_update(kind, lr, ha, hb, eps, wd, nesterov, g[i], w[i], s0[i], s1[i]);
+    for (int i = 0; i < VN; ++i) {
+      const float gi = h.wd != 0.f ? fmaf(h.wd, w[i], g[i]) : g[i];
+      px_rule<FAM>(kind, h, gi, w[i], s0[i], s1[i], s2[FAM == 1 ? i : 0]);
+    }
     st_f32<VN>(a.master + e, w);
     if (a.slot0) st_f32<VN>(a.slot0 + e, s0);
     if (a.slot1) st_f32<VN>(a.slot1 + e, s1);
+    if (FAM == 1 && a.slot2) st_f32<VN>(a.slot2 + e, s2);
     if (a.ema) {
       float m[VN];
       ld_f32<VN>(a.ema + e, m);
@@ -181,6 +157,13 @@ px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr
   if (W > 1 && mode != 1) px_block_barrier(pads, epoch_ctr, a.ch_end, a.rank, W);
 }
 
+// device timestamp (ns) — a graph-capturable probe for "exposed communication" measurements
+__global__ void px_stamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+
 // scale = max_norm / max(sqrt(total), max_norm)  (tf.clip_by_global_norm);
 // also exports the norm and zeroes the accumulator for the next step.
 __global__ void px_clip_scale_kernel(const float* sumsq, float max_norm, float* scale_out,
@@ -196,42 +179,48 @@ __global__ void px_clip_scale_kernel(const float* sumsq, float max_norm, float* 
 // refreshed values are pulled back into the local parameter mirror.
 // Reference: sync=False ⇒ no accumulators, update ops race on the PS
 // variables (ps/between_graph_parallel.py:137-146).
-template <typename T, int W>
+template <typename T, int W, int FAM>
 __global__ void __launch_bounds__(512)
 px_dense_async_kernel(const T* __restrict__ my_grads, T* __restrict__ my_params,
-                      PeerPtrs master, PeerPtrs slot0, PeerPtrs slot1, const float* hp,
+                      PeerPtrs master, PeerPtrs slot0, PeerPtrs slot1, PeerPtrs slot2,
+                      const float* hp,
                       const float* clip, size_t n, int kind, int rank) {
   constexpr int VN = Vec16<T>::N;
   const size_t slice = n / W;
   const size_t nvec = n / VN;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const float lr = hp[HP_LR], ha = hp[HP_A], hb = hp[HP_B], eps = hp[HP_EPS], wd = hp[HP_WD],
-              nesterov = hp[HP_FLAGS];
+  const PxHP h = px_load_hp(hp);
   float gmul = hp[HP_GSCALE];
   if (clip != nullptr) gmul *= *clip;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
     const size_t e = v * VN;
     const int owner = (int)(e / slice);
     const size_t le = e - (size_t)owner * slice;
-    float *pm = nullptr, *p0 = nullptr, *p1 = nullptr;
+    float *pm = nullptr, *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
 #pragma unroll
     for (int p = 0; p < W; ++p)     // master/slots arrive in NATURAL rank order
       if (p == owner) {
         pm = reinterpret_cast<float*>(master.p[p]) + le;
         p0 = slot0.p[p] ? reinterpret_cast<float*>(slot0.p[p]) + le : nullptr;
         p1 = slot1.p[p] ? reinterpret_cast<float*>(slot1.p[p]) + le : nullptr;
+        p2 = (FAM == 1 && slot2.p[p]) ? reinterpret_cast<float*>(slot2.p[p]) + le : nullptr;
       }
-    float g[VN], w[VN], s0[VN], s1[VN];
+    float g[VN], w[VN], s0[VN], s1[VN], s2[FAM == 1 ? VN : 1];
     Vec16<T>::unpack(ld_v4(my_grads + e), g);
     ld_f32<VN>(pm, w);
     if (p0) ld_f32<VN>(p0, s0);
     if (p1) ld_f32<VN>(p1, s1);
+    if (FAM == 1 && p2) ld_f32<VN>(p2, s2);
 #pragma unroll
-    for (int i = 0; i < VN; ++i)
-      px_update(kind, lr, ha, hb, eps, wd, nesterov, g[i] * gmul, w[i], s0[i], s1[i]);
+    for (int i = 0; i < VN; ++i) {
+      float gi = g[i] * gmul;
+      if (h.wd != 0.f) gi = fmaf(h.wd, w[i], gi);
+      px_rule<FAM>(kind, h, gi, w[i], s0[i], s1[i], s2[FAM == 1 ? i : 0]);
+    }
     st_f32<VN>(pm, w);
     if (p0) st_f32<VN>(p0, s0);
     if (p1) st_f32<VN>(p1, s1);
+    if (FAM == 1 && p2) st_f32<VN>(p2, s2);
     st_v4(my_params + e, Vec16<T>::pack(w));
   }
 }
@@ -257,7 +246,7 @@ extern "C" {
 
 // dtype 0 fp32 / 1 bf16.  grads/params: `world` pointers in natural order.
 int px_dense_step(const void* const* grads, const void* const* params, float* master,
-                  float* slot0, float* slot1, float* ema, float* red, const float* hp,
+                  float* slot0, float* slot1, float* slot2, float* ema, float* red, const float* hp,
                   const float* clip, float* sumsq, size_t n, float avg, float ema_decay,
                   int kind, int mode, int dtype, void* pads_dev, void* epoch_ctr, int ch_start,
                   int ch_end, int rank, int world, int max_blocks, int use_mc,
@@ -275,7 +264,7 @@ int px_dense_step(const void* const* grads, const void* const* params, float* ma
   a.grads = px_rotate(grads, rank, world);
   a.params = px_rotate(params, rank, world);
   }
-  a.master = master; a.slot0 = slot0; a.slot1 = slot1; a.ema = ema; a.red = red;
+  a.master = master; a.slot0 = slot0; a.slot1 = slot1; a.slot2 = slot2; a.ema = ema; a.red = red;
   a.hp = hp; a.clip = clip; a.sumsq = sumsq; a.n = n; a.avg = avg; a.ema_decay = ema_decay;
   a.rank = rank; a.ch_start = ch_start; a.ch_end = ch_end; a.kind = kind; a.mode = mode;
   const int threads = 512;
@@ -284,12 +273,23 @@ int px_dense_step(const void* const* grads, const void* const* params, float* ma
     size_t b = (n / vn + threads - 1) / threads;
     blocks = (int)(b < 1 ? 1 : (b > 148 * 4 ? 148 * 4 : b));
   }
-#define LAUNCH(T, W)                                                                  \
-  px_dense_step_kernel<T, W><<<blocks, threads, 0, stream>>>(a, (uint32_t* const*)pads_dev, \
-                                                            (uint32_t*)epoch_ctr)
+#define LAUNCH(T, W)                                                                       \
+  do {                                                                                     \
+    if (PX_KIND_FAMILY(kind) == 0)                                                         \
+      px_dense_step_kernel<T, W, 0><<<blocks, threads, 0, stream>>>(                       \
+          a, (uint32_t* const*)pads_dev, (uint32_t*)epoch_ctr);                            \
+    else                                                                                   \
+      px_dense_step_kernel<T, W, 1><<<blocks, threads, 0, stream>>>(                       \
+          a, (uint32_t* const*)pads_dev, (uint32_t*)epoch_ctr);                            \
+  } while (0)
   if (dtype == 0) { PX_DISPATCH_WORLD(world, LAUNCH, float); }
   else { PX_DISPATCH_WORLD(world, LAUNCH, __nv_bfloat16); }
 #undef LAUNCH
+  return (int)cudaGetLastError();
+}
+
+int px_stamp(void* slot, cudaStream_t stream) {
+  px_stamp_kernel<<<1, 1, 0, stream>>>((unsigned long long*)slot);
   return (int)cudaGetLastError();
 }
 
@@ -300,22 +300,30 @@ int px_clip_scale(const float* sumsq, float max_norm, float* scale_out, float* n
 }
 
 int px_dense_async(const void* my_grads, void* my_params, const void* const* master,
-                   const void* const* slot0, const void* const* slot1, const float* hp,
+                   const void* const* slot0, const void* const* slot1,
+                   const void* const* slot2, const float* hp,
                    const float* clip, size_t n, int kind, int dtype, int rank, int world,
                    int max_blocks, cudaStream_t stream) {
   if (world < 1 || world > 8) return -3;
   const int vn = dtype == 0 ? 4 : 8;
   if (n % ((size_t)world * vn) != 0) return -1;
-  PeerPtrs M{}, S0{}, S1{};
+  PeerPtrs M{}, S0{}, S1{}, S2{};
   for (int i = 0; i < world; ++i) {
     M.p[i] = const_cast<void*>(master[i]);
     S0.p[i] = slot0 ? const_cast<void*>(slot0[i]) : nullptr;
     S1.p[i] = slot1 ? const_cast<void*>(slot1[i]) : nullptr;
+    S2.p[i] = slot2 ? const_cast<void*>(slot2[i]) : nullptr;
   }
   const int blocks = px_clamp_blocks(n / vn, 512, max_blocks);
 #define LAUNCH(T, W)                                                                   \
-  px_dense_async_kernel<T, W><<<blocks, 512, 0, stream>>>(                             \
-      (const T*)my_grads, (T*)my_params, M, S0, S1, hp, clip, n, kind, rank)
+  do {                                                                                 \
+    if (PX_KIND_FAMILY(kind) == 0)                                                     \
+      px_dense_async_kernel<T, W, 0><<<blocks, 512, 0, stream>>>(                      \
+          (const T*)my_grads, (T*)my_params, M, S0, S1, S2, hp, clip, n, kind, rank);  \
+    else                                                                               \
+      px_dense_async_kernel<T, W, 1><<<blocks, 512, 0, stream>>>(                      \
+          (const T*)my_grads, (T*)my_params, M, S0, S1, S2, hp, clip, n, kind, rank);  \
+  } while (0)
   if (dtype == 0) { PX_DISPATCH_WORLD(world, LAUNCH, float); }
   else { PX_DISPATCH_WORLD(world, LAUNCH, __nv_bfloat16); }
 #undef LAUNCH

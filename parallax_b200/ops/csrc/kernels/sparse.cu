@@ -1,49 +1,75 @@
-// Sparse path: remote-gather lookup, local aggregation (dedup), P2P push to
-// the owning rank, owner-side accumulate + sparse optimizer, async (Hogwild)
-// remote apply.
+// Sparse path, one *group* of co-indexed tables per launch:
+//   px_sparse_lookup_kernel  remote-gather lookup (NVLink peer loads), all member tables
+//   px_sparse_push_kernel    local aggregation (SMEM dedup) + P2P push + `pushed` flag:
+//                            ONE launch per group and step
+//   px_sparse_owner_kernel   owner side: cross-source merge + sparse optimizer + `applied`
+//                            flag: ONE (cooperative) launch per group and step
+// (async / Hogwild mode: the push kernel applies the optimizer remotely, no owner kernel.)
 //
-// What this replaces in the reference: worker GPU →
-// local-chief CPU SparseConditionalAccumulator → gRPC → PS CPU accumulator
-// (sorted two-pointer merge, whole value tensor re-allocated per apply,
-// tensorflow/core/kernels/sparse_conditional_accumulator.h:192-319) → chief
-// take_grad → serial CPU SparseApplyAdagrad row loop
-// (tensorflow/core/kernels/training_ops.cc:1338-1351) → token queues; and for
-// lookups dynamic_partition → per-shard PS CPU gather → gRPC → dynamic_stitch
-// (tensorflow/python/ops/embedding_ops.py:151-209,
-//  gather_functor_gpu.cu.h:32-70, dynamic_partition_op_gpu.cu.cc:60-110).
+// A group is a set of row-partitioned tables that share (V, P, strategy, owner map) and are
+// looked up with the SAME ids in one call (LM1B: softmax_w + softmax_b; any single table is a
+// group of one).  The ids are deduplicated once and every member table's rows travel together.
 //
-// Step protocol (sync mode), all flags are monotonically increasing step
-// numbers living in each rank's signal area:
-//   lookup(t)  waits  applied[o] >= t-1  for every owner o      (rows fresh)
-//   push(t)    writes rows+ids+count into owner's ring[src=me], then
-//              st.release.sys pushed[me] = t at the owner
-//   claim(t)   (owner) waits pushed[s] >= t for every source s, merges
-//              duplicate rows across sources
-//   apply(t)   (owner) optimizer on every touched row once, then publishes
-//              applied[me] = t to every rank and bumps the local step counter
+// What this replaces in the reference: worker GPU → local-chief CPU
+// SparseConditionalAccumulator → gRPC → PS CPU accumulator (sorted two-pointer merge, whole
+// value tensor re-allocated per apply, tensorflow/core/kernels/sparse_conditional_accumulator.h
+// :192-319) → chief take_grad → serial CPU SparseApplyAdagrad row loop (tensorflow/core/kernels/
+// training_ops.cc:1338-1351) → token queues; and for lookups dynamic_partition → per-shard PS CPU
+// gather → gRPC → dynamic_stitch (tensorflow/python/ops/embedding_ops.py:151-209,
+// gather_functor_gpu.cu.h:32-70, dynamic_partition_op_gpu.cu.cc:60-110).
+//
+// Step protocol (sync mode); flags are monotonically increasing step numbers in the group's
+// symmetric header, written with st.release.sys and polled with ld.acquire.sys:
+//   lookup(t)  waits applied[o] >= t-1 for every owner o   (rows fresh, receive rings drained)
+//   push(t)    writes rows + local row ids + counts into the owner's ring[src = me], then
+//              pushed[me] = t at the owner
+//   owner(t)   waits pushed[s] >= t for every source s, links the entries of every touched row
+//              into a list (one atomicExch per entry), grid barrier, then the list head sums the
+//              (bf16 or fp32) wire rows in fp32 and applies the optimizer once per row; publishes
+//              applied[me] = t to every rank.
+//
+// Wire format ("boundary between workers and servers", graph_transform_lib.py:1315-1370): rows
+// cross NVLink in the gradient's own dtype (bf16 gradients stay bf16; the widening cast runs on the
+// owner, after the wire) unless the boundary optimisation is switched off, in which case the
+// sender widens to fp32 first.
 #include "common.cuh"
 #include "launch.h"
+#include "optim_rules.cuh"
 
-struct TableGeom {
-  int V, P, W, rows_per_part, D4;   // D4 = padded row length in float4 units
-  int strategy;                     // 0 mod, 1 div
-  int replicated;                   // 1: every rank holds the full table (AR mode)
-  int extras, base;                 // div strategy
+#define PX_GRP_MAX 4            // member tables per group
+
+struct GroupGeom {
+  int V, P, W, rows_per_part;
+  int strategy;                 // 0 mod, 1 div
+  int replicated;               // 1: every rank holds the full table (AR mode)
+  int extras, base;             // div strategy
+  const int* part_owner;        // [P] owner rank of partition p (byte-greedy placement)
+  const int* part_slot;         // [P] index of partition p among its owner's partitions
 };
 
-// per-rank sparse control block (local memory, one per table)
+// per-rank control block of a group (local memory)
 struct SparseCtl {
-  uint32_t step;        // completed steps
-  uint32_t push_done;   // CTA ticket counter (push kernel)
-  uint32_t apply_done;  // CTA ticket counter (apply kernel)
-  int32_t n_uniq;
+  uint32_t step;                // completed steps
+  uint32_t push_done;           // CTA ticket counter (push kernel)
+  uint32_t apply_done;          // CTA ticket counter (owner kernel)
+  uint32_t bar;                 // grid barrier arrivals (owner kernel)
+  int32_t n_dup;                // staging rows handed out this step
+  int32_t overflow;             // #positions that fell back to un-deduplicated entries (stat)
   int32_t owner_cnt[PX_MAX_RANKS];
+  unsigned long long t_push[2]; // %globaltimer at push start / flag publication
+  unsigned long long t_own[3];  // owner kernel: start / all sources arrived / applied published
 };
 
-// flags inside the per-table symmetric header: [pushed[W] | applied[W] | cnt[W]]
-#define PX_TBL_HDR_WORDS (3 * PX_MAX_RANKS)
+// group header (symmetric): [pushed[R] | applied[R] | cnt[R]]
+#define PX_GRP_HDR_WORDS (3 * PX_MAX_RANKS)
 
-__device__ __forceinline__ void geom_map(const TableGeom& g, int id, int& owner, int& local) {
+__device__ __forceinline__ unsigned long long px_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ void geom_map(const GroupGeom& g, int id, int& owner, int& local) {
   if (g.replicated) { owner = 0; local = id; return; }
   int p, idx;
   if (g.strategy == 0) { p = id % g.P; idx = id / g.P; }
@@ -52,22 +78,39 @@ __device__ __forceinline__ void geom_map(const TableGeom& g, int id, int& owner,
     if (id < thr) { p = id / (g.base + 1); idx = id - p * (g.base + 1); }
     else { p = (id - g.extras) / max(g.base, 1); idx = id - (p * g.base + g.extras); }
   }
-  owner = p % g.W;
-  local = (p / g.W) * g.rows_per_part + idx;
+  owner = __ldg(g.part_owner + p);
+  local = __ldg(g.part_slot + p) * g.rows_per_part + idx;
 }
 
-__device__ __forceinline__ uint32_t hash_id(int id) {
+__device__ __forceinline__ uint32_t hash_cta(int id) {
   uint32_t x = (uint32_t)id * 2654435761u;
   return x ^ (x >> 15);
 }
+__device__ __forceinline__ uint32_t hash_slot(int id) {
+  uint32_t x = (uint32_t)id * 0x85EBCA6Bu;
+  x ^= x >> 13; x *= 0xC2B2AE35u;
+  return x ^ (x >> 16);
+}
 
 // ------------------------------------------------------------------ lookup
-// out[i,:] = table_owner(ids[i])[local(ids[i]), :]; LPR lanes cooperate on a row.
-template <typename IdT, typename OutT>
+struct LookupTable {
+  const void* const* srcs;      // device array[W]: fp32 tables or bf16 shadows of every rank
+  void* out;                    // [n, D4*4] rows
+  int D4;
+  int src_bf16;                 // 1: srcs are bf16 shadow copies (out is bf16 too)
+  int out_bf16;
+};
+struct LookupArgs {
+  LookupTable t[PX_GRP_MAX];
+  int nt;
+};
+
+// out_t[i,:] = table_t@owner(ids[i])[local(ids[i]), :] for every member table; LPR lanes per row.
+template <typename IdT>
 __global__ void __launch_bounds__(256)
-px_sparse_lookup_kernel(const IdT* __restrict__ ids, int n, float* const* __restrict__ tables,
-                        OutT* __restrict__ out, int32_t* __restrict__ pend_ids, TableGeom g,
-                        const uint32_t* applied, const SparseCtl* ctl, int lpr, int wait) {
+px_sparse_lookup_kernel(const IdT* __restrict__ ids, int n, LookupArgs a,
+                        int32_t* __restrict__ pend_ids, GroupGeom g, const uint32_t* applied,
+                        const SparseCtl* ctl, int lpr, int wait) {
   if (wait) {
     if (threadIdx.x < g.W) {
       const uint32_t need = ctl->step;
@@ -85,146 +128,37 @@ px_sparse_lookup_kernel(const IdT* __restrict__ ids, int n, float* const* __rest
     if (pend_ids != nullptr && sub == 0) pend_ids[i] = valid ? id : -1;
     int owner, local;
     geom_map(g, id, owner, local);
-    const float4* src = reinterpret_cast<const float4*>(tables[g.replicated ? 0 : owner]) +
-                        (size_t)local * g.D4;
-    OutT* dst = out + (size_t)i * g.D4 * 4;
-    for (int c = sub; c < g.D4; c += lpr) {
-      uint4 v = valid ? ld_v4(src + c) : make_uint4(0, 0, 0, 0);   // OOB -> zeros
-      if (sizeof(OutT) == 4) {
-        st_v4(reinterpret_cast<float4*>(dst) + c, v);
+#pragma unroll 1
+    for (int t = 0; t < a.nt; ++t) {
+      const LookupTable& T = a.t[t];
+      const char* src = reinterpret_cast<const char*>(T.srcs[owner]);
+      if (T.src_bf16) {
+        // bf16 shadow → bf16 rows: 8 elements per 16-byte load, half the NVLink/HBM bytes
+        const int nv = (T.D4 + 1) / 2;             // 16-byte vectors per row (row padded to 8)
+        const uint4* s = reinterpret_cast<const uint4*>(src) + (size_t)local * nv;
+        uint4* d = reinterpret_cast<uint4*>(T.out) + (size_t)i * nv;
+        for (int c = sub; c < nv; c += lpr)
+          st_v4(d + c, valid ? ld_v4(s + c) : make_uint4(0, 0, 0, 0));
       } else {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(__uint_as_float(v.x), __uint_as_float(v.y));
-        __nv_bfloat162 hi = __floats2bfloat162_rn(__uint_as_float(v.z), __uint_as_float(v.w));
-        uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-        *reinterpret_cast<uint2*>(reinterpret_cast<char*>(dst) + (size_t)c * 8) = o;
+        const float4* s = reinterpret_cast<const float4*>(src) + (size_t)local * T.D4;
+        for (int c = sub; c < T.D4; c += lpr) {
+          const uint4 v = valid ? ld_v4(s + c) : make_uint4(0, 0, 0, 0);   // OOB -> zeros
+          if (!T.out_bf16) {
+            st_v4(reinterpret_cast<float4*>(T.out) + (size_t)i * T.D4 + c, v);
+          } else {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(__uint_as_float(v.x), __uint_as_float(v.y));
+            __nv_bfloat162 hi = __floats2bfloat162_rn(__uint_as_float(v.z), __uint_as_float(v.w));
+            *reinterpret_cast<uint2*>(reinterpret_cast<char*>(T.out) +
+                                      ((size_t)i * T.D4 + c) * 8) =
+                make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+          }
+        }
       }
     }
-  }
-}
-
-// ------------------------------------------------------------------- dedup
-// Outputs (compact, per unique id u): uniq_id[u], uniq_k[u] (index inside its
-// owner bucket), uniq_cnt[u] (how many positions carry that id) and, per
-// position i, pos2u[i] (its unique slot, -1 for padding).  ctl->n_uniq,
-// ctl->owner_cnt[o].  (Arrays are named uniq_head/next at the ABI for
-// historical reasons: uniq_head == uniq_cnt, next == pos2u.)
-
-// Single-CTA variant: the hash table lives in shared memory ("local
-// aggregation dedups indices in SMEM before shipping").  n <= smem capacity.
-__global__ void __launch_bounds__(1024)
-px_sparse_dedup_smem_kernel(const int32_t* __restrict__ pend_ids, int n, int hbits,
-                            int32_t* __restrict__ uniq_id, int32_t* __restrict__ uniq_k,
-                            int32_t* __restrict__ uniq_head, int32_t* __restrict__ next,
-                            SparseCtl* ctl, TableGeom g, int dedup) {
-  extern __shared__ int32_t smem[];
-  const int H = 1 << hbits;
-  int32_t* keys = smem;          // [H]
-  int32_t* slot_u = smem + H;    // [H]
-  __shared__ int s_nuniq;
-  __shared__ int s_owner_cnt[PX_MAX_RANKS];
-  for (int h = threadIdx.x; h < H; h += blockDim.x) keys[h] = -1;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) uniq_head[i] = 0;
-  if (threadIdx.x < PX_MAX_RANKS) s_owner_cnt[threadIdx.x] = 0;
-  if (threadIdx.x == 0) s_nuniq = 0;
-  __syncthreads();
-  // pass 1: insert
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int id = pend_ids[i];
-    if (id < 0) continue;
-    if (!dedup) {
-      int owner, local; geom_map(g, id, owner, local);
-      const int u = atomicAdd(&s_nuniq, 1);
-      uniq_id[u] = id; uniq_k[u] = atomicAdd(&s_owner_cnt[owner], 1);
-      uniq_head[u] = 1; next[i] = u;
-      continue;
-    }
-    uint32_t h = hash_id(id) & (H - 1);
-    while (true) {
-      const int old = atomicCAS(&keys[h], -1, id);
-      if (old == -1) {
-        int owner, local; geom_map(g, id, owner, local);
-        const int u = atomicAdd(&s_nuniq, 1);
-        slot_u[h] = u; uniq_id[u] = id; uniq_k[u] = atomicAdd(&s_owner_cnt[owner], 1);
-        break;
-      }
-      if (old == id) break;
-      h = (h + 1) & (H - 1);
-    }
-  }
-  __syncthreads();
-  // pass 2: map positions to their unique entry and count them
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int id = pend_ids[i];
-    if (id < 0) { next[i] = -1; continue; }
-    if (!dedup) continue;
-    uint32_t h = hash_id(id) & (H - 1);
-    while (keys[h] != id) h = (h + 1) & (H - 1);
-    const int u = slot_u[h];
-    next[i] = u;
-    atomicAdd(&uniq_head[u], 1);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) ctl->n_uniq = s_nuniq;
-  if (threadIdx.x < PX_MAX_RANKS) ctl->owner_cnt[threadIdx.x] = s_owner_cnt[threadIdx.x];
-}
-
-// Multi-CTA variant, hash table in global memory (L2-resident): pass A inserts,
-// pass B links and clears the slots it visits.
-__global__ void __launch_bounds__(256)
-px_sparse_dedup_insert_kernel(const int32_t* __restrict__ pend_ids, int n, int hbits,
-                              int32_t* keys, int32_t* slot_u, int32_t* __restrict__ uniq_id,
-                              int32_t* __restrict__ uniq_k, int32_t* __restrict__ uniq_head,
-                              int32_t* __restrict__ next, SparseCtl* ctl, TableGeom g, int dedup) {
-  const int H = 1 << hbits;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int id = pend_ids[i];
-    if (id < 0) { next[i] = -1; continue; }
-    if (!dedup) {
-      int owner, local; geom_map(g, id, owner, local);
-      const int u = atomicAdd(&ctl->n_uniq, 1);
-      uniq_id[u] = id; uniq_k[u] = atomicAdd(&ctl->owner_cnt[owner], 1);
-      uniq_head[u] = 1; next[i] = u;
-      continue;
-    }
-    uint32_t h = hash_id(id) & (H - 1);
-    while (true) {
-      const int old = atomicCAS(&keys[h], -1, id);
-      if (old == -1) {
-        int owner, local; geom_map(g, id, owner, local);
-        const int u = atomicAdd(&ctl->n_uniq, 1);
-        slot_u[h] = u; uniq_id[u] = id; uniq_k[u] = atomicAdd(&ctl->owner_cnt[owner], 1);
-        uniq_head[u] = 0;
-        break;
-      }
-      if (old == id) break;
-      h = (h + 1) & (H - 1);
-    }
-  }
-}
-__global__ void __launch_bounds__(256)
-px_sparse_dedup_link_kernel(const int32_t* __restrict__ pend_ids, int n, int hbits,
-                            const int32_t* keys, const int32_t* slot_u, int32_t* uniq_head,
-                            int32_t* __restrict__ next) {
-  const int H = 1 << hbits;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int id = pend_ids[i];
-    if (id < 0) continue;
-    uint32_t h = hash_id(id) & (H - 1);
-    while (ld_volatile_u32(reinterpret_cast<const uint32_t*>(keys) + h) != (uint32_t)id)
-      h = (h + 1) & (H - 1);
-    const int u = slot_u[h];
-    next[i] = u;
-    atomicAdd(&uniq_head[u], 1);
   }
 }
 
 // -------------------------------------------------------------------- push
-// One warp per unique id: sum the rows of all positions carrying it (fp32),
-// scale, and store the row + its local index into the owner's receive ring
-// (or every rank's ring in replicated/AR mode) over NVLink.  The last CTA
-// publishes counts and the `pushed` flag.  CH = row chunks of 32 float4 held
-// in registers so the duplicate list is walked once (rows up to 512 floats);
-// longer rows re-walk per group of CH chunks.
 template <typename GradT>
 __device__ __forceinline__ float4 ld_grad4(const GradT* base, size_t f4_index) {
   if (sizeof(GradT) == 4) {
@@ -239,163 +173,303 @@ __device__ __forceinline__ float4 ld_grad4(const GradT* base, size_t f4_index) {
   }
 }
 
-__device__ __forceinline__ void sparse_update4(int kind, float lr, float a, float b, float eps,
-                                               float nesterov, const float4& g, float4& w,
-                                               float4& s0, float4& s1) {
-  float gg[4] = {g.x, g.y, g.z, g.w};
-  float ww[4] = {w.x, w.y, w.z, w.w};
-  float a0[4] = {s0.x, s0.y, s0.z, s0.w};
-  float a1[4] = {s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float gi = gg[i];
-    switch (kind) {
-      case 0: ww[i] = fmaf(-lr, gi, ww[i]); break;
-      case 1:
-        a0[i] = fmaf(a, a0[i], gi);
-        ww[i] = nesterov != 0.f ? fmaf(-lr, fmaf(a, a0[i], gi), ww[i]) : fmaf(-lr, a0[i], ww[i]);
-        break;
-      case 2:
-        a0[i] = fmaf(gi, gi, a0[i]);
-        ww[i] = fmaf(-lr * gi, rsqrtf(a0[i]), ww[i]);
-        break;
-      case 3:
-        a0[i] = fmaf(a, a0[i], (1.f - a) * gi);
-        a1[i] = fmaf(b, a1[i], (1.f - b) * gi * gi);
-        ww[i] -= lr * a0[i] / (sqrtf(a1[i]) + eps);
-        break;
-      case 4:
-        a0[i] = fmaf(a, a0[i], (1.f - a) * gi * gi);
-        a1[i] = fmaf(b, a1[i], lr * gi * rsqrtf(a0[i] + eps));
-        ww[i] -= a1[i];
-        break;
-    }
+template <typename WireT>
+__device__ __forceinline__ void st_wire4(char* row_base, int c, const float4& v) {
+  if (sizeof(WireT) == 4) {
+    st_v4_stream(reinterpret_cast<float4*>(row_base) + c,
+                 make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z),
+                            __float_as_uint(v.w)));
+  } else {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    const uint2 o = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};"
+                 ::"l"(row_base + (size_t)c * 8), "r"(o.x), "r"(o.y) : "memory");
   }
-  w = make_float4(ww[0], ww[1], ww[2], ww[3]);
-  s0 = make_float4(a0[0], a0[1], a0[2], a0[3]);
-  s1 = make_float4(a1[0], a1[1], a1[2], a1[3]);
+}
+template <typename WireT>
+__device__ __forceinline__ float4 ld_wire4(const char* row_base, int c) {
+  if (sizeof(WireT) == 4) {
+    const uint4 v = ld_v4_stream(reinterpret_cast<const float4*>(row_base) + c);
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z),
+                       __uint_as_float(v.w));
+  } else {
+    uint2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+                 : "=r"(v.x), "=r"(v.y) : "l"(row_base + (size_t)c * 8) : "memory");
+    return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u),
+                       __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+  }
 }
 
-// Kernel A — position-parallel (LPR lanes per position): a position whose id
-// is unique in this batch goes straight to its destination (owner's ring, or a
-// remote optimizer application in async mode); positions sharing an id are
-// summed with vector atomics into a local fp32 staging row.  Duplicate-heavy
-// (Zipfian) batches therefore cost O(1) depth instead of a serial list walk.
-struct PushDst {
-  char* const* rings; size_t ring_ids_off; int cap; int rank;           // sync: rings
-  float* const* tables; float* const* slot0s; float* const* slot1s;      // async: remote apply
-  const float* hp; int kind;
+
+// optimizer on 4 elements of one table row (+ bf16 shadow refresh); used by the owner kernel on
+// local rows and by the async push on remote rows
+template <int FAM>
+__device__ __forceinline__ void px_row_apply4(int kind, const PxHP& h, const float4& g,
+                                              float* table, float* slot0, float* slot1,
+                                              float* slot2, __nv_bfloat16* shadow, size_t row,
+                                              int D4, int c) {
+  const size_t off = row * D4 + c;
+  float4* pw = reinterpret_cast<float4*>(table) + off;
+  float4* p0 = slot0 ? reinterpret_cast<float4*>(slot0) + off : nullptr;
+  float4* p1 = slot1 ? reinterpret_cast<float4*>(slot1) + off : nullptr;
+  float4* p2 = (FAM == 1 && slot2) ? reinterpret_cast<float4*>(slot2) + off : nullptr;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 w = *pw, s0 = z, s1 = z, s2 = z;
+  if (p0) s0 = *p0;
+  if (p1) s1 = *p1;
+  if (p2) s2 = *p2;
+  px_rule4<FAM>(kind, h, g, w, s0, s1, s2);
+  *pw = w;
+  if (p0) *p0 = s0;
+  if (p1) *p1 = s1;
+  if (p2) *p2 = s2;
+  if (shadow) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<char*>(shadow) +
+                              (row * ((D4 + 1) / 2 * 2) + c) * 8) =
+        make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+}
+
+struct PushTable {
+  const void* grads;            // [n, D4*4] gradient rows (GradT)
+  float* staging;               // [n/2+1, D4*4] fp32 rows for ids carried by several positions
+  char* const* rings;           // sync: device array[W] of receive-ring bases
+  float* const* tables;         // async: device arrays[W] for the remote optimizer application
+  float* const* slot0s;
+  float* const* slot1s;
+  float* const* slot2s;
+  __nv_bfloat16* const* shadows;
+  const float* hp;
+  int D4, kind;
+  float scale;                  // ScaleGradients factor when it runs on the sender
+};
+struct PushArgs {
+  PushTable t[PX_GRP_MAX];
+  int nt;
+  int32_t* const* ring_ids;     // device array[W]: id rings ([W_src][cap] local rows)
+  uint32_t* const* hdrs;        // device array[W]: group headers
+  int cap, rank;
 };
 
-__device__ __forceinline__ void emit_row4(const PushDst& d, const TableGeom& g, int owner,
-                                          int local, int k, int c, float4 v, bool async) {
-  if (!async) {
-    const uint4 o = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z),
-                               __float_as_uint(v.w));
+// destination of one row (all member tables): the owner's ring slot (sync) or the owner's
+// table row itself (async)
+template <typename WireT, bool ASYNC, int FAM>
+__device__ __forceinline__ void emit_row(const PushArgs& a, const GroupGeom& g, int t, int owner,
+                                         int local, int k, int c, float4 v) {
+  const PushTable& T = a.t[t];
+  if (!ASYNC) {
+    const size_t row_bytes = (size_t)T.D4 * 4 * sizeof(WireT);
     if (g.replicated) {
       for (int p = 0; p < g.W; ++p) {
-        const int q = (d.rank + p) % g.W;
-        st_v4_stream(reinterpret_cast<float4*>(d.rings[q]) + ((size_t)d.rank * d.cap + k) * g.D4 + c, o);
+        const int q = (a.rank + p) % g.W;
+        st_wire4<WireT>(T.rings[q] + ((size_t)a.rank * a.cap + k) * row_bytes, c, v);
       }
     } else {
-      st_v4_stream(reinterpret_cast<float4*>(d.rings[owner]) + ((size_t)d.rank * d.cap + k) * g.D4 + c, o);
+      st_wire4<WireT>(T.rings[owner] + ((size_t)a.rank * a.cap + k) * row_bytes, c, v);
     }
   } else {
-    float4* pw = reinterpret_cast<float4*>(d.tables[owner]) + (size_t)local * g.D4 + c;
-    float4* p0 = d.slot0s ? reinterpret_cast<float4*>(d.slot0s[owner]) + (size_t)local * g.D4 + c : nullptr;
-    float4* p1 = d.slot1s ? reinterpret_cast<float4*>(d.slot1s[owner]) + (size_t)local * g.D4 + c : nullptr;
-    float4 w = *pw, s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);
-    if (p0) s0 = *p0;
-    if (p1) s1 = *p1;
-    sparse_update4(d.kind, d.hp[0], d.hp[1], d.hp[2], d.hp[3], d.hp[7], v, w, s0, s1);
-    *pw = w;
-    if (p0) *p0 = s0;
-    if (p1) *p1 = s1;
+    px_row_apply4<FAM>(T.kind, px_load_hp(T.hp), v, T.tables[owner],
+                       T.slot0s ? T.slot0s[owner] : nullptr, T.slot1s ? T.slot1s[owner] : nullptr,
+                       T.slot2s ? T.slot2s[owner] : nullptr,
+                       T.shadows ? T.shadows[owner] : nullptr, (size_t)local, T.D4, c);
   }
 }
 
-__device__ __forceinline__ void emit_id(const PushDst& d, const TableGeom& g, int owner, int local,
-                                        int k) {
+__device__ __forceinline__ void emit_id(const PushArgs& a, const GroupGeom& g, int owner,
+                                        int local, int k) {
   if (g.replicated) {
-    for (int p = 0; p < g.W; ++p)
-      reinterpret_cast<int32_t*>(d.rings[p] + d.ring_ids_off)[(size_t)d.rank * d.cap + k] = local;
+    for (int p = 0; p < g.W; ++p) a.ring_ids[p][(size_t)a.rank * a.cap + k] = local;
   } else {
-    reinterpret_cast<int32_t*>(d.rings[owner] + d.ring_ids_off)[(size_t)d.rank * d.cap + k] = local;
+    a.ring_ids[owner][(size_t)a.rank * a.cap + k] = local;
   }
 }
 
-template <typename GradT, bool ASYNC>
+// ONE launch: local aggregation + push + flag.
+// The id space is partitioned over the CTAs by a hash, so every CTA owns all positions of "its"
+// ids: it deduplicates them in a shared-memory hash table ("local aggregation dedups indices in
+// SMEM before shipping"), reserves ring slots with one global atomic per (CTA, owner), ships rows
+// whose id is unique in the batch straight from the gradient buffer, sums rows sharing an id with
+// vector atomics into a local fp32 staging row (O(1) depth for Zipfian batches) and flushes those
+// once.  No grid-wide phase is needed; the last CTA publishes the counts and the `pushed` flag.
+// SMEM layout: keys[H] | cnt[H] | kk[H] (k inside the owner bucket; bit 31 clear) | dup[H]
+template <typename GradT, typename WireT, bool ASYNC, int FAM>
 __global__ void __launch_bounds__(256)
-px_sparse_scatter_kernel(const GradT* __restrict__ pend_grads, int n,
-                         const int32_t* __restrict__ pos2u, const int32_t* __restrict__ uniq_id,
-                         const int32_t* __restrict__ uniq_k, const int32_t* __restrict__ uniq_cnt,
-                         float* __restrict__ staging, const SparseCtl* ctl, PushDst d,
-                         uint32_t* const* __restrict__ hdrs, TableGeom g, float scale, int lpr) {
-  if (!ASYNC) {   // do not overwrite a ring the owner may still be draining
-    if (threadIdx.x < g.W) {
-      const uint32_t need = ctl->step;
-      const uint32_t* applied = hdrs[d.rank] + PX_MAX_RANKS;
-      while ((int32_t)(ld_acquire_sys(applied + threadIdx.x) - need) < 0) { }
+px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, GroupGeom g,
+                      SparseCtl* ctl, int hbits, int dedup) {
+  extern __shared__ int32_t smem[];
+  const int H = 1 << hbits;
+  int32_t* keys = smem;
+  int32_t* cnt = smem + H;
+  int32_t* kk = smem + 2 * H;
+  int32_t* dup = smem + 3 * H;
+  __shared__ int s_owner_cnt[PX_MAX_RANKS], s_base_k[PX_MAX_RANKS];
+  __shared__ int s_ndup, s_base_dup, s_overflow;
+  __shared__ bool s_last;
+  const int G = gridDim.x, c_me = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (c_me == 0 && threadIdx.x == 0) ctl->t_push[0] = px_globaltimer();
+  for (int h = threadIdx.x; h < H; h += blockDim.x) { keys[h] = -1; cnt[h] = 0; }
+  if (threadIdx.x < PX_MAX_RANKS) s_owner_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_ndup = 0; s_overflow = 0; }
+  __syncthreads();
+  // ---- pass 1: insert my ids, count positions per id
+  if (dedup) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int id = pend_ids[i];
+      if (id < 0) continue;
+      if ((int)(((unsigned long long)hash_cta(id) * (unsigned)G) >> 32) != c_me) continue;
+      uint32_t h = hash_slot(id) & (H - 1);
+      int probes = 0;
+      while (true) {
+        const int old = atomicCAS(&keys[h], -1, id);
+        if (old == -1 || old == id) { atomicAdd(&cnt[h], 1); break; }
+        h = (h + 1) & (H - 1);
+        if (++probes >= H) { atomicAdd(&s_overflow, 1); break; }   // table full: raw entry later
+      }
+    }
+    __syncthreads();
+    // ---- pass 2: one ring slot per unique id, one staging row per duplicated id
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+      const int id = keys[h];
+      if (id < 0) continue;
+      int owner, local;
+      geom_map(g, id, owner, local);
+      kk[h] = atomicAdd(&s_owner_cnt[owner], 1);
+      dup[h] = cnt[h] > 1 ? atomicAdd(&s_ndup, 1) : -1;
     }
     __syncthreads();
   }
-  const int rows_per_block = blockDim.x / lpr;
-  const int sub = threadIdx.x % lpr;
-  const float mul = ASYNC ? scale * d.hp[6] : scale;
-  for (int i = blockIdx.x * rows_per_block + threadIdx.x / lpr; i < n;
-       i += gridDim.x * rows_per_block) {
-    const int u = pos2u[i];
-    if (u < 0) continue;
-    const int cnt = uniq_cnt[u];
-    if (cnt == 1) {
-      const int id = uniq_id[u], k = uniq_k[u];
-      int owner, local;
-      geom_map(g, id, owner, local);
-      for (int c = sub; c < g.D4; c += lpr) {
-        float4 v = ld_grad4<GradT>(pend_grads, (size_t)i * g.D4 + c);
-        v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
-        emit_row4(d, g, owner, local, k, c, v, ASYNC);
+  // raw (un-deduplicated) entries: local_aggregation off → every position i % G == c_me;
+  // or the (statistically never hit) SMEM overflow
+  const bool raw_all = !dedup;
+  if (raw_all || s_overflow > 0) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int id = pend_ids[i];
+      if (id < 0) continue;
+      bool raw = false;
+      if (raw_all) raw = (i % G) == c_me;
+      else if ((int)(((unsigned long long)hash_cta(id) * (unsigned)G) >> 32) == c_me) {
+        uint32_t h = hash_slot(id) & (H - 1);
+        int probes = 0;
+        while (keys[h] != id && keys[h] != -1 && ++probes <= H) h = (h + 1) & (H - 1);
+        raw = keys[h] != id;
       }
-      if (!ASYNC && sub == 0) emit_id(d, g, owner, local, k);
-    } else {
-      float4* dst = reinterpret_cast<float4*>(staging) + (size_t)u * g.D4;
-      for (int c = sub; c < g.D4; c += lpr)
-        atomicAdd(dst + c, ld_grad4<GradT>(pend_grads, (size_t)i * g.D4 + c));
+      if (raw) {
+        int owner, local;
+        geom_map(g, id, owner, local);
+        atomicAdd(&s_owner_cnt[owner], 1);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < PX_MAX_RANKS) {
+    const int m = s_owner_cnt[threadIdx.x];
+    s_base_k[threadIdx.x] = m > 0 ? atomicAdd(&ctl->owner_cnt[threadIdx.x], m) : 0;
+    s_owner_cnt[threadIdx.x] = 0;              // re-used as the raw-entry cursor below
+  }
+  if (threadIdx.x == 0) {
+    s_base_dup = s_ndup > 0 ? atomicAdd(&ctl->n_dup, s_ndup) : 0;
+    if (s_overflow > 0) atomicAdd(&ctl->overflow, s_overflow);
+  }
+  __syncthreads();
+  // raw entries take the slots after the deduplicated ones of this CTA
+  if (dedup && s_overflow > 0) {
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+      if (keys[h] < 0) continue;
+      int owner, local;
+      geom_map(g, keys[h], owner, local);
+      atomicMax(&s_owner_cnt[owner], kk[h] + 1);
+    }
+    __syncthreads();
+  }
+  // ---- pass 3: ship unique rows, stage duplicated ones (warp per position)
+  for (int i0 = wid * 32; i0 < n; i0 += nwarps * 32) {
+    const int i = i0 + lane;
+    int id = -1, h_found = -1;
+    bool mine = false, raw = false;
+    if (i < n) {
+      id = pend_ids[i];
+      if (id >= 0) {
+        if (raw_all) { mine = (i % G) == c_me; raw = mine; }
+        else if ((int)(((unsigned long long)hash_cta(id) * (unsigned)G) >> 32) == c_me) {
+          mine = true;
+          uint32_t h = hash_slot(id) & (H - 1);
+          int probes = 0;
+          while (keys[h] != id && keys[h] != -1 && ++probes <= H) h = (h + 1) & (H - 1);
+          if (keys[h] == id) h_found = (int)h; else raw = true;
+        }
+      }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, mine);
+    while (m) {
+      const int src_lane = __ffs(m) - 1;
+      m &= m - 1;
+      const int pi = i0 + src_lane;
+      const int pid = __shfl_sync(0xffffffffu, id, src_lane);
+      const int ph = __shfl_sync(0xffffffffu, h_found, src_lane);
+      const bool praw = __shfl_sync(0xffffffffu, (int)raw, src_lane) != 0;
+      int owner, local;
+      geom_map(g, pid, owner, local);
+      int k = 0, pcnt = 1;
+      if (praw) {
+        if (lane == 0) k = s_base_k[owner] + atomicAdd(&s_owner_cnt[owner], 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+      } else {
+        k = s_base_k[owner] + kk[ph];
+        pcnt = cnt[ph];
+      }
+      if (pcnt == 1) {
+        for (int t = 0; t < a.nt; ++t) {
+          const PushTable& T = a.t[t];
+          const float mul = ASYNC ? T.scale * T.hp[HP_GSCALE] : T.scale;
+          for (int c = lane; c < T.D4; c += 32) {
+            float4 v = ld_grad4<GradT>(reinterpret_cast<const GradT*>(T.grads),
+                                       (size_t)pi * T.D4 + c);
+            v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
+            emit_row<WireT, ASYNC, FAM>(a, g, t, owner, local, k, c, v);
+          }
+        }
+        if (!ASYNC && lane == 0) emit_id(a, g, owner, local, k);
+      } else {
+        const int d = s_base_dup + dup[ph];
+        for (int t = 0; t < a.nt; ++t) {
+          const PushTable& T = a.t[t];
+          float4* dst = reinterpret_cast<float4*>(T.staging) + (size_t)d * T.D4;
+          for (int c = lane; c < T.D4; c += 32)
+            atomicAdd(dst + c, ld_grad4<GradT>(reinterpret_cast<const GradT*>(T.grads),
+                                               (size_t)pi * T.D4 + c));
+        }
+      }
     }
   }
-}
-
-// Kernel B — unique-parallel: flush the staged (duplicate) rows, re-zero the
-// staging rows, then the last CTA publishes counts + `pushed` flag (sync) or
-// bumps the step (async) and re-arms the local counters.
-template <bool ASYNC>
-__global__ void __launch_bounds__(256)
-px_sparse_flush_kernel(const int32_t* __restrict__ uniq_id, const int32_t* __restrict__ uniq_k,
-                       const int32_t* __restrict__ uniq_cnt, float* __restrict__ staging,
-                       SparseCtl* ctl, PushDst d, uint32_t* const* __restrict__ hdrs, TableGeom g,
-                       float scale, int lpr) {
-  const int rows_per_block = blockDim.x / lpr;
-  const int sub = threadIdx.x % lpr;
-  const int n_uniq = ctl->n_uniq;
-  const float mul = ASYNC ? scale * d.hp[6] : scale;
-  for (int u = blockIdx.x * rows_per_block + threadIdx.x / lpr; u < n_uniq;
-       u += gridDim.x * rows_per_block) {
-    if (uniq_cnt[u] <= 1) continue;
-    const int id = uniq_id[u], k = uniq_k[u];
-    int owner, local;
-    geom_map(g, id, owner, local);
-    float4* src = reinterpret_cast<float4*>(staging) + (size_t)u * g.D4;
-    for (int c = sub; c < g.D4; c += lpr) {
-      float4 v = src[c];
-      src[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
-      emit_row4(d, g, owner, local, k, c, v, ASYNC);
+  __syncthreads();        // every position of my duplicated ids is staged (they are all mine)
+  // ---- pass 4: flush duplicated ids (warp per id), re-zero the staging rows
+  if (dedup && s_ndup > 0) {
+    for (int h = wid; h < H; h += nwarps) {
+      if (keys[h] < 0 || cnt[h] <= 1) continue;
+      int owner, local;
+      geom_map(g, keys[h], owner, local);
+      const int k = s_base_k[owner] + kk[h];
+      const int d = s_base_dup + dup[h];
+      for (int t = 0; t < a.nt; ++t) {
+        const PushTable& T = a.t[t];
+        const float mul = ASYNC ? T.scale * T.hp[HP_GSCALE] : T.scale;
+        float4* src = reinterpret_cast<float4*>(T.staging) + (size_t)d * T.D4;
+        for (int c = lane; c < T.D4; c += 32) {
+          float4 v = __ldcg(src + c);
+          __stcg(src + c, make_float4(0.f, 0.f, 0.f, 0.f));
+          v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
+          emit_row<WireT, ASYNC, FAM>(a, g, t, owner, local, k, c, v);
+        }
+      }
+      if (!ASYNC && lane == 0) emit_id(a, g, owner, local, k);
     }
-    if (!ASYNC && sub == 0) emit_id(d, g, owner, local, k);
   }
+  // ---- completion: last CTA publishes counts + `pushed` (sync) / bumps the step (async)
   __threadfence_system();
   __syncthreads();
-  __shared__ bool s_last;
   if (threadIdx.x == 0) s_last = (atomicAdd(&ctl->push_done, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!s_last) return;
@@ -404,262 +478,300 @@ px_sparse_flush_kernel(const int32_t* __restrict__ uniq_id, const int32_t* __res
   if (!ASYNC) {
     if (threadIdx.x < g.W) {
       const int o = threadIdx.x;
-      const int cnt = g.replicated ? ctl->owner_cnt[0] : ctl->owner_cnt[o];
-      uint32_t* hdr = hdrs[o];
-      reinterpret_cast<volatile int32_t*>(hdr + 2 * PX_MAX_RANKS)[d.rank] = cnt;   // cnt[src]
+      const int cn = g.replicated ? ctl->owner_cnt[0] : ctl->owner_cnt[o];
+      uint32_t* hdr = a.hdrs[o];
+      reinterpret_cast<volatile int32_t*>(hdr + 2 * PX_MAX_RANKS)[a.rank] = cn;   // cnt[src]
       __threadfence_system();
-      st_release_sys(hdr + d.rank, step);                                          // pushed[src]
+      st_release_sys(hdr + a.rank, step);                                         // pushed[src]
     }
     __syncthreads();
   }
   if (threadIdx.x < PX_MAX_RANKS) ctl->owner_cnt[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
-    ctl->n_uniq = 0; ctl->push_done = 0;
+    ctl->n_dup = 0; ctl->push_done = 0;
+    ctl->t_push[1] = px_globaltimer();
     if (ASYNC) ctl->step = step;
   }
 }
 
 // ------------------------------------------------------------------ owner
-__device__ __forceinline__ void wait_pushed(const uint32_t* hdr, const SparseCtl* ctl, int W) {
-  if (threadIdx.x < W) {
+struct OwnerTable {
+  char* ring;                   // my receive ring: [W_src][cap][D4*4] WireT
+  float* table; float* slot0; float* slot1; float* slot2;
+  __nv_bfloat16* shadow;        // bf16 copy read by lookups (or null)
+  const float* hp;
+  int D4, kind;
+  float avg;                    // 1/num_workers (average_sparse) × owner-side gradient scale
+};
+struct OwnerArgs {
+  OwnerTable t[PX_GRP_MAX];
+  int nt;
+  const int32_t* ring_ids;      // [W_src][cap]
+  uint32_t* hdr;                // my group header
+  uint32_t* const* hdrs;        // every rank's header (to publish `applied`)
+  int32_t* slotmap;             // [rows_local], -1 when idle
+  int32_t* next;                // [W_src * cap]
+  int cap, rank, use_merge;
+};
+
+// ONE launch: wait for every source, merge rows that several sources touched, apply the sparse
+// optimizer once per touched row, publish `applied`.  Launched cooperatively when use_merge (one
+// grid barrier between linking and applying).
+template <typename WireT, int FAM>
+__global__ void __launch_bounds__(256)
+px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
+  __shared__ bool s_last;
+  const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamp) ctl->t_own[0] = px_globaltimer();
+  if (threadIdx.x < g.W) {
     const uint32_t need = ctl->step + 1;
-    while ((int32_t)(ld_acquire_sys(hdr + threadIdx.x) - need) < 0) { }
+    while ((int32_t)(ld_acquire_sys(a.hdr + threadIdx.x) - need) < 0) { }
   }
   __syncthreads();
-}
-
-// claim: merge duplicate rows arriving from different sources.  The first
-// entry to claim a row becomes its accumulator; later ones add into it.
-__global__ void __launch_bounds__(256)
-px_sparse_claim_kernel(char* ring, uint32_t* hdr, size_t ring_ids_off, int cap, int32_t* slotmap,
-                       const SparseCtl* ctl, TableGeom g) {
-  wait_pushed(hdr, ctl, g.W);
+  if (stamp) ctl->t_own[1] = px_globaltimer();
   const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
-  const int32_t* cnt = reinterpret_cast<const int32_t*>(hdr + 2 * PX_MAX_RANKS);
-  const int32_t* ids = reinterpret_cast<const int32_t*>(ring + ring_ids_off);
-  float4* rows = reinterpret_cast<float4*>(ring);
-  for (int s = 0; s < g.W; ++s) {
-    const int c = ld_volatile_u32(reinterpret_cast<const uint32_t*>(cnt) + s);
-    for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < c; j += gridDim.x * warps) {
-      const int e = s * cap + j;
-      const int r = ids[e];
-      int old = 0;
-      if (lane == 0) old = atomicCAS(&slotmap[r], -1, e);
-      old = __shfl_sync(0xffffffffu, old, 0);
-      if (old != -1) {
-        for (int cidx = lane; cidx < g.D4; cidx += 32) {
-          const float4 v = rows[(size_t)e * g.D4 + cidx];
-          atomicAdd(&rows[(size_t)old * g.D4 + cidx], v);
-        }
+  const uint32_t* cnt = a.hdr + 2 * PX_MAX_RANKS;
+  if (a.use_merge) {
+    // link: every entry pushes itself on the list of its row (at most one entry per source when
+    // the senders aggregate locally, so lists are <= W long)
+    for (int s = 0; s < g.W; ++s) {
+      const int c = (int)ld_volatile_u32(cnt + s);
+      for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < c; j += gridDim.x * blockDim.x) {
+        const int e = s * a.cap + j;
+        a.next[e] = atomicExch(&a.slotmap[a.ring_ids[e]], e);
       }
     }
+    // grid barrier (all CTAs are co-resident: cooperative launch)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atomicAdd(&ctl->bar, 1u);
+      while (ld_volatile_u32(&ctl->bar) < gridDim.x) { }
+      __threadfence();
+    }
+    __syncthreads();
   }
-}
-
-// apply: every claimed row gets exactly one optimizer application with the
-// summed gradient (× avg).  `use_slotmap`=0 when entries are known unique
-// (world 1 with local aggregation): claim is skipped entirely.
-__global__ void __launch_bounds__(256)
-px_sparse_apply_kernel(char* ring, uint32_t* hdr, size_t ring_ids_off, int cap, int32_t* slotmap,
-                       float* table, float* slot0, float* slot1, const float* hp, float avg,
-                       int kind, SparseCtl* ctl, uint32_t* const* __restrict__ hdrs, TableGeom g,
-                       int rank, int use_slotmap) {
-  wait_pushed(hdr, ctl, g.W);
-  const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
-  const int32_t* cnt = reinterpret_cast<const int32_t*>(hdr + 2 * PX_MAX_RANKS);
-  const int32_t* ids = reinterpret_cast<const int32_t*>(ring + ring_ids_off);
-  const float4* rows = reinterpret_cast<const float4*>(ring);
-  const float lr = hp[0], ha = hp[1], hb = hp[2], eps = hp[3], nesterov = hp[7];
-  const float gmul = avg * hp[6];
   for (int s = 0; s < g.W; ++s) {
-    const int c = ld_volatile_u32(reinterpret_cast<const uint32_t*>(cnt) + s);
+    const int c = (int)ld_volatile_u32(cnt + s);
     for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < c; j += gridDim.x * warps) {
-      const int e = s * cap + j;
-      const int r = ids[e];
-      if (use_slotmap) {
-        int owner_e = 0;
-        if (lane == 0) owner_e = slotmap[r];
-        owner_e = __shfl_sync(0xffffffffu, owner_e, 0);
-        if (owner_e != e) continue;
+      const int e = s * a.cap + j;
+      const int r = a.ring_ids[e];
+      if (a.use_merge) {
+        if (__ldcg(a.slotmap + r) != e) continue;          // not the list head
       }
-      for (int cidx = lane; cidx < g.D4; cidx += 32) {
-        float4 gv = rows[(size_t)e * g.D4 + cidx];
-        gv.x *= gmul; gv.y *= gmul; gv.z *= gmul; gv.w *= gmul;
-        float4* pw = reinterpret_cast<float4*>(table) + (size_t)r * g.D4 + cidx;
-        float4 w = *pw, s0 = make_float4(0, 0, 0, 0), s1 = make_float4(0, 0, 0, 0);
-        float4* p0 = slot0 ? reinterpret_cast<float4*>(slot0) + (size_t)r * g.D4 + cidx : nullptr;
-        float4* p1 = slot1 ? reinterpret_cast<float4*>(slot1) + (size_t)r * g.D4 + cidx : nullptr;
-        if (p0) s0 = *p0;
-        if (p1) s1 = *p1;
-        sparse_update4(kind, lr, ha, hb, eps, nesterov, gv, w, s0, s1);
-        *pw = w;
-        if (p0) *p0 = s0;
-        if (p1) *p1 = s1;
+#pragma unroll 1
+      for (int t = 0; t < a.nt; ++t) {
+        const OwnerTable& T = a.t[t];
+        const size_t row_bytes = (size_t)T.D4 * 4 * sizeof(WireT);
+        const float gmul = T.avg * T.hp[HP_GSCALE];
+        const PxHP hp = px_load_hp(T.hp);
+        for (int cidx = lane; cidx < T.D4; cidx += 32) {
+          float4 gv = ld_wire4<WireT>(T.ring + (size_t)e * row_bytes, cidx);
+          if (a.use_merge) {
+            for (int x = __ldcg(a.next + e); x != -1; x = __ldcg(a.next + x)) {
+              const float4 o = ld_wire4<WireT>(T.ring + (size_t)x * row_bytes, cidx);
+              gv.x += o.x; gv.y += o.y; gv.z += o.z; gv.w += o.w;
+            }
+          }
+          gv.x *= gmul; gv.y *= gmul; gv.z *= gmul; gv.w *= gmul;
+          px_row_apply4<FAM>(T.kind, hp, gv, T.table, T.slot0, T.slot1, T.slot2, T.shadow,
+                             (size_t)r, T.D4, cidx);
+        }
       }
       __syncwarp();
-      if (use_slotmap && lane == 0) slotmap[r] = -1;
+      if (a.use_merge && lane == 0) a.slotmap[r] = -1;
     }
   }
   // ---- completion: publish applied[me] = step to every rank
   __threadfence_system();
   __syncthreads();
-  __shared__ bool s_last;
   if (threadIdx.x == 0) s_last = (atomicAdd(&ctl->apply_done, 1u) == gridDim.x - 1);
   __syncthreads();
   if (!s_last) return;
   __threadfence_system();
   const uint32_t step = ctl->step + 1;
-  if (threadIdx.x < g.W) st_release_sys(hdrs[threadIdx.x] + PX_MAX_RANKS + rank, step);
+  if (threadIdx.x < g.W) st_release_sys(a.hdrs[threadIdx.x] + PX_MAX_RANKS + a.rank, step);
   __syncthreads();
-  if (threadIdx.x == 0) { ctl->step = step; ctl->apply_done = 0; }
+  if (threadIdx.x == 0) {
+    ctl->step = step; ctl->apply_done = 0; ctl->bar = 0;
+    ctl->t_own[2] = px_globaltimer();
+  }
 }
 
 // ---------------------------------------------------------------------------
-extern "C" {
-
-struct PxTableGeom { int V, P, W, rows_per_part, D4, strategy, replicated, extras, base; };
-static inline TableGeom to_geom(const PxTableGeom* g) {
-  TableGeom t; t.V = g->V; t.P = g->P; t.W = g->W; t.rows_per_part = g->rows_per_part;
-  t.D4 = g->D4; t.strategy = g->strategy; t.replicated = g->replicated; t.extras = g->extras;
-  t.base = g->base; return t;
+template <typename GT, typename WT, bool AS, int FAM>
+static void launch_push(int blocks, size_t smem, cudaStream_t stream, const int32_t* pend_ids,
+                        int n, const PushArgs& a, const GroupGeom& G, SparseCtl* ctl, int hbits,
+                        int dedup) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(px_sparse_push_kernel<GT, WT, AS, FAM>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4 * 8192);
+    attr = true;
+  }
+  px_sparse_push_kernel<GT, WT, AS, FAM><<<blocks, 256, smem, stream>>>(pend_ids, n, a, G, ctl,
+                                                                         hbits, dedup);
 }
 
+extern "C" {
+
+struct PxGroupGeom {
+  int V, P, W, rows_per_part, strategy, replicated, extras, base;
+  const int* part_owner; const int* part_slot;
+};
+static inline GroupGeom to_geom(const PxGroupGeom* g) {
+  GroupGeom t; t.V = g->V; t.P = g->P; t.W = g->W; t.rows_per_part = g->rows_per_part;
+  t.strategy = g->strategy; t.replicated = g->replicated; t.extras = g->extras; t.base = g->base;
+  t.part_owner = g->part_owner; t.part_slot = g->part_slot; return t;
+}
+
+// C mirrors of the per-table descriptors (plain pointers / ints, filled from Python)
+struct PxLookupTable { const void* srcs; void* out; int D4, src_bf16, out_bf16, pad; };
+struct PxPushTable {
+  const void* grads; float* staging; void* rings; void* tables; void* slot0s; void* slot1s;
+  void* slot2s; void* shadows; const float* hp; int D4, kind; float scale; int pad;
+};
+struct PxOwnerTable {
+  void* ring; float* table; float* slot0; float* slot1; float* slot2; void* shadow;
+  const float* hp; int D4, kind; float avg; int pad;
+};
+
 size_t px_sparse_ctl_bytes() { return sizeof(SparseCtl); }
-int px_sparse_hdr_words() { return PX_TBL_HDR_WORDS; }
+int px_sparse_hdr_words() { return PX_GRP_HDR_WORDS; }
+int px_sparse_group_max() { return PX_GRP_MAX; }
+// byte offset of the device timestamps inside SparseCtl (t_push[2], t_own[3]: 5 x u64)
+int px_sparse_ctl_time_offset() { return (int)offsetof(SparseCtl, t_push); }
+int px_sparse_ctl_overflow_offset() { return (int)offsetof(SparseCtl, overflow); }
 
 static inline int pick_lpr(int D4) { int l = 1; while (l < D4 && l < 32) l <<= 1; return l; }
 
-// ids_is64: 1 = int64 ids, 0 = int32.  out_dtype 0 fp32 / 1 bf16.
-int px_sparse_lookup(const void* ids, int ids_is64, int n, void* tables_dev, void* out,
-                     int out_dtype, int32_t* pend_ids, const PxTableGeom* g, const void* hdr_mine,
+// ids_is64: 1 = int64 ids, 0 = int32.
+int px_sparse_lookup(const void* ids, int ids_is64, int n, const PxLookupTable* tabs, int nt,
+                     int32_t* pend_ids, const PxGroupGeom* g, const void* hdr_mine,
                      const void* ctl, int wait, cudaStream_t stream) {
   if (n <= 0) return 0;
-  const TableGeom G = to_geom(g);
-  const int lpr = pick_lpr(G.D4);
+  if (nt < 1 || nt > PX_GRP_MAX) return -4;
+  const GroupGeom G = to_geom(g);
+  LookupArgs a{};
+  a.nt = nt;
+  int maxv = 1;
+  for (int t = 0; t < nt; ++t) {
+    a.t[t].srcs = (const void* const*)tabs[t].srcs; a.t[t].out = tabs[t].out;
+    a.t[t].D4 = tabs[t].D4; a.t[t].src_bf16 = tabs[t].src_bf16; a.t[t].out_bf16 = tabs[t].out_bf16;
+    const int v = tabs[t].src_bf16 ? (tabs[t].D4 + 1) / 2 : tabs[t].D4;
+    if (v > maxv) maxv = v;
+  }
+  const int lpr = pick_lpr(maxv);
   const int threads = 256, rpb = threads / lpr;
   int blocks = (n + rpb - 1) / rpb;
   if (blocks > 148 * 8) blocks = 148 * 8;
   const uint32_t* applied = reinterpret_cast<const uint32_t*>(hdr_mine) + PX_MAX_RANKS;
-#define LK(IdT, OutT)                                                                          \
-  px_sparse_lookup_kernel<IdT, OutT><<<blocks, threads, 0, stream>>>(                          \
-      (const IdT*)ids, n, (float* const*)tables_dev, (OutT*)out, pend_ids, G, applied,         \
-      (const SparseCtl*)ctl, lpr, wait)
-  if (ids_is64) { if (out_dtype == 0) LK(long long, float); else LK(long long, __nv_bfloat16); }
-  else { if (out_dtype == 0) LK(int, float); else LK(int, __nv_bfloat16); }
-#undef LK
+  if (ids_is64)
+    px_sparse_lookup_kernel<long long><<<blocks, threads, 0, stream>>>(
+        (const long long*)ids, n, a, pend_ids, G, applied, (const SparseCtl*)ctl, lpr, wait);
+  else
+    px_sparse_lookup_kernel<int><<<blocks, threads, 0, stream>>>(
+        (const int*)ids, n, a, pend_ids, G, applied, (const SparseCtl*)ctl, lpr, wait);
   return (int)cudaGetLastError();
 }
 
-// Local aggregation.  hbits: log2 of hash size (>= 2n).  If smem_ok the
-// single-CTA shared-memory variant is used, else the global two-pass variant
-// (keys/slot_u: device scratch of 2^hbits int32 each; keys are reset here).
-int px_sparse_dedup(const int32_t* pend_ids, int n, int hbits, int32_t* keys, int32_t* slot_u,
-                    int32_t* uniq_id, int32_t* uniq_k, int32_t* uniq_head, int32_t* next,
-                    void* ctl, const PxTableGeom* g, int dedup, int use_smem,
-                    cudaStream_t stream) {
-  const TableGeom G = to_geom(g);
-  if (use_smem) {
-    const size_t smem = (size_t)2 * sizeof(int32_t) << hbits;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(px_sparse_dedup_smem_kernel,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_set = true;
-    }
-    if (smem > 200 * 1024) return -2;
-    px_sparse_dedup_smem_kernel<<<1, 1024, smem, stream>>>(pend_ids, n, hbits, uniq_id, uniq_k,
-                                                           uniq_head, next, (SparseCtl*)ctl, G,
-                                                           dedup);
-  } else {
-    int blocks = (n + 255) / 256;
-    if (blocks > 148 * 4) blocks = 148 * 4;
-    if (blocks < 1) blocks = 1;
-    if (dedup) cudaMemsetAsync(keys, 0xff, sizeof(int32_t) << hbits, stream);
-    px_sparse_dedup_insert_kernel<<<blocks, 256, 0, stream>>>(
-        pend_ids, n, hbits, keys, slot_u, uniq_id, uniq_k, uniq_head, next, (SparseCtl*)ctl, G,
-        dedup);
-    if (dedup)
-      px_sparse_dedup_link_kernel<<<blocks, 256, 0, stream>>>(pend_ids, n, hbits, keys, slot_u,
-                                                              uniq_head, next);
+static inline int push_hbits(int n, int blocks) {
+  // >= 4x the expected ids per CTA, 1024..8192 slots (16 B of SMEM per slot)
+  long long want = 4LL * ((n + blocks - 1) / blocks);
+  int hb = 10;
+  while ((1LL << hb) < want && hb < 13) ++hb;
+  return hb;
+}
+
+// grad_dtype / wire_dtype: 0 fp32, 1 bf16.  async: 1 = remote optimizer application (Hogwild).
+// All member tables of a group use the same optimizer kind family.
+int px_sparse_push(const int32_t* pend_ids, int n, const PxPushTable* tabs, int nt,
+                   int grad_dtype, int wire_dtype, int async, void* ring_ids_dev, void* hdrs_dev,
+                   int cap, const PxGroupGeom* g, void* ctl, int rank, int dedup, int max_blocks,
+                   cudaStream_t stream) {
+  if (nt < 1 || nt > PX_GRP_MAX) return -4;
+  const GroupGeom G = to_geom(g);
+  PushArgs a{};
+  a.nt = nt; a.ring_ids = (int32_t* const*)ring_ids_dev; a.hdrs = (uint32_t* const*)hdrs_dev;
+  a.cap = cap; a.rank = rank;
+  int fam = 0;
+  for (int t = 0; t < nt; ++t) {
+    PushTable& T = a.t[t];
+    T.grads = tabs[t].grads; T.staging = tabs[t].staging; T.rings = (char* const*)tabs[t].rings;
+    T.tables = (float* const*)tabs[t].tables; T.slot0s = (float* const*)tabs[t].slot0s;
+    T.slot1s = (float* const*)tabs[t].slot1s; T.slot2s = (float* const*)tabs[t].slot2s;
+    T.shadows = (__nv_bfloat16* const*)tabs[t].shadows; T.hp = tabs[t].hp;
+    T.D4 = tabs[t].D4; T.kind = tabs[t].kind; T.scale = tabs[t].scale;
+    if (t == 0) fam = PX_KIND_FAMILY(T.kind);
+    else if (fam != PX_KIND_FAMILY(T.kind)) return -6;
   }
-  return (int)cudaGetLastError();
-}
-
-// grad_dtype 0 fp32 / 1 bf16.  rings_dev/hdrs_dev: device arrays of `world` pointers.
-// sync push: scatter (position-parallel) + flush (duplicates, flags).
-int px_sparse_push(const void* pend_grads, int grad_dtype, int n, const int32_t* pos2u,
-                   const int32_t* uniq_id, const int32_t* uniq_k, const int32_t* uniq_cnt,
-                   float* staging, void* ctl, void* rings_dev, void* hdrs_dev,
-                   size_t ring_ids_off, int cap, const PxTableGeom* g, float scale, int rank,
-                   int max_blocks, cudaStream_t stream) {
-  const TableGeom G = to_geom(g);
-  PushDst d{};
-  d.rings = (char* const*)rings_dev; d.ring_ids_off = ring_ids_off; d.cap = cap; d.rank = rank;
-  const int lpr = pick_lpr(G.D4), rpb = 256 / lpr;
-  int blocks = (n + rpb - 1) / rpb;
+  int blocks = (n + 31) / 32;
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
-  if (grad_dtype == 0)
-    px_sparse_scatter_kernel<float, false><<<blocks, 256, 0, stream>>>(
-        (const float*)pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging,
-        (const SparseCtl*)ctl, d, (uint32_t* const*)hdrs_dev, G, scale, lpr);
-  else
-    px_sparse_scatter_kernel<__nv_bfloat16, false><<<blocks, 256, 0, stream>>>(
-        (const __nv_bfloat16*)pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging,
-        (const SparseCtl*)ctl, d, (uint32_t* const*)hdrs_dev, G, scale, lpr);
-  // only ids carried by several positions are staged: a small grid suffices
-  const int fblocks = blocks > 96 ? 96 : blocks;
-  px_sparse_flush_kernel<false><<<fblocks, 256, 0, stream>>>(
-      uniq_id, uniq_k, uniq_cnt, staging, (SparseCtl*)ctl, d, (uint32_t* const*)hdrs_dev, G,
-      scale, lpr);
+  const int hbits = push_hbits(n, blocks);
+  const size_t smem = (size_t)4 * sizeof(int32_t) << hbits;
+  SparseCtl* C = (SparseCtl*)ctl;
+#define PUSH(GT, WT, AS, FAM) launch_push<GT, WT, AS, FAM>(blocks, smem, stream, pend_ids, n, a, G, C, hbits, dedup)
+  if (async) {
+    if (grad_dtype == 0) { if (fam == 0) PUSH(float, float, true, 0); else PUSH(float, float, true, 1); }
+    else { if (fam == 0) PUSH(__nv_bfloat16, float, true, 0); else PUSH(__nv_bfloat16, float, true, 1); }
+  } else if (grad_dtype == 0) {
+    if (wire_dtype != 0) return -5;             // never narrow fp32 gradients
+    PUSH(float, float, false, 0);
+  } else {
+    if (wire_dtype == 0) PUSH(__nv_bfloat16, float, false, 0);
+    else PUSH(__nv_bfloat16, __nv_bfloat16, false, 0);
+  }
+#undef PUSH
   return (int)cudaGetLastError();
 }
 
-int px_sparse_claim(void* ring, void* hdr, size_t ring_ids_off, int cap, int32_t* slotmap,
-                    const void* ctl, const PxTableGeom* g, int blocks, cudaStream_t stream) {
-  const TableGeom G = to_geom(g);
+int px_sparse_owner(const PxOwnerTable* tabs, int nt, int wire_dtype, const int32_t* ring_ids,
+                    void* hdr, void* hdrs_dev, int32_t* slotmap, int32_t* next, int cap,
+                    const PxGroupGeom* g, void* ctl, int rank, int use_merge, int blocks,
+                    cudaStream_t stream) {
+  if (nt < 1 || nt > PX_GRP_MAX) return -4;
+  GroupGeom G = to_geom(g);
+  OwnerArgs a{};
+  a.nt = nt; a.ring_ids = ring_ids; a.hdr = (uint32_t*)hdr; a.hdrs = (uint32_t* const*)hdrs_dev;
+  a.slotmap = slotmap; a.next = next; a.cap = cap; a.rank = rank; a.use_merge = use_merge;
+  int fam = 0;
+  for (int t = 0; t < nt; ++t) {
+    OwnerTable& T = a.t[t];
+    T.ring = (char*)tabs[t].ring; T.table = tabs[t].table; T.slot0 = tabs[t].slot0;
+    T.slot1 = tabs[t].slot1; T.slot2 = tabs[t].slot2; T.shadow = (__nv_bfloat16*)tabs[t].shadow;
+    T.hp = tabs[t].hp; T.D4 = tabs[t].D4; T.kind = tabs[t].kind; T.avg = tabs[t].avg;
+    if (t == 0) fam = PX_KIND_FAMILY(T.kind);
+    else if (fam != PX_KIND_FAMILY(T.kind)) return -6;
+  }
   if (blocks < 1) blocks = 1;
-  px_sparse_claim_kernel<<<blocks, 256, 0, stream>>>((char*)ring, (uint32_t*)hdr, ring_ids_off,
-                                                     cap, slotmap, (const SparseCtl*)ctl, G);
-  return (int)cudaGetLastError();
-}
-
-int px_sparse_apply(void* ring, void* hdr, size_t ring_ids_off, int cap, int32_t* slotmap,
-                    float* table, float* slot0, float* slot1, const float* hp, float avg, int kind,
-                    void* ctl, void* hdrs_dev, const PxTableGeom* g, int rank, int use_slotmap,
-                    int blocks, cudaStream_t stream) {
-  const TableGeom G = to_geom(g);
-  if (blocks < 1) blocks = 1;
-  px_sparse_apply_kernel<<<blocks, 256, 0, stream>>>(
-      (char*)ring, (uint32_t*)hdr, ring_ids_off, cap, slotmap, table, slot0, slot1, hp, avg, kind,
-      (SparseCtl*)ctl, (uint32_t* const*)hdrs_dev, G, rank, use_slotmap);
-  return (int)cudaGetLastError();
-}
-
-int px_sparse_async_apply(const void* pend_grads, int grad_dtype, int n, const int32_t* pos2u,
-                          const int32_t* uniq_id, const int32_t* uniq_k,
-                          const int32_t* uniq_cnt, float* staging, void* ctl, void* tables_dev,
-                          void* slot0s_dev, void* slot1s_dev, const float* hp, float scale,
-                          int kind, const PxTableGeom* g, int max_blocks, cudaStream_t stream) {
-  const TableGeom G = to_geom(g);
-  PushDst d{};
-  d.tables = (float* const*)tables_dev; d.slot0s = (float* const*)slot0s_dev;
-  d.slot1s = (float* const*)slot1s_dev; d.hp = hp; d.kind = kind;
-  const int lpr = pick_lpr(G.D4), rpb = 256 / lpr;
-  int blocks = (n + rpb - 1) / rpb;
-  if (blocks > max_blocks) blocks = max_blocks;
-  if (blocks < 1) blocks = 1;
-  if (grad_dtype == 0)
-    px_sparse_scatter_kernel<float, true><<<blocks, 256, 0, stream>>>(
-        (const float*)pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging,
-        (const SparseCtl*)ctl, d, nullptr, G, scale, lpr);
-  else
-    px_sparse_scatter_kernel<__nv_bfloat16, true><<<blocks, 256, 0, stream>>>(
-        (const __nv_bfloat16*)pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging,
-        (const SparseCtl*)ctl, d, nullptr, G, scale, lpr);
-  const int fblocks = blocks > 96 ? 96 : blocks;
-  px_sparse_flush_kernel<true><<<fblocks, 256, 0, stream>>>(
-      uniq_id, uniq_k, uniq_cnt, staging, (SparseCtl*)ctl, d, nullptr, G, scale, lpr);
+  static int max_coop = 0;
+  if (max_coop == 0) {
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, px_sparse_owner_kernel<float, 1>, 256,
+                                                  0);
+    max_coop = per_sm * sms;
+    if (max_coop < 1) max_coop = 1;
+  }
+  SparseCtl* C = (SparseCtl*)ctl;
+  const void* fn;
+  if (wire_dtype == 0) fn = fam == 0 ? (const void*)px_sparse_owner_kernel<float, 0>
+                                     : (const void*)px_sparse_owner_kernel<float, 1>;
+  else fn = fam == 0 ? (const void*)px_sparse_owner_kernel<__nv_bfloat16, 0>
+                     : (const void*)px_sparse_owner_kernel<__nv_bfloat16, 1>;
+  void* args[] = {&a, &G, &C};
+  cudaError_t e;
+  if (use_merge) {
+    // one grid barrier inside: every CTA must be resident
+    if (blocks > max_coop) blocks = max_coop;
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    e = cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, 0, stream);
+  } else {
+    e = cudaLaunchKernel(fn, dim3(blocks), dim3(256), args, 0, stream);
+  }
+  if (e != cudaSuccess) return (int)e;
   return (int)cudaGetLastError();
 }
 

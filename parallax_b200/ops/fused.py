@@ -90,15 +90,35 @@ def gate_interleave_perm(S, device):
     return _perm_cache[key]
 
 
+def _wgrad_chunks(T):
+    """How many pieces the weight-gradient GEMMs are cut into along time so that the
+    earlier pieces run on the side stream underneath the (latency-bound) recurrent
+    backward chain.  `PARALLAX_LSTM_WGRAD_CHUNKS=1` keeps them after the loop."""
+    import os
+    n = int(os.environ.get("PARALLAX_LSTM_WGRAD_CHUNKS", "2"))
+    return max(1, min(n, T // 2 if T >= 4 else 1))
+
+
 class _LSTMLayerFn(torch.autograd.Function):
+    """`W` is either the stacked `[E+P, 4S]` kernel of the reference's LSTM cell
+    (`Wh is None`; rows `[:E]` multiply x, rows `[E:]` multiply h — one parameter, one
+    gradient written straight into its bucket sink) or just `Wx` with `Wh` separate."""
+
     @staticmethod
-    def forward(ctx, x, Wx, Wh, bias, W_P, c0, h0, forget_bias):
+    def forward(ctx, x, W, Wh, bias, W_P, c0, h0, forget_bias):
         L = _lib()
         T, Bsz, E = x.shape
         S, P = W_P.shape
         dt = x.dtype
         dev = x.device
         x = x.contiguous()
+        stacked = Wh is None
+        ctx.stacked = stacked
+        ctx.param_refs = (W, bias, W_P)
+        if stacked:
+            Wx, Wh = W.detach()[:E], W.detach()[E:]
+        else:
+            Wx = W
         # tcgen05 path: recurrent GEMM with the LSTM cell fused into its epilogue
         # (gate-interleaved column layout, see gemm_tc.cu)
         tc = (dt == torch.bfloat16 and Bsz % 128 == 0 and P % 64 == 0 and S % 32 == 0 and
@@ -128,7 +148,7 @@ class _LSTMLayerFn(torch.autograd.Function):
         else:
             gpre = torch.empty(Bsz, 4 * S, dtype=dt, device=dev)
             for t in range(T):
-                torch.addmm(xw[t], h_all[t], Wh, out=gpre)
+                torch.addmm(xw[t], h_all[t], Wh_l, out=gpre)
                 _check(L.px_lstm_cell_fwd(_p(gpre), _p(c_all[t]), _p(act[t]),
                                           _p(c_all[t + 1]), _p(m_all[t]), Bsz, S,
                                           float(forget_bias), _DT[dt], st), "lstm_cell_fwd")
@@ -141,10 +161,12 @@ class _LSTMLayerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dH, dcT, dhT):
+        from . import sinks
         L = _lib()
         x, Wx, Wh, W_P, act, c_all, m_all, h_all = ctx.saved_tensors   # Wx/Wh: layout of `act`
         T, Bsz, E, S, P = ctx.dims
-        tc = ctx.tc
+        tc, stacked = ctx.tc, ctx.stacked
+        W_ref, bias_ref, WP_ref = ctx.param_refs
         dt, dev = x.dtype, x.device
         dH = dH.contiguous()
         dgates = torch.empty(T, Bsz, 4 * S, dtype=dt, device=dev)
@@ -163,6 +185,51 @@ class _LSTMLayerFn(torch.autograd.Function):
                   (4 * S) % 1024 == 0 and Wh.is_contiguous())
         WhT = None if use_tc else Wh.t().contiguous()
         st = _stream()
+
+        # ---- weight-gradient outputs: the parameters' bucket sinks when a dense group
+        # registered them (no pack copy afterwards), else fresh tensors
+        def sink_of(ref, shape):
+            s_ = None if tc else sinks.get(ref)
+            if s_ is not None and s_.dtype == dt and tuple(s_.shape) == tuple(shape):
+                return s_, True
+            return torch.empty(shape, dtype=dt, device=dev), False
+        if stacked:
+            dW, w_sunk = sink_of(W_ref, (E + P, 4 * S))
+            dWx_o, dWh_o = dW[:E], dW[E:]
+        else:
+            dWx_o, w_sunk = sink_of(W_ref, (E, 4 * S))
+            dWh_o = torch.empty(P, 4 * S, dtype=dt, device=dev)
+        dbias_o, b_sunk = sink_of(bias_ref, (4 * S,))
+        dWP_o, p_sunk = sink_of(WP_ref, (S, P))
+        # ---- weight-gradient GEMMs on the side stream, cut in time chunks so the earlier
+        # ones run underneath the recurrent chain
+        cur = torch.cuda.current_stream(dev)
+        ws = sinks.side_stream(dev)
+        nchunks = _wgrad_chunks(T)
+        bounds = [round(i * T / nchunks) for i in range(nchunks + 1)]   # over t, ascending
+        state = {"first": True}
+
+        def wgrad(lo, hi):
+            """accumulate the contribution of steps [lo, hi) (their dgates / dh_tot are final)"""
+            ws.wait_stream(cur)
+            with torch.cuda.stream(ws):
+                dg = dgates[lo:hi].view(-1, 4 * S)
+                hT = h_all[lo:hi].reshape(-1, P).t()
+                xT = x[lo:hi].reshape(-1, E).t()
+                mT = m_all[lo:hi].reshape(-1, S).t()
+                dh2 = dh_tot[lo:hi].view(-1, P)
+                if state["first"]:
+                    torch.mm(hT, dg, out=dWh_o)
+                    torch.mm(xT, dg, out=dWx_o)
+                    torch.sum(dg, 0, out=dbias_o)
+                    torch.mm(mT, dh2, out=dWP_o)
+                    state["first"] = False
+                else:
+                    dWh_o.addmm_(hT, dg)
+                    dWx_o.addmm_(xT, dg)
+                    dbias_o.add_(dg.sum(0))
+                    dWP_o.addmm_(mT, dh2)
+        pending_hi = T
         if dh_rec is None:
             dh_tot[T - 1].copy_(dH[T - 1])
         else:
@@ -181,24 +248,58 @@ class _LSTMLayerFn(torch.autograd.Function):
             else:
                 dh_rec = _gemm.gemm_tn(dgates[0], Wh, splits=16, bn=64) if use_tc \
                     else torch.mm(dgates[0], WhT)
+            if t in bounds[1:-1]:
+                wgrad(t, pending_hi)
+                pending_hi = t
         _count(T)
         dg2 = dgates.view(T * Bsz, 4 * S)
-        dWh = h_all[:T].reshape(T * Bsz, P).t() @ dg2
-        dWx = x.view(T * Bsz, E).t() @ dg2
-        dbias = dg2.sum(0)
-        dW_P = m_all.view(T * Bsz, S).t() @ dh_tot.view(T * Bsz, P)
+        # dx first: the embedding gradient is what the rest of backward (and the sparse
+        # push) is waiting for; the last weight-gradient chunk goes to the side stream
         dx = (dg2 @ Wx.t()).view(T, Bsz, E)
+        wgrad(0, pending_hi)
+        ev = torch.cuda.Event()
+        ev.record(ws)
+        for t_ in (dgates, dh_tot, x, h_all, m_all, dWh_o, dWx_o, dbias_o, dWP_o):
+            t_.record_stream(ws)
+        outs, plain = [], False
+        for ref, o, sunk in ((W_ref, dW if stacked else dWx_o, w_sunk),
+                             (bias_ref, dbias_o, b_sunk), (WP_ref, dWP_o, p_sunk)):
+            if sunk:
+                # in the bucket already: hand it to the dense group directly (its fused
+                # reduce/update kernel waits for `ev`), nothing goes through AccumulateGrad
+                sinks.deliver(ref, ev)
+                outs.append(None)
+            else:
+                outs.append(o)
+                plain = True
+        if plain or not stacked:
+            cur.wait_event(ev)        # plain tensors are consumed on the current stream
+        dW_out, dbias, dW_P = outs
+        dWh = None if stacked else dWh_o
         if tc:          # back to the caller's (plain) gate-column order
             _, inv = gate_interleave_perm(S, dev)
-            dWh, dWx, dbias = dWh.index_select(1, inv), dWx.index_select(1, inv), \
-                dbias.index_select(0, inv)
-        return dx, dWx, dWh, dbias, dW_P, dc, dh_rec, None
+            if stacked:
+                dW_out = dW_out.index_select(1, inv)      # (tc path never uses sinks)
+            else:
+                dW_out, dWh = dW_out.index_select(1, inv), dWh.index_select(1, inv)
+            dbias = dbias.index_select(0, inv)
+        return dx, dW_out, dWh, dbias, dW_P, dc, dh_rec, None
 
 
 def lstm_layer(x, Wx, Wh, bias, W_P, c0, h0, forget_bias=1.0):
     if x.is_cuda and x.dtype in _DT:
         return _LSTMLayerFn.apply(x, Wx, Wh, bias, W_P, c0, h0, forget_bias)
     return lstm_layer_reference(x, Wx, Wh, bias, W_P, c0, h0, forget_bias)
+
+
+def lstm_layer_stacked(x, W, bias, W_P, c0, h0, forget_bias=1.0):
+    """Same layer with the reference's stacked kernel `W = [Wx; Wh]` ([E+P, 4S],
+    `examples/lm1b/language_model.py:76-87`) passed whole: one parameter, one gradient
+    tensor, written by the weight-gradient GEMMs directly into the parameter's bucket."""
+    E = x.shape[-1]
+    if x.is_cuda and x.dtype in _DT:
+        return _LSTMLayerFn.apply(x, W, None, bias, W_P, c0, h0, forget_bias)
+    return lstm_layer_reference(x, W[:E], W[E:], bias, W_P, c0, h0, forget_bias)
 
 
 # ===========================================================================

@@ -29,15 +29,16 @@ import math
 
 import torch
 
-KINDS = ("sgd", "momentum", "adagrad", "adam", "rmsprop")        # fused sm_100a kernels
-KIND_ID = {k: i for i, k in enumerate(KINDS)}
-# The rest of the reference's recognised update ops (`graph_transform_lib.py:56-75`:
-# ApplyAdadelta, ApplyFtrl, ApplyProximalGradientDescent, ApplyProximalAdagrad,
-# ApplyAdagradDA, ApplyCenteredRMSProp) run on the host / library fabrics; the NVLink
-# fabric rejects them until their cases are added to `px_update` (they need three
-# more hyper-parameters and, for centered RMSProp, a third slot).
-HOST_KINDS = ("adadelta", "ftrl", "proximal_sgd", "proximal_adagrad", "adagrad_da",
-              "centered_rmsprop")
+# Every kind has a fused sm_100a rule (`ops/csrc/kernels/optim_rules.cuh`), split in two
+# template families so the five hot rules keep their register budget: KINDS (family 0)
+# and EXT_KINDS (family 1: the rest of the reference's recognised update ops,
+# `graph_transform_lib.py:56-75` — ApplyAdadelta, ApplyFtrl, ApplyProximalGradientDescent,
+# ApplyProximalAdagrad, ApplyAdagradDA, ApplyCenteredRMSProp; up to three slots).
+KINDS = ("sgd", "momentum", "adagrad", "adam", "rmsprop")
+EXT_KINDS = ("adadelta", "ftrl", "proximal_sgd", "proximal_adagrad", "adagrad_da",
+             "centered_rmsprop")
+HOST_KINDS = EXT_KINDS            # historical name
+KIND_ID = {k: i for i, k in enumerate(KINDS + EXT_KINDS)}
 # number of fp32 state slots per kind
 NUM_SLOTS = {"sgd": 0, "momentum": 1, "adagrad": 1, "adam": 2, "rmsprop": 2,
              "adadelta": 2, "ftrl": 2, "proximal_sgd": 0, "proximal_adagrad": 1,
@@ -53,10 +54,10 @@ SLOT_NAMES = {
 
 
 def require_fused(kind, where):
-    if kind not in KINDS:
+    if kind not in KIND_ID:
         raise NotImplementedError(
-            "optimizer kind %r has no fused kernel yet (%s); it runs on fabric='host' or "
-            "'library'.  Fused kinds: %s" % (kind, where, ", ".join(KINDS)))
+            "optimizer kind %r has no fused kernel (%s).  Fused kinds: %s"
+            % (kind, where, ", ".join(KIND_ID)))
 
 # layout of the device-side hyper-parameter vector read by the kernels
 HP_LR, HP_A, HP_B, HP_EPS, HP_WD, HP_STEP, HP_GSCALE, HP_FLAGS = range(8)

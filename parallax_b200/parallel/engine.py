@@ -50,6 +50,39 @@ class _LookupFn(torch.autograd.Function):
         return None, None, None
 
 
+class _GroupLookupFn(torch.autograd.Function):
+    """One fused lookup of several co-indexed tables (`parallax.nn.lookup_many`):
+    rows_k = table_k[ids] for every member; backward hands all gradients to the group,
+    which ships them with one push kernel."""
+
+    @staticmethod
+    def forward(ctx, anchor, ids, group):
+        ctx.group = group
+        outs, token = group.lookup(ids.reshape(-1))
+        ctx.token = token
+        return tuple(o.reshape(*ids.shape, t.D) for o, t in zip(outs, group.tables))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        ctx.group.add_pending(ctx.token, list(grads))
+        return None, None, None
+
+
+def lookup_many(modules, ids):
+    """rows of several embedding modules for the SAME ids.  On the NVLink fabric, when
+    the modules form a co-lookup group (`Model.co_lookup_groups`), this is one lookup
+    kernel forward and one push / one owner kernel backward for all of them; anywhere
+    else it is the plain sequence of lookups."""
+    tabs = [getattr(m, "table", None) for m in modules]
+    grp = getattr(tabs[0], "group", None) if tabs[0] is not None else None
+    if grp is not None and len(modules) > 1 and list(grp.tables) == tabs:
+        if torch.is_grad_enabled():
+            return list(_GroupLookupFn.apply(modules[0]._anchor, ids, grp))
+        outs, _ = grp.lookup(ids.reshape(-1), record=False)
+        return [o.reshape(*ids.shape, t.D) for o, t in zip(outs, grp.tables)]
+    return [m(ids) for m in modules]
+
+
 class ShardedEmbedding(tnn.Module):
     """Drop-in replacement for ``nn.Embedding(sparse=True)`` whose storage is
     a partitioned table on the fabric."""
@@ -257,14 +290,16 @@ class TrainEngine(object):
             loss.backward()
         if ev is not None:
             ev["bwd"].record()
-        if self.dense is not None:
-            self.dense.finish_step(step)
-        if ev is not None:
-            ev["dense"].record(self.fabric.comm_stream)
+        # sparse groups not yet pushed from inside backward, then the held-back last dense
+        # bucket: the embedding push/apply is what the next step's lookup waits for
         for t in self._table_order():
             t.finish_step(step)
         if ev is not None:
             ev["sparse"].record(self.fabric.comm_stream)
+        if self.dense is not None:
+            self.dense.finish_step(step)
+        if ev is not None:
+            ev["dense"].record(self.fabric.comm_stream)
         if self.backend == "nvlink":
             torch.cuda.current_stream(self.comm.device).wait_stream(
                 self.fabric.comm_stream)
@@ -422,42 +457,72 @@ class TrainEngine(object):
         re-laid out between timing windows instead, keeping weights and optimizer
         slots."""
         names = sorted(self.tables) if names is None else names
-        for name in names:
-            old = self.tables[name]
-            if old.layout.P == num_partitions or old.layout.replicated:
-                continue
-            weight, slots = old.full_weight(), old.full_slots()
-            path = name[:-len(".weight")] if name.endswith(".weight") else name
-            holder = None
-            for p_, m_ in self.model.named_modules():
-                if isinstance(m_, ShardedEmbedding) and m_.table is old:
-                    holder, path = m_, p_
-            strategy = old.layout.strategy
-            if self.backend in ("host", "library"):
-                from .host_backend import HostSparseTable
+        if self.backend == "nvlink":
+            self._repartition_nvlink(num_partitions, names)
+        else:
+            from .host_backend import HostSparseTable
+            for name in names:
+                old = self.tables[name]
+                if old.layout.P == num_partitions or old.layout.replicated:
+                    continue
+                weight, slots = old.full_weight(), old.full_slots()
+                holder = None
+                for p_, m_ in self.model.named_modules():
+                    if isinstance(m_, ShardedEmbedding) and m_.table is old:
+                        holder = m_
                 new = _HostTableAdapter(HostSparseTable(
-                    name, weight, num_partitions, strategy, self.graph.sparse_optimizer,
-                    self.comm, self.route, self.graph, self.config, device=old.t.device))
-            else:
-                from .nvlink_backend import NVSparseTable
-                opts = dict(self.config.sess_config) \
-                    if isinstance(self.config.sess_config, dict) else {}
-                out_dtype, cap = old.out_dtype, old.cap
-                old.release()
-                new = NVSparseTable(name, weight, num_partitions, strategy,
-                                    self.graph.sparse_optimizer, self.fabric, self.route,
-                                    self.graph, self.config, out_dtype=out_dtype, options=opts)
-                if cap:
-                    new.capacity_hint = cap
-            new.load_full(weight, slots)
-            self.tables[name] = new
-            if holder is not None:
-                holder.table = new
+                    name, weight, num_partitions, old.layout.strategy,
+                    self.graph.sparse_optimizer, self.comm, self.route, self.graph,
+                    self.config, device=old.t.device))
+                new.load_full(weight, slots)
+                self.tables[name] = new
+                if holder is not None:
+                    holder.table = new
         # captured graphs hold the old tables; the new ones allocate their rings
         # lazily, so run a few eager steps before capturing again
         self._graph_state = None
         self._graph_not_before = self.global_step + \
             int(self.config.sess_option("graph_warmup", 3))
+
+    def _repartition_nvlink(self, num_partitions, names):
+        from .nvlink_backend import NVSparseTable, NVSparseGroup
+        from .layout import assign_owners
+        opts = dict(self.config.sess_config) \
+            if isinstance(self.config.sess_config, dict) else {}
+        ps_cfg = self.config.communication_config.ps_config
+        new_groups = []
+        for grp in list(self.sparse_groups):
+            olds = list(grp.tables)
+            if not any(t.name in names for t in olds) or grp.layout.replicated or \
+                    grp.layout.P == num_partitions:
+                new_groups.append(grp)
+                continue
+            state = [(t.full_weight(), t.full_slots()) for t in olds]
+            nsl = olds[0].nslots
+            nbytes = sum(((t.V + num_partitions - 1) // num_partitions) * t.Dp * 4 * (1 + nsl)
+                         for t in olds)
+            owners = assign_owners([("g", num_partitions, nbytes)], self.comm.world)["g"] \
+                if bool(ps_cfg.boundary_among_servers) else None
+            cap = grp.cap
+            for t in olds:
+                t.release()
+            news = []
+            for t, (w, sl) in zip(olds, state):
+                nt = NVSparseTable(t.name, w, num_partitions, t.layout.strategy,
+                                   self.graph.sparse_optimizer, self.fabric, self.route,
+                                   self.graph, self.config, out_dtype=t.out_dtype,
+                                   options=opts, owners=owners, auto_group=False)
+                nt.load_full(w, sl)
+                news.append(nt)
+                self.tables[t.name] = nt
+                for m_ in self.model.modules():
+                    if isinstance(m_, ShardedEmbedding) and m_.table is t:
+                        m_.table = nt
+            ng = NVSparseGroup(news)
+            if cap:
+                ng.capacity_hint = ng.capacity_hint or cap
+            new_groups.append(ng)
+        self.sparse_groups = new_groups
 
     # ------------------------------------------------------------ reporting
     def export_report(self, path):

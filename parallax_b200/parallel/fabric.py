@@ -98,6 +98,14 @@ class Comm(object):
         dist.all_gather_object(out, obj, group=self.host_group())
         return out
 
+    def all_reduce_max_int(self, value):
+        """max over ranks of a small host integer (gloo, off the GPU streams)."""
+        if not self.distributed:
+            return int(value)
+        t = torch.tensor([int(value)], dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.host_group())
+        return int(t.item())
+
     def broadcast_object(self, obj, src=0):
         if not self.distributed:
             return obj

@@ -3,12 +3,14 @@
 Dense variables → `NVDenseGroup` (buckets in symmetric memory, fused
 reduce-scatter + optimizer + parameter all-gather kernel per bucket, launched
 from autograd hooks on a dedicated comm stream so it overlaps backward).
-Sparse variables → `NVSparseTable` (row-partitioned shard in symmetric
-memory; remote-gather lookup; dedup + P2P push; owner-side claim/apply).
+Sparse variables → `nv_sparse.NVSparseTable` / `NVSparseGroup` (row-partitioned
+shards in symmetric memory; remote-gather lookup; one push kernel and one owner
+kernel per co-lookup group and step).
 
 Static schedule: every kernel that synchronises with peers is issued on ONE
-comm stream in an order fixed at build time (buckets in index order, then
-tables in name order) — identical on all ranks, so no cross-rank wait cycle
+comm stream in an order fixed by the model (sparse groups when their last gradient
+of the step arrives, dense buckets in index order, the last bucket after the sparse
+groups) — identical on all ranks, so no cross-rank wait cycle
 can form and no per-step negotiation is needed (what Horovod's coordinator
 does every 5 ms tick, `horovod/common/operations.cc:1274-1590`).
 """
@@ -19,8 +21,10 @@ import torch
 
 from .. import optim as _optim
 from ..log import parallax_log
+from ..ops import sinks as _sinks
 from . import modes, nvops
-from .layout import TableLayout
+from .layout import TableLayout, assign_owners
+from .nv_sparse import NVSparseTable, NVSparseGroup, hp_stage     # noqa: F401 (re-export)
 from .symmetric import (SymmetricHeap, IpcExchange, CH_COMM, CH_MAIN, CH_SMALL)
 
 MODE_FUSED, MODE_REDUCE, MODE_UPDATE = 0, 1, 2
@@ -104,8 +108,12 @@ class NVDenseGroup(object):
         self.clip_rules = graph.clip_rules()
         self.ema_rule = graph.ema
         self.last_grad_norm = {}
-        self.hp_host = torch.zeros(_optim.HP_SIZE, dtype=torch.float32).pin_memory()
-        self.hp = torch.zeros(_optim.HP_SIZE, dtype=torch.float32, device=self.device)
+        self._hp = hp_stage(fabric, optimizer)
+        self.hp = self._hp.dev
+        # the last bucket to launch is held back until the sparse groups of the step have
+        # been pushed (`finish_step`): it becomes ready right when backward reaches the
+        # embedding gradients, and must not sit in front of their push on the comm stream
+        self.defer_last = bool(opts.get("dense_defer_last", True))
         self._build_buckets()
         self._install_hooks()
         self._next = 0
@@ -243,8 +251,21 @@ class NVDenseGroup(object):
 
     def _install_hooks(self):
         for b in self.buckets:
+            b.async_events = []
             for idx, (name, p, off, numel) in enumerate(b.items):
                 p.register_post_accumulate_grad_hook(self._make_hook(b, idx))
+                _sinks.register(p, b.grad_views[idx], self._make_deliver(b, idx))
+
+    def _make_deliver(self, b, idx):
+        def deliver(event=None):
+            # a fused op wrote this gradient straight into the bucket (`ops.sinks`)
+            b.pending[idx] = b.grad_views[idx]
+            if event is not None:
+                b.async_events.append(event)
+            b.ready += 1
+            if b.ready == len(b.items):
+                self._bucket_ready(b)
+        return deliver
 
     def _make_hook(self, b, idx):
         def hook(p):
@@ -257,10 +278,7 @@ class NVDenseGroup(object):
 
     # ----------------------------------------------------------------- step
     def begin_step(self, step):
-        hp = self.optimizer.hyper(step)
-        for i, v in enumerate(hp):
-            self.hp_host[i] = v
-        self.hp.copy_(self.hp_host, non_blocking=True)
+        self._hp.upload(step)
         if self.pull_mirrors and step > 1:
             # mirror refresh deferred to "first use": all-gather of the owners'
             # parameter slices before the forward pass
@@ -275,6 +293,8 @@ class NVDenseGroup(object):
         for v, g in zip(b.grad_views, b.pending):
             if g is None:
                 v.zero_()
+            elif g is v:
+                pass        # delivered in place (`ops.sinks`): no pack copy
             else:
                 views.append(v)
                 grads.append(g if g.dtype == v.dtype else g.to(v.dtype))
@@ -282,6 +302,8 @@ class NVDenseGroup(object):
             torch._foreach_copy_(views, grads)
             nvops._count(1)
         if b.need_scale:
+            for ev in b.async_events:     # scaled in place: the producer must be done
+                torch.cuda.current_stream(self.device).wait_event(ev)
             for v, s in zip(b.grad_views, b.scales):
                 if s != 1.0:
                     v.mul_(s)
@@ -290,10 +312,13 @@ class NVDenseGroup(object):
         b.is_ready = True
         self._drain()
 
-    def _drain(self):
+    def _drain(self, final=False):
         """Launch consecutive ready buckets in index order on the comm stream."""
+        last = len(self.buckets) - 1
         while self._next < len(self.buckets) and \
                 getattr(self.buckets[self._next], "is_ready", False):
+            if self._next == last and self.defer_last and not final:
+                break
             b = self.buckets[self._next]
             self._launch(b)
             self._next += 1
@@ -311,11 +336,14 @@ class NVDenseGroup(object):
     def _launch_impl(self, b):
         fab, heap, cs = self.fabric, self.heap, self.fabric.comm_stream
         cs.wait_event(b.event)
+        for ev in b.async_events:        # side-stream producers of in-place gradients
+            cs.wait_event(ev)
         W = self.world
         mb = fab.max_blocks
         ema_decay = self.ema_rule.decay if self.ema_rule is not None else 0.0
         s0 = b.slots[0] if self.nslots > 0 else None
         s1 = b.slots[1] if self.nslots > 1 else None
+        s2 = b.slots[2] if self.nslots > 2 else None
         st = self.clip_state.get(b.clip)
         if self.update == "sharded":
             if st is None:
@@ -323,24 +351,25 @@ class NVDenseGroup(object):
                                  b.master, s0, s1, b.ema, None, self.hp, None,
                                  None, b.n, 1.0 / W, ema_decay, self.kind,
                                  MODE_FUSED, b.dtype, CH_COMM, max_blocks=mb,
-                                 stream=cs, use_mc=b.mc)
+                                 stream=cs, use_mc=b.mc, slot2=s2)
             else:
                 nvops.dense_step(heap, self._grad_sources(b), self._param_targets(b),
                                  b.master, s0, s1, b.ema, b.red, self.hp, None,
                                  st.local, b.n, 1.0 / W, ema_decay, self.kind,
                                  MODE_REDUCE, b.dtype, CH_COMM, max_blocks=mb,
-                                 stream=cs, use_mc=b.mc)
+                                 stream=cs, use_mc=b.mc, slot2=s2)
                 if b is st.buckets[-1]:
                     self._finish_clip(st, cs)
                     for bb in st.buckets:
                         t0 = bb.slots[0] if self.nslots > 0 else None
                         t1 = bb.slots[1] if self.nslots > 1 else None
+                        t2 = bb.slots[2] if self.nslots > 2 else None
                         nvops.dense_step(heap, self._grad_sources(bb),
                                          self._param_targets(bb), bb.master, t0, t1,
                                          bb.ema, bb.red, self.hp, st.scale, None,
                                          bb.n, 1.0 / W, ema_decay, self.kind,
                                          MODE_UPDATE, bb.dtype, CH_COMM,
-                                         max_blocks=mb, stream=cs, use_mc=bb.mc)
+                                         max_blocks=mb, stream=cs, use_mc=bb.mc, slot2=t2)
         elif self.update == "replicated":
             # classic AR: all-reduce (mean) then every replica updates itself
             if self.protocol == "nccl" and W > 1:
@@ -410,32 +439,38 @@ class NVDenseGroup(object):
         ema_decay = self.ema_rule.decay if self.ema_rule is not None else 0.0
         s0 = b.slots[0] if self.nslots > 0 else None
         s1 = b.slots[1] if self.nslots > 1 else None
+        s2 = b.slots[2] if self.nslots > 2 else None
         g = (ctypes.c_void_p * 1)(b.grad_buf.local_ptr)
         p = (ctypes.c_void_p * 1)(b.param_buf.local_ptr)
         b._keep = (g, p)
         nvops.dense_step(self.heap, g, p, b.master, s0, s1, b.ema, None, self.hp,
                          clip, None, b.n, 1.0, ema_decay, self.kind, MODE_FUSED,
-                         b.dtype, CH_COMM, rank=0, world=1, stream=cs)
+                         b.dtype, CH_COMM, rank=0, world=1, stream=cs, slot2=s2)
 
     def _async_update(self, b, clip, cs):
         W = self.world
         mc = b.master._symm.c_ptrs()
         s0 = b.slots[0]._symm.c_ptrs() if self.nslots > 0 else None
         s1 = b.slots[1]._symm.c_ptrs() if self.nslots > 1 else None
+        s2 = b.slots[2]._symm.c_ptrs() if self.nslots > 2 else None
         nvops.dense_async(b.grad_flat, b.param_flat, mc, s0, s1, self.hp, clip,
                           b.n, self.kind, b.dtype, self.rank, W,
-                          max_blocks=self.fabric.max_blocks * 2, stream=cs)
+                          max_blocks=self.fabric.max_blocks * 2, stream=cs, slot2_c=s2)
+
+    def close(self):
+        _sinks.unregister_all(self.params)
 
     def finish_step(self, step):
         # buckets whose parameters received no gradient this step
         for b in self.buckets:
             if not getattr(b, "is_ready", False):
                 self._bucket_ready(b)
-        self._drain()
+        self._drain(final=True)
         assert self._next == len(self.buckets)
         torch.cuda.current_stream(self.device).wait_stream(self.fabric.comm_stream)
         for b in self.buckets:
             b.ready, b.is_ready, b.launched = 0, False, False
+            b.async_events = []
         self._next = 0
 
     def zero_grad(self):
@@ -508,351 +543,6 @@ class NVDenseGroup(object):
 
 
 # ===========================================================================
-class NVSparseTable(object):
-    SMEM_MAX_N = 8192
-
-    def __init__(self, name, weight, num_partitions, strategy, optimizer, fabric,
-                 route, graph, config, init=None, out_dtype=None, options=None):
-        self.name = name
-        self.fabric, self.heap = fabric, fabric.heap
-        self.comm = fabric.comm
-        self.rank, self.world, self.device = fabric.rank, fabric.world, fabric.device
-        self.route, self.optimizer = route, optimizer
-        _optim.require_fused(optimizer.kind, "NVLink fabric")
-        self.kind = optimizer.kind
-        self.nslots = _optim.NUM_SLOTS[self.kind]
-        self.V, self.D = int(weight.shape[0]), int(weight.shape[1])
-        self.Dp = (self.D + 3) // 4 * 4
-        self.D4 = self.Dp // 4
-        self.replicated = route.sparse == modes.SPARSE_ALLGATHER
-        self.layout = TableLayout(self.V, num_partitions, self.world, strategy,
-                                  replicated=self.replicated)
-        self.geom = nvops.make_geom(self.layout, self.D4)
-        self.average = bool(config.average_sparse)
-        ps = config.communication_config.ps_config
-        self.local_aggregation = bool(ps.local_aggregation)
-        self.scale = graph.scale_for(name)
-        # PSConfig.boundary_between_workers_and_servers: where gradient
-        # post-processing (the ScaleGradients factor) runs — on the sender inside
-        # the push kernel (True, the reference moves such ops to the side that
-        # shrinks/keeps the wire traffic, graph_transform_lib.py:1315-1370) or on
-        # the owner inside the apply kernel (False).
-        self.scale_on_sender = bool(ps.boundary_between_workers_and_servers)
-        opts = options or {}
-        self.out_dtype = out_dtype or torch.float32
-        self.anchor_device = self.device
-        self.max_blocks = int(opts.get("sparse_blocks", 148 * 4))
-        self.capacity_hint = (opts.get("sparse_capacity") or {}).get(name)
-        # push/apply as soon as the table's last gradient of the step has arrived
-        # (softmax tables: right after the loss backward, overlapping the LSTM
-        # backward) instead of after the whole backward pass.  The comm-stream
-        # order stays identical on all ranks because autograd order is.
-        self.early_push = bool(opts.get("sparse_early_push", True))
-        self._fwd_calls = self._bwd_calls = 0
-        self._cur_step = 0
-        self._done_step = -1
-        L = self.layout
-        rows = L.rows_local
-        # table + slots in symmetric memory (async mode updates them remotely)
-        self.tab_buf = self.heap.alloc(rows * self.Dp * 4, "table:" + name)
-        self.table = self.tab_buf.tensor(torch.float32, rows * self.Dp).view(rows, self.Dp)
-        self.slot_bufs, self.slots = [], []
-        for v in optimizer.slot_init():
-            sb = self.heap.alloc(rows * self.Dp * 4, "slot:" + name)
-            t = sb.tensor(torch.float32, rows * self.Dp).view(rows, self.Dp)
-            t.fill_(v)
-            self.slot_bufs.append(sb)
-            self.slots.append(t)
-        self._init_weights(weight, init)
-        if self.replicated:
-            # every replica reads and updates its own full copy
-            self.tables_dev = torch.tensor([self.tab_buf.local_ptr] * self.world,
-                                           dtype=torch.int64, device=self.device)
-            self.slots_dev = [torch.tensor([sb.local_ptr] * self.world,
-                                           dtype=torch.int64, device=self.device)
-                              for sb in self.slot_bufs]
-        else:
-            self._tables_dev = None
-            self._slots_dev = None
-        self.slotmap = torch.full((rows,), -1, dtype=torch.int32, device=self.device)
-        self.ctl = torch.zeros(ops_ctl_words(), dtype=torch.int32, device=self.device)
-        self.hp_host = torch.zeros(_optim.HP_SIZE, dtype=torch.float32).pin_memory()
-        self.hp = torch.zeros(_optim.HP_SIZE, dtype=torch.float32, device=self.device)
-        # header (flags) lives in its own small symmetric segment
-        self.hdr_buf = self.heap.alloc(256, "hdr:" + name)
-        self._hdrs_dev = None
-        self.ring_buf = None
-        self.cap = 0
-        self.scratch_n = 0
-        self.calls = []          # (ids32, grad) per lookup this step
-        self.stats = {"pushed_rows": 0, "steps": 0}
-
-    def _init_weights(self, weight, init):
-        L = self.layout
-        g, l = L.global_ids_of_owner(0 if self.replicated else self.rank)
-        if weight.device.type == "meta":
-            # lazy: initialise only this owner's rows, in chunks, on the device
-            gen = torch.Generator(device=self.device)
-            gen.manual_seed(int(init["seed"]) * 1000003 + (0 if self.replicated
-                                                           else self.rank))
-            self.table[:, :self.D].uniform_(-init["scale"], init["scale"],
-                                            generator=gen)
-            if self.Dp != self.D:
-                self.table[:, self.D:].zero_()
-        else:
-            w = weight.detach().to(torch.float32)
-            chunk = 1 << 20
-            for s in range(0, g.numel(), chunk):
-                gi, li = g[s:s + chunk], l[s:s + chunk].to(self.device)
-                self.table[li, :self.D] = w[gi].to(self.device)
-
-    # ---------------------------------------------------------------- forward
-    def lookup(self, flat_ids, record=True):
-        n = int(flat_ids.numel())
-        ids = flat_ids if flat_ids.is_cuda else flat_ids.to(self.device,
-                                                             non_blocking=True)
-        if ids.dtype not in (torch.int64, torch.int32):
-            ids = ids.to(torch.int64)
-        ids = ids.contiguous()
-        out = torch.empty((n, self.Dp), dtype=self.out_dtype, device=self.device)
-        pend = torch.empty(n, dtype=torch.int32, device=self.device) if record else None
-        if record:
-            self._fwd_calls += 1
-        nvops.sparse_lookup(ids, n, self._tdev(), out, pend, self.geom,
-                            self.hdr_buf.local_ptr, self.ctl,
-                            wait=self.route.sync and self.world > 1)
-        if self.Dp != self.D:
-            out = out[:, :self.D]
-        return out, pend
-
-    def _tdev(self):
-        """Device array of every rank's table pointer (built lazily: in a
-        simulated world the peers allocate after us)."""
-        if self.replicated:
-            return self.tables_dev
-        if self._tables_dev is None:
-            self._tables_dev = self.tab_buf.dev_ptrs()
-            self._slots_dev = [sb.dev_ptrs() for sb in self.slot_bufs]
-        return self._tables_dev
-
-    def _sdev(self, i):
-        self._tdev()
-        sd = self.slots_dev if self.replicated else self._slots_dev
-        return sd[i] if i < len(sd) else None
-
-    def add_pending(self, token, grad_rows):
-        g = grad_rows
-        if self.Dp != self.D:
-            g = torch.nn.functional.pad(g, (0, self.Dp - self.D))
-        if g.dtype not in (torch.float32, torch.bfloat16):
-            g = g.float()
-        self.calls.append((token, g.contiguous()))
-        self._bwd_calls += 1
-        if self.early_push and self._bwd_calls == self._fwd_calls and self._cur_step > 0 \
-                and self.ring_ready():
-            self._run_step(self._cur_step)
-
-    def ring_ready(self):
-        """Early push needs every lazy allocation done (first step runs at the end)."""
-        return self.scratch_n > 0 and (not self.route.sync or self.ring_buf is not None)
-
-    # ----------------------------------------------------------------- update
-    def _ensure_capacity(self, n):
-        if n > self.scratch_n:
-            cap = max(int(n * 1.25) + 16, 64)
-            dev = self.device
-            mk = lambda: torch.empty(cap, dtype=torch.int32, device=dev)
-            self.uniq_id, self.uniq_k, self.uniq_cnt, self.pos2u = mk(), mk(), mk(), mk()
-            # fp32 staging rows for ids carried by several positions (kept zero
-            # between steps by the flush kernel)
-            self.staging = torch.zeros(cap, self.Dp, dtype=torch.float32, device=dev)
-            self.hbits = max(6, int(math.ceil(math.log2(max(2 * cap, 2)))))
-            self.use_smem = cap <= self.SMEM_MAX_N
-            if not self.use_smem:
-                self.keys = torch.full((1 << self.hbits,), -1, dtype=torch.int32, device=dev)
-                self.slot_u = torch.empty(1 << self.hbits, dtype=torch.int32, device=dev)
-            else:
-                self.keys = self.slot_u = None
-            self.scratch_n = cap
-        if self.route.sync and self.ring_buf is None:
-            want = self.capacity_hint or max(int(n * 1.25) + 16, 64)
-            if self.comm.distributed:
-                want = max(self.comm.all_gather_object(int(want)))
-            self.cap = int(want)
-            rows_b = self.world * self.cap * self.Dp * 4
-            ids_b = self.world * self.cap * 4
-            self.ring_ids_off = (rows_b + 255) // 256 * 256
-            self.ring_buf = self.heap.alloc(self.ring_ids_off + ids_b, "ring:" + self.name)
-            self._rings_dev = None
-            if self.comm.distributed:
-                torch.cuda.synchronize(self.device)
-                self.comm.barrier()
-        if self.route.sync and n > self.cap:
-            raise RuntimeError(
-                "sparse table %r: %d gradient rows in one step exceed the ring "
-                "capacity %d fixed at the first step; pass sess_config="
-                "{'sparse_capacity': {%r: N}}" % (self.name, n, self.cap, self.name))
-
-    @property
-    def hdrs_dev(self):
-        if self._hdrs_dev is None:
-            self._hdrs_dev = self.hdr_buf.dev_ptrs()
-        return self._hdrs_dev
-
-    @property
-    def rings_dev(self):
-        if self._rings_dev is None:
-            self._rings_dev = self.ring_buf.dev_ptrs()
-        return self._rings_dev
-
-    def warm(self, n):
-        """Allocate everything a step of `n` gradient rows needs (no lazy
-        allocation / pointer upload will happen inside the step)."""
-        self._ensure_capacity(n)
-        self._tdev()
-        if self.route.sync:
-            self.rings_dev, self.hdrs_dev
-
-    def begin_step(self, step):
-        hp = self.optimizer.hyper(step)
-        for i, v in enumerate(hp):
-            self.hp_host[i] = v
-        self.hp.copy_(self.hp_host, non_blocking=True)
-        self._cur_step = step
-        self._fwd_calls = self._bwd_calls = 0
-
-    def finish_step(self, step, stream=None):
-        if self._done_step == step and not self.calls:
-            return                           # already pushed from the backward pass
-        self._run_step(step, stream)
-
-    def _run_step(self, step, stream=None):
-        from ..utils import timeline
-        self._done_step = step
-        if timeline.enabled():
-            cs = stream if stream is not None else self.fabric.comm_stream
-            with timeline.activity(self.name, "SPARSE_PUSH_APPLY", gpu=True, stream=cs,
-                                   args="rows=%d" % sum(c[0].numel() for c in self.calls)):
-                self._finish_step_impl(step, stream)
-        else:
-            self._finish_step_impl(step, stream)
-
-    def _finish_step_impl(self, step, stream=None):
-        self.stage_push(step, stream)
-        if self.route.sync:
-            self.stage_apply(step, stream)
-
-    def stage_push(self, step, stream=None):
-        """Sender side: local aggregation + push (or remote apply in async
-        mode).  Separate from `stage_apply` so that a world simulated on one GPU
-        can enqueue every rank's push before any rank's (spinning) owner kernels —
-        streams of one process may share a hardware queue."""
-        cs = stream if stream is not None else self.fabric.comm_stream
-        calls, self.calls = self.calls, []
-        if calls:
-            pend_ids = calls[0][0] if len(calls) == 1 else torch.cat([c[0] for c in calls])
-            grads = calls[0][1] if len(calls) == 1 else torch.cat([c[1] for c in calls])
-        else:
-            pend_ids = torch.empty(0, dtype=torch.int32, device=self.device)
-            grads = torch.empty((0, self.Dp), dtype=torch.float32, device=self.device)
-        n = int(pend_ids.numel())
-        self._ensure_capacity(max(n, 1))
-        self._last_n = n
-        self.stats["pushed_rows"] += n
-        self.stats["steps"] += 1
-        cur = torch.cuda.current_stream(self.device)
-        cs.wait_stream(cur)
-        if not torch.cuda.is_current_stream_capturing():
-            pend_ids.record_stream(cs)
-            grads.record_stream(cs)
-        nvops.sparse_dedup(pend_ids, n, self.hbits, self.keys, self.slot_u,
-                           self.uniq_id, self.uniq_k, self.uniq_cnt, self.pos2u,
-                           self.ctl, self.geom, self.local_aggregation,
-                           self.use_smem, stream=cs)
-        s0d, s1d = self._sdev(0), self._sdev(1)
-        if not self.route.sync:
-            nvops.sparse_async_apply(grads, n, self.pos2u, self.uniq_id, self.uniq_k,
-                                     self.uniq_cnt, self.staging, self.ctl,
-                                     self._tdev(), s0d, s1d, self.hp, self.scale,
-                                     self.kind, self.geom, self.max_blocks, stream=cs)
-            return
-        nvops.sparse_push(grads, n, self.pos2u, self.uniq_id, self.uniq_k,
-                          self.uniq_cnt, self.staging, self.ctl, self.rings_dev,
-                          self.hdrs_dev, self.ring_ids_off, self.cap, self.geom,
-                          self.scale if self.scale_on_sender else 1.0, self.rank,
-                          self.max_blocks, stream=cs)
-
-    def stage_apply(self, step, stream=None):
-        """Owner side: merge rows from all sources, apply the sparse optimizer."""
-        cs = stream if stream is not None else self.fabric.comm_stream
-        n = getattr(self, "_last_n", 1)
-        # 8 warps per CTA, one row per warp; bounded by the configured cap
-        blk_own = max(1, min(self.max_blocks, (n * self.world + 7) // 8))
-        need_claim = self.world > 1 or not self.local_aggregation
-        if need_claim:
-            nvops.sparse_claim(self.ring_buf.local_ptr, self.hdr_buf.local_ptr,
-                               self.ring_ids_off, self.cap, self.slotmap, self.ctl,
-                               self.geom, blk_own, stream=cs)
-        avg = (1.0 / self.world) if self.average else 1.0
-        if not self.scale_on_sender:
-            avg *= self.scale
-        nvops.sparse_apply(self.ring_buf.local_ptr, self.hdr_buf.local_ptr,
-                           self.ring_ids_off, self.cap, self.slotmap, self.table,
-                           self.slots[0] if self.nslots > 0 else None,
-                           self.slots[1] if self.nslots > 1 else None, self.hp, avg,
-                           self.kind, self.ctl, self.hdrs_dev, self.geom, self.rank,
-                           need_claim, blk_own, stream=cs)
-
-    # -------------------------------------------------------------- checkpoint
-    def _gather_full(self, local):
-        L, W = self.layout, self.world
-        local = local[:, :self.D].contiguous()
-        out = torch.zeros(self.V, self.D)
-        if self.replicated or W == 1:
-            g, l = L.global_ids_of_owner(0 if self.replicated else self.rank)
-            out[g] = local.cpu()[l]
-            return out
-        shards = self.comm.all_gather_tensors(local)
-        for o in range(W):
-            g, l = L.global_ids_of_owner(o)
-            out[g] = shards[o].cpu()[l]
-        return out
-
-    def full_weight(self):
-        torch.cuda.synchronize(self.device)
-        return self._gather_full(self.table)
-
-    def full_slots(self):
-        torch.cuda.synchronize(self.device)
-        return [self._gather_full(s) for s in self.slots]
-
-    def release(self):
-        """Free this table's symmetric segments (collective)."""
-        torch.cuda.synchronize(self.device)
-        if self.comm.distributed:
-            self.comm.barrier()
-        for b in [self.tab_buf, self.hdr_buf, self.ring_buf] + list(self.slot_bufs):
-            if b is not None:
-                self.heap.free(b)
-        self.table = None
-        self.slots = []
-
-    def load_full(self, weight, slots=None):
-        g, l = self.layout.global_ids_of_owner(0 if self.replicated else self.rank)
-        l = l.to(self.device)
-        self.table[l, :self.D] = weight.float()[g].to(self.device)
-        if slots is not None:
-            for s, full in zip(self.slots, slots):
-                s[l, :self.D] = full.float()[g].to(self.device)
-        torch.cuda.synchronize(self.device)
-
-
-def ops_ctl_words():
-    from .. import ops
-    return int(ops.lib().px_sparse_ctl_bytes()) // 4
-
-
-# ===========================================================================
 def build_nvlink(engine):
     """Module surgery for the NVLink fabric (called by `TrainEngine._build`)."""
     from .engine import ShardedEmbedding, _set_submodule
@@ -878,20 +568,65 @@ def build_nvlink(engine):
     cdt = {None: None, "float32": torch.float32, "fp32": torch.float32,
            "bfloat16": torch.bfloat16, "bf16": torch.bfloat16}.get(cdt, cdt)
     # sparse tables first (their weights may be meta / huge)
-    sparse_items = list(engine.analysis.sparse_modules.items())
-    for path, mod in sorted(sparse_items, key=lambda kv: kv[0]):
-        pname = path + ".weight" if path else "weight"
+    sparse_items = sorted(engine.analysis.sparse_modules.items(), key=lambda kv: kv[0])
+    pname_of = lambda path: path + ".weight" if path else "weight"
+    # co-lookup groups: tables that the model looks up with the same ids in one call
+    # (`parallax.nn.lookup_many`); declared by the model (`co_lookup_groups`, module
+    # paths) or sess_config["sparse_groups"]
+    declared = list(opts.get("sparse_groups") or
+                    getattr(engine.model, "co_lookup_groups", None) or [])
+    known = {path for path, _ in sparse_items}
+    group_of, groups = {}, []
+    for paths in declared:
+        paths = [p_ for p_ in paths if p_ in known]
+        if len(paths) > 1:
+            groups.append(paths)
+            for p_ in paths:
+                group_of[p_] = len(groups) - 1
+    # byte-greedy placement of every partition of every sparse variable on its owner
+    # (`ps/between_graph_parallel.py:49-70`); PSConfig.boundary_among_servers=False keeps
+    # the naive round-robin placement
+    nslots = _optim.NUM_SLOTS[g.sparse_optimizer.kind]
+    def item_bytes(path, mod):
+        info = engine.analysis.variables[pname_of(path)]
+        rows = (int(mod.weight.shape[0]) + info.partitions - 1) // info.partitions
+        return info.partitions, rows * ((int(mod.weight.shape[1]) + 3) // 4 * 16) * (1 + nslots)
+    mods = dict(sparse_items)
+    place_items, seen = [], set()
+    for path, mod in sparse_items:
+        key = ("g", group_of[path]) if path in group_of else ("t", path)
+        if key in seen:
+            continue
+        seen.add(key)
+        members = groups[group_of[path]] if path in group_of else [path]
+        parts = {item_bytes(m_, mods[m_])[0] for m_ in members}
+        if len(parts) != 1:
+            raise ValueError("co-lookup group %s: members differ in partition count" % members)
+        place_items.append((key, parts.pop(),
+                            sum(item_bytes(m_, mods[m_])[1] for m_ in members)))
+    owners = assign_owners(place_items, comm.world) \
+        if bool(ps_cfg.boundary_among_servers) else {}
+    for path, mod in sparse_items:
+        pname = pname_of(path)
         info = engine.analysis.variables[pname]
         part = getattr(mod, "partitioner", None)
+        key = ("g", group_of[path]) if path in group_of else ("t", path)
         t = NVSparseTable(
             pname, mod.weight, info.partitions,
             part.strategy if part is not None else "mod", g.sparse_optimizer,
             fabric, engine.route, g, cfg,
             init={"seed": getattr(mod, "init_seed", 1234),
                   "scale": getattr(mod, "init_scale", 0.05)},
-            out_dtype=cdt or torch.float32, options=opts)
+            out_dtype=cdt or torch.float32, options=opts, owners=owners.get(key),
+            auto_group=False)
         engine.tables[pname] = t
         _set_submodule(engine.model, path, ShardedEmbedding(t))
+    engine.sparse_groups = []
+    for paths in groups:
+        engine.sparse_groups.append(NVSparseGroup([engine.tables[pname_of(p_)] for p_ in paths]))
+    for path, _ in sparse_items:
+        if path not in group_of:
+            engine.sparse_groups.append(NVSparseGroup([engine.tables[pname_of(path)]]))
     engine.model.to(dev)
     if cdt is not None:
         for p in engine.model.parameters():

@@ -70,11 +70,12 @@ def allgather(heap, buf_cptrs, slice_bytes, channels, max_blocks=32, stream=None
 
 def dense_step(heap, grads_cptrs, params_cptrs, master, slot0, slot1, ema, red,
                hp, clip, sumsq, n, avg, ema_decay, kind, mode, dtype, channels,
-               rank=None, world=None, max_blocks=32, stream=None, use_mc=False):
+               rank=None, world=None, max_blocks=32, stream=None, use_mc=False,
+               slot2=None):
     L = ops.lib()
     _count()
     ops.check(L.px_dense_step(
-        grads_cptrs, params_cptrs, _p(master), _p(slot0), _p(slot1), _p(ema),
+        grads_cptrs, params_cptrs, _p(master), _p(slot0), _p(slot1), _p(slot2), _p(ema),
         _p(red), _p(hp), _p(clip), _p(sumsq), n, avg, ema_decay, KIND_ID[kind],
         mode, DT[dtype], _p(heap.pads_dev()) if heap is not None else _vp(0),
         _p(heap.epoch) if heap is not None else _vp(0), channels[0], channels[1],
@@ -92,11 +93,11 @@ def clip_scale(sumsq_total, max_norm, scale_out, norm_out, zero_after, stream=No
 
 
 def dense_async(my_grads, my_params, master_c, slot0_c, slot1_c, hp, clip, n,
-                kind, dtype, rank, world, max_blocks=64, stream=None):
+                kind, dtype, rank, world, max_blocks=64, stream=None, slot2_c=None):
     L = ops.lib()
     _count()
     ops.check(L.px_dense_async(_p(my_grads), _p(my_params), master_c, slot0_c,
-                               slot1_c, _p(hp), _p(clip), n, KIND_ID[kind],
+                               slot1_c, slot2_c, _p(hp), _p(clip), n, KIND_ID[kind],
                                DT[dtype], rank, world, max_blocks, _s(stream)),
               "dense_async")
 
@@ -107,77 +108,7 @@ def sumsq(x, n, dtype, mul, out, stream=None):
     ops.check(L.px_sumsq(_p(x), n, DT[dtype], mul, _p(out), _s(stream)), "sumsq")
 
 
-def make_geom(layout, D4):
-    g = ops.PxTableGeom()
-    g.V, g.P, g.W = layout.V, layout.P, layout.world
-    g.rows_per_part, g.D4 = layout.rows_per_part, D4
-    g.strategy = 0 if layout.strategy == "mod" else 1
-    g.replicated = 1 if layout.replicated else 0
-    g.extras = getattr(layout, "_extras", 0)
-    g.base = getattr(layout, "_base", 0)
-    return g
-
-
-def sparse_lookup(ids, n, tables_dev, out, pend_ids, geom, hdr_ptr, ctl, wait,
-                  stream=None):
+def stamp(slot_ptr, stream=None):
+    """Write %globaltimer (ns) into a device u64 — a graph-capturable timestamp."""
     L = ops.lib()
-    _count()
-    ops.check(L.px_sparse_lookup(
-        _p(ids), 1 if ids.dtype == torch.int64 else 0, n, _p(tables_dev), _p(out),
-        DT[out.dtype], _p(pend_ids), ctypes.byref(geom), _vp(hdr_ptr), _p(ctl),
-        1 if wait else 0, _s(stream)), "sparse_lookup")
-
-
-def sparse_dedup(pend_ids, n, hbits, keys, slot_u, uniq_id, uniq_k, uniq_cnt,
-                 pos2u, ctl, geom, dedup, use_smem, stream=None):
-    L = ops.lib()
-    _count(1 if use_smem else (3 if dedup else 1))
-    ops.check(L.px_sparse_dedup(_p(pend_ids), n, hbits, _p(keys), _p(slot_u),
-                                _p(uniq_id), _p(uniq_k), _p(uniq_cnt), _p(pos2u),
-                                _p(ctl), ctypes.byref(geom), 1 if dedup else 0,
-                                1 if use_smem else 0, _s(stream)), "sparse_dedup")
-
-
-def sparse_push(pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging, ctl,
-                rings_dev, hdrs_dev, ring_ids_off, cap, geom, scale, rank,
-                max_blocks=592, stream=None):
-    L = ops.lib()
-    _count(2)
-    ops.check(L.px_sparse_push(_p(pend_grads), DT[pend_grads.dtype], n, _p(pos2u),
-                               _p(uniq_id), _p(uniq_k), _p(uniq_cnt), _p(staging),
-                               _p(ctl), _p(rings_dev), _p(hdrs_dev), ring_ids_off, cap,
-                               ctypes.byref(geom), scale, rank, max_blocks,
-                               _s(stream)), "sparse_push")
-
-
-def sparse_claim(ring_ptr, hdr_ptr, ring_ids_off, cap, slotmap, ctl, geom,
-                 max_blocks=64, stream=None):
-    L = ops.lib()
-    _count()
-    ops.check(L.px_sparse_claim(_vp(ring_ptr), _vp(hdr_ptr), ring_ids_off, cap,
-                                _p(slotmap), _p(ctl), ctypes.byref(geom),
-                                max_blocks, _s(stream)), "sparse_claim")
-
-
-def sparse_apply(ring_ptr, hdr_ptr, ring_ids_off, cap, slotmap, table, slot0,
-                 slot1, hp, avg, kind, ctl, hdrs_dev, geom, rank, use_slotmap,
-                 max_blocks=64, stream=None):
-    L = ops.lib()
-    _count()
-    ops.check(L.px_sparse_apply(_vp(ring_ptr), _vp(hdr_ptr), ring_ids_off, cap,
-                                _p(slotmap), _p(table), _p(slot0), _p(slot1),
-                                _p(hp), avg, KIND_ID[kind], _p(ctl), _p(hdrs_dev),
-                                ctypes.byref(geom), rank, 1 if use_slotmap else 0,
-                                max_blocks, _s(stream)), "sparse_apply")
-
-
-def sparse_async_apply(pend_grads, n, pos2u, uniq_id, uniq_k, uniq_cnt, staging, ctl,
-                       tables_dev, slot0s_dev, slot1s_dev, hp, scale, kind, geom,
-                       max_blocks=592, stream=None):
-    L = ops.lib()
-    _count(2)
-    ops.check(L.px_sparse_async_apply(
-        _p(pend_grads), DT[pend_grads.dtype], n, _p(pos2u), _p(uniq_id), _p(uniq_k),
-        _p(uniq_cnt), _p(staging), _p(ctl), _p(tables_dev), _p(slot0s_dev),
-        _p(slot1s_dev), _p(hp), scale, KIND_ID[kind], ctypes.byref(geom), max_blocks,
-        _s(stream)), "sparse_async_apply")
+    ops.check(L.px_stamp(_vp(slot_ptr), _s(stream)), "stamp")

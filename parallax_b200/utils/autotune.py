@@ -99,8 +99,8 @@ class EngineAutotuner(object):
         cb, sb, done = vals
         eng = self.engine
         eng.fabric.max_blocks = max(1, min(128, cb))
-        for t in eng.tables.values():
-            t.max_blocks = max(1, sb)
+        for grp in getattr(eng, "sparse_groups", ()):
+            grp.max_blocks = max(1, sb)
         self.done = done
         if self.log and eng.comm.rank == 0:
             with open(self.log, "a") as f:

@@ -393,8 +393,9 @@ def test_remaining_tf_optimizers_math():
                                0.01 * g / (ms - mg * mg + 1e-3).sqrt())
     assert len(spec.slot_init()) == 3
     with pytest.raises(NotImplementedError, match="no fused kernel"):
-        optim.require_fused("ftrl", "NVLink fabric")
-    optim.require_fused("adam", "NVLink fabric")
+        optim.require_fused("lion", "NVLink fabric")
+    for kind in optim.KINDS + optim.EXT_KINDS:       # every recognised update op is fused
+        optim.require_fused(kind, "NVLink fabric")
 
 
 @pytest.mark.parametrize("name", ["adadelta", "ftrl", "proximal_sgd", "proximal_adagrad",

@@ -103,7 +103,9 @@ def test_broadcast_and_allgather(world):
 
 @pytest.mark.parametrize("world", [1, 2, 4])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("kind", ["sgd", "momentum", "adagrad", "adam", "rmsprop"])
+@pytest.mark.parametrize("kind", ["sgd", "momentum", "adagrad", "adam", "rmsprop",
+                                  "adadelta", "ftrl", "ftrl_p", "proximal_sgd",
+                                  "proximal_adagrad", "adagrad_da", "centered_rmsprop"])
 def test_dense_step_fused(world, dtype, kind):
     """reduce-scatter + optimizer + param all-gather in one kernel."""
     from parallax_b200 import optim
@@ -112,7 +114,19 @@ def test_dense_step_fused(world, dtype, kind):
     fabs = _setup(world)
     opt = {"sgd": optim.GradientDescent(0.1), "momentum": optim.Momentum(0.1, 0.9, True),
            "adagrad": optim.Adagrad(0.1, 0.5), "adam": optim.Adam(0.01),
-           "rmsprop": optim.RMSProp(0.01, momentum=0.9)}[kind]
+           "rmsprop": optim.RMSProp(0.01, momentum=0.9),
+           "adadelta": optim.Adadelta(0.5, rho=0.9, epsilon=1e-4),
+           "ftrl": optim.Ftrl(0.1, l1_regularization_strength=0.01,
+                              l2_regularization_strength=0.02),
+           "ftrl_p": optim.Ftrl(0.1, learning_rate_power=-0.3,
+                                l1_regularization_strength=0.01),
+           "proximal_sgd": optim.ProximalGradientDescent(0.1, 0.05, 0.1),
+           "proximal_adagrad": optim.ProximalAdagrad(0.1, 0.5, l1_regularization_strength=0.05,
+                                                     l2_regularization_strength=0.1),
+           "adagrad_da": optim.AdagradDA(0.1, l1_regularization_strength=0.01,
+                                         l2_regularization_strength=0.1),
+           "centered_rmsprop": optim.CenteredRMSProp(0.01, momentum=0.9, epsilon=1e-3)}[kind]
+    kind = opt.kind
     vn = 4 if dtype == torch.float32 else 8
     n = world * vn * 32 * 7
     sl = n // world
@@ -145,7 +159,8 @@ def test_dense_step_fused(world, dtype, kind):
                              slots[r][0] if len(slots[r]) > 0 else None,
                              slots[r][1] if len(slots[r]) > 1 else None, ema[r],
                              None, hp, None, None, n, 1.0 / world, 0.9, kind, 0,
-                             dtype, CH_COMM, max_blocks=4, stream=f.comm_stream)
+                             dtype, CH_COMM, max_blocks=4, stream=f.comm_stream,
+                             slot2=slots[r][2] if len(slots[r]) > 2 else None)
         torch.cuda.synchronize()
         gmean = torch.stack(grads).sum(0) / world
         optim.apply_dense_(kind, ref_w, gmean, ref_slots, hp_list)

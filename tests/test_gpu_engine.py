@@ -54,6 +54,22 @@ def test_engine_matches_host_oracle(run_option, opt_name):
                                rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("opt_name", ["ftrl", "centered_rmsprop", "adagrad_da"])
+def test_engine_extended_optimizers_match_host_oracle(opt_name):
+    """The long tail of the reference's recognised update ops runs on the fused kernels
+    (rule family 1), dense and sparse."""
+    mk = lambda: {"ftrl": optim.Ftrl(0.2, l1_regularization_strength=0.001),
+                  "centered_rmsprop": optim.CenteredRMSProp(0.01, momentum=0.5, epsilon=1e-3),
+                  "adagrad_da": optim.AdagradDA(0.2, l1_regularization_strength=0.001)}[opt_name]
+    l_ref, sd_ref = _run("host", "HYBRID", mk(), 5)
+    l_nv, sd_nv = _run("nvlink", "HYBRID", mk(), 5)
+    np.testing.assert_allclose(l_nv, l_ref, rtol=2e-4, atol=2e-5)
+    for n, w in sd_ref["dense"]["master"].items():
+        torch.testing.assert_close(sd_nv["dense"]["master"][n], w, rtol=2e-4, atol=2e-5)
+    torch.testing.assert_close(sd_nv["sparse"]["emb.weight"]["weight"],
+                               sd_ref["sparse"]["emb.weight"]["weight"], rtol=2e-4, atol=2e-5)
+
+
 def test_engine_replicated_update_and_async():
     l_ref, sd_ref = _run("host", "MPI", optim.Momentum(0.1, 0.9), 4)
     l_nv, sd_nv = _run("nvlink", "MPI", optim.Momentum(0.1, 0.9), 4,
