@@ -51,6 +51,14 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dense-nvls", default="auto", choices=["auto", "on", "off"],
                     help="NVLS multicast dense step: auto = on a full 8-GPU box")
+    ap.add_argument("--protocol", default="nvlink", choices=["nvlink", "nccl"],
+                    help="nccl = same engine / same CUDA graph, every cross-GPU byte through "
+                         "NCCL collectives (the in-engine library baseline)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the secondary blocks (same-engine NCCL arm, fp32 LM1B, "
+                         "ResNet-50, sustained run, self-check)")
+    ap.add_argument("--sustained-s", type=float, default=3.0,
+                    help="length of the additional sustained-clock run (seconds)")
     return ap.parse_args()
 
 
@@ -100,13 +108,17 @@ class ClockSampler(object):
         return out
 
     def stop(self, t0=None, t1=None):
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        return self.window(t0, t1)
+
+    def window(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
         recs = self._parse(list(self.lines))
         inside = [r for r in recs if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)]
         window = "timed region"
@@ -226,56 +238,51 @@ def build_bert(args, parallax, torch):
     return graph, make_batch, desc, "bert_tokens_per_sec", "tokens/s", None
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        return reference_arm(args)
+def _max_over_ranks(torch, dist, world, dev, vals):
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+def measure(args, model, dtype, K, Wm, world, rank, protocol="nvlink", e2e=True,
+            comm_stamps=False, sustained_s=0.0, sampler=None):
+    """Build a session for `model`, run Wm warm-up + exactly K timed steps (device events,
+    max over ranks) and the optional extra regions; returns the result block."""
     import torch
     import torch.distributed as dist
-    if args.impl == "nccl":
-        from baseline.nccl_reference import main as nccl_main
-        return nccl_main(args)
     import parallax_b200 as parallax
     from parallax_b200.parallel import nvops
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    assert world == args.gpus or world == 1, "launch with torchrun for --gpus > 1"
-    if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device", "metric": "lm1b_words_per_sec"}))
-        return 1
-    torch.manual_seed(1234 + rank)
+    margs = argparse.Namespace(**vars(args))
+    margs.model, margs.dtype = model, dtype
     builder = {"lm1b": build_lm1b, "resnet50": build_resnet, "ncf": build_ncf,
-               "bert": build_bert}[args.model]
-    graph, make_batch, desc, metric, unit, baseline = builder(args, parallax, torch)
-    sc = {"compute_dtype": args.dtype, "cuda_graph": not args.no_graph}
+               "bert": build_bert}[model]
+    graph, make_batch, desc, metric, unit, baseline = builder(margs, parallax, torch)
+    sc = {"compute_dtype": dtype, "cuda_graph": not args.no_graph}
     if args.dense_nvls != "auto":
         sc["dense_nvls"] = args.dense_nvls == "on"
-    cfg = parallax.Config(run_option=args.run_option, search_partitions=False,
-                          sess_config=sc)
+    run_option = "MPI" if model == "resnet50" else args.run_option
+    cfg = parallax.Config(run_option=run_option, search_partitions=False, sess_config=sc)
+    if protocol == "nccl":
+        cfg.communication_config = parallax.CommunicationConfig(
+            parallax.PSConfig(protocol="nccl"))
     sess, nw, wid, _ = parallax.parallel_run(graph, "localhost:0", sync=True,
                                              parallax_config=cfg)
     eng = sess.engine
     dev = eng.comm.device
     gen = torch.Generator().manual_seed(99 + rank)
-    # untimed warm-up: at least 3 steps, and — when the step is graph-captured —
-    # enough to cover the eager steps plus the capture itself (which must never
-    # fall inside the timed region).  The JSON reports the number actually run.
-    K, Wm = args.steps, max(args.warmup, 3)
     if sc["cuda_graph"]:
         Wm = max(Wm, int(sc.get("graph_warmup", 3)) + 2)
+    items = desc["items_per_step"] * world
 
     # ---- device-timed arm: inputs resident on the device -------------------
     batches = [{k: v.to(dev) for k, v in make_batch(gen).items()} for _ in range(4)]
-    sampler = ClockSampler(dev.index or 0)
-    if rank == 0:
-        sampler.start()          # streaming by the time the timed region starts
     for i in range(Wm):
         eng.train_step(batches[i % 4])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t_window0 = time.time()
+    t_w0 = time.time()
     l0 = nvops.launches["n"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -284,19 +291,42 @@ def main():
         out = eng.train_step(batches[i % 4])
     e1.record()
     torch.cuda.synchronize()
+    t_w1 = time.time()
     launches = nvops.launches["n"] - l0
     if world > 1:
         dist.barrier()
-    ms = e0.elapsed_time(e1)
-    loss_val = float(out["loss"])
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, = _max_over_ranks(torch, dist, world, dev, [e0.elapsed_time(e1)])
+    res = {"metric": metric, "value": items * K / (ms / 1e3), "unit": unit,
+           "ms_per_step": ms / K, "steps": K, "warmup": Wm, "dtype": dtype,
+           "gpu_launches": launches, "loss": float(out["loss"]),
+           "cuda_graph": bool(getattr(eng, "graph_captured", False)),
+           "run_option": eng.run_option.lower(), "protocol": protocol,
+           "_desc": desc, "_baseline": baseline, "_window": (t_w0, t_w1)}
+
+    # ---- sustained run: the same step for >= sustained_s seconds -------------
+    if sustained_s > 0:
+        n_s = max(K, int(sustained_s * 1e3 / max(ms / K, 1e-3)) + 1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        s_w0 = time.time()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(n_s):
+            eng.train_step(batches[i % 4])
+        s1.record()
+        torch.cuda.synchronize()
+        s_w1 = time.time()
+        if world > 1:
+            dist.barrier()
+        ms_s, = _max_over_ranks(torch, dist, world, dev, [s0.elapsed_time(s1)])
+        res["sustained"] = {"steps": n_s, "seconds": ms_s / 1e3, "ms_per_step": ms_s / n_s,
+                            "value": items * n_s / (ms_s / 1e3), "unit": unit}
+        if sampler is not None and rank == 0:
+            res["sustained"]["clocks"] = sampler.window(s_w0, s_w1)
 
     # ---- end-to-end arm: public API, pinned H2D in, loss D2H out -------------
-    e2e = None
-    if not args.no_e2e:
+    if e2e:
         host_batches = [{k: v.pin_memory() for k, v in make_batch(gen).items()}
                         for _ in range(4)]
         h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
@@ -314,55 +344,134 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        t2 = torch.tensor([s0.elapsed_time(s1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        ms2 = float(t2.item())
-        e2e = {"value": desc["items_per_step"] * world * K / (ms2 / 1e3), "unit": unit,
-               "ms_per_step": ms2 / K, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "last_loss": float(loss[0])}
-    clocks = sampler.stop(t_window0, time.time()) if rank == 0 else None
-    # exposed (non-overlapped) comm per step, dense vs sparse — eager steps, device events
-    comm_bd = None
-    try:
-        comm_bd = eng.comm_breakdown(batches[0], steps=5)
-        tb = torch.tensor([comm_bd[k] for k in sorted(comm_bd)], device=dev)
-        if world > 1:
-            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
-        comm_bd = {k: round(float(v), 4) for k, v in zip(sorted(comm_bd), tb)}
-        comm_bd["note"] = ("eager (ungraphed) steps, max over ranks; at N>1 eager steps are "
-                           "CPU-launch-bound and the 'exposed' figures are dominated by "
-                           "cross-rank launch skew absorbed in the kernels' start barriers, "
-                           "not by data movement — compare ms_per_step across N for the "
-                           "graph-replayed cost of communication")
-    except Exception as e:  # pragma: no cover
-        comm_bd = {"error": str(e)}
+        ms2, = _max_over_ranks(torch, dist, world, dev, [s0.elapsed_time(s1)])
+        res["e2e"] = {"value": items * K / (ms2 / 1e3), "unit": unit,
+                      "ms_per_step": ms2 / K, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": 4, "last_loss": float(loss[0])}
 
-    value = desc["items_per_step"] * world * K / (ms / 1e3)
+    # ---- exposed communication, measured inside the CUDA-graph replay ---------
+    if comm_stamps:
+        try:
+            bd = eng.comm_breakdown_replayed(batches[0], steps=20)
+            keys = sorted(k for k in bd if k != "graph_replay")
+            vals = _max_over_ranks(torch, dist, world, dev, [bd[k] for k in keys])
+            res["comm"] = {k: round(v, 4) for k, v in zip(keys, vals)}
+            res["comm"]["how"] = ("%globaltimer probes captured in the step graph, 20 replays, "
+                                  "max over ranks" if bd["graph_replay"] else "eager steps")
+        except Exception as e:  # pragma: no cover
+            res["comm"] = {"error": repr(e)}
+    sess.close()
+    return res
+
+
+def _public(block, keep=("value", "unit", "ms_per_step", "steps", "warmup", "dtype", "loss",
+                         "e2e", "sustained", "comm", "gpu_launches", "cuda_graph",
+                         "protocol", "run_option", "metric")):
+    return {k: block[k] for k in keep if k in block}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+    import torch
+    import torch.distributed as dist
+    if args.impl == "nccl":
+        from baseline.nccl_reference import main as nccl_main
+        return nccl_main(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun for --gpus > 1"
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device", "metric": "lm1b_words_per_sec"}))
+        return 1
+    from parallax_b200.parallel.fabric import Comm
+    comm = Comm.from_env()            # one process group for every arm below
+    torch.manual_seed(1234 + rank)
+    K, Wm = args.steps, max(args.warmup, 3)
+    extras = not args.no_extras and not args.small
+    sampler = ClockSampler(comm.device.index or 0)
+    if rank == 0:
+        sampler.start()          # streaming by the time the timed region starts
+
+    # ---- correctness first: the live fabric vs a single-device oracle ---------
+    selfcheck = None
+    if extras:
+        from parallax_b200.utils import selfcheck as sc_
+        try:
+            r = sc_.check(world, rank, "HYBRID", "adagrad", steps=4)
+            oks = comm.all_gather_object((r["ok"], r["max_abs_err"]))
+            selfcheck = {"ok": all(o for o, _ in oks), "max_abs_err": max(e for _, e in oks),
+                         "what": "MLP+embedding, HYBRID/adagrad, 4 steps vs single-device "
+                                 "oracle on the concatenated batch", "backend": r["backend"]}
+        except Exception as e:
+            selfcheck = {"ok": False, "error": repr(e)}
+        if not selfcheck["ok"]:
+            if rank == 0:
+                print(json.dumps({"error": "self-check failed", "selfcheck": selfcheck,
+                                  "metric": "lm1b_words_per_sec"}))
+            return 1
+
+    main_blk = measure(args, args.model, args.dtype, K, Wm, world, rank,
+                       protocol=args.protocol, e2e=not args.no_e2e, comm_stamps=extras,
+                       sustained_s=args.sustained_s if extras else 0.0, sampler=sampler)
+    clocks = sampler.window(*main_blk["_window"]) if rank == 0 else None
+    blocks = {}
+    if extras and args.model == "lm1b":
+        def arm(name, **kw):
+            try:
+                blocks[name] = _public(measure(args, **kw))
+            except Exception as e:      # a secondary block must never lose the headline
+                blocks[name] = {"error": repr(e)}
+        if world > 1 and args.protocol == "nvlink":
+            arm("same_engine_nccl", model="lm1b", dtype=args.dtype, K=K, Wm=Wm, world=world,
+                rank=rank, protocol="nccl", e2e=False)
+            b = blocks["same_engine_nccl"]
+            if "value" in b:
+                b["what"] = ("identical model, engine and CUDA-graph capture; dense = "
+                             "ncclAllReduce on the bucket + local fused optimizer, sparse = "
+                             "ncclAllGather of (ids, rows) + owner apply, lookup = "
+                             "ncclAllGather(ids) + local gather + ncclReduceScatter")
+                b["nvlink_over_nccl"] = main_blk["value"] / b["value"]
+        arm("lm1b_fp32", model="lm1b", dtype="fp32", K=K, Wm=Wm, world=world, rank=rank,
+            e2e=False)
+        arm("resnet50", model="resnet50", dtype="bf16", K=K, Wm=Wm, world=world, rank=rank,
+            e2e=True)
+        if "value" in blocks.get("resnet50", {}):
+            blocks["resnet50"]["vs_baseline"] = blocks["resnet50"]["value"] / BASELINE_RESNET_IPS
+            blocks["resnet50"]["config"] = {"model": "resnet50_v1", "global_batch": 64 * world,
+                                            "parallelism": "dp%d/mpi(AR)/sync" % world,
+                                            "optimizer": "momentum(0.9)", "layout": "channels_last"}
+    sampler.stop()
+    desc, baseline = main_blk["_desc"], main_blk["_baseline"]
     if rank == 0:
         rec = {
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world,
-            "steps": K, "warmup": Wm, "ms_per_step": ms / K,
+            "metric": main_blk["metric"], "value": main_blk["value"], "unit": main_blk["unit"],
+            "n_gpus": world, "steps": K, "warmup": main_blk["warmup"],
+            "ms_per_step": main_blk["ms_per_step"],
             "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": (value / baseline) if baseline else None, "dtype": args.dtype,
+            "vs_baseline": (main_blk["value"] / baseline) if baseline else None,
+            "dtype": args.dtype,
             "data": "synthetic (random ids / images, random-init weights)",
             "impl": "parallax_b200",
             "config": {"model": desc["model"],
                        "global_batch": desc["per_gpu_batch"] * world,
                        "seq_len": desc["seq_len"],
-                       "parallelism": "dp%d/%s/sync" % (world, eng.run_option.lower()),
-                       "optimizer": desc["optimizer"],
+                       "parallelism": "dp%d/%s/sync" % (world, main_blk["run_option"]),
+                       "optimizer": desc["optimizer"], "protocol": args.protocol,
                        "l2": "inputs larger than L2 (tables >> 126 MB, fresh random rows each step)"
                        if args.model == "lm1b" else "activations+weights >> L2 per step",
-                       "cuda_graph": bool(getattr(eng, "graph_captured", False)),
-                       "valid": not args.small},
+                       "cuda_graph": main_blk["cuda_graph"], "valid": not args.small},
             "baseline": {"value": baseline,
                          "what": "Parallax-HYBRID on 48x TITAN Xp (BASELINE.md)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "comm": comm_bd,
-            "loss": loss_val,
+            "clocks": clocks, "e2e": main_blk.get("e2e"),
+            "gpu_launches": main_blk["gpu_launches"], "comm": main_blk.get("comm"),
+            "sustained": main_blk.get("sustained"), "loss": main_blk["loss"],
+            "selfcheck": selfcheck,
         }
+        rec.update(blocks)
         print(json.dumps(rec))
-    sess.close()
+    comm.shutdown()
     return 0
 
 

@@ -7,13 +7,24 @@ so an existing checkpoint is restored automatically at start
 (`mpi/runner.py:178-193`, `hybrid/runner.py:243-257`); partitioned variables
 are saved as slices of one logical variable.
 
-Format: ``<ckpt_dir>/model.ckpt-<global_step>.pt`` holding full *logical*
-tensors keyed by single-device variable names (weights, optimizer slots, EMA
-shadows, global_step) plus a ``checkpoint`` index file naming the latest one —
-so it can be resumed under a different world size, run option or partition
-count.  Gathering of sharded state is a collective (all ranks participate);
-only the chief writes.
+Two formats, both layout-independent (resumable under a different world size,
+run option or partition count), both named by a ``checkpoint`` index file:
+
+* **sharded** (NVLink fabric, default) — a directory
+  ``<ckpt_dir>/model.ckpt-<global_step>/`` with ``manifest.json``, ``dense.pt``
+  (chief: full logical dense tensors, slots, EMA, buffers) and one
+  ``sparse-<variable>-rank<r>.pt`` per owner holding ``(global row ids, rows,
+  slot rows)`` of exactly the rows that rank owns — TF's sharded Saver for
+  partitioned variables (`tensorflow/python/training/saver.py:287-433`): no rank
+  ever materialises a whole table, so a 100 M-row table saves and restores
+  without a gather.  Restore reads its own shard when the placement is unchanged
+  and otherwise scatters every shard's rows to their new owners.
+* **single file** ``model.ckpt-<global_step>.pt`` (host / library fabric, or
+  ``sess_config={"sharded_checkpoint": False}``) — full logical tensors; gathering
+  is a collective, only the chief writes.
 """
+import json
+import re
 import os
 import time
 
@@ -23,6 +34,7 @@ from .log import parallax_log
 
 INDEX = "checkpoint"
 PREFIX = "model.ckpt-"
+MANIFEST = "manifest.json"
 
 
 def latest_checkpoint(ckpt_dir):
@@ -36,11 +48,96 @@ def latest_checkpoint(ckpt_dir):
         if os.path.exists(path):
             return path
     cands = [f for f in os.listdir(ckpt_dir)
-             if f.startswith(PREFIX) and f.endswith(".pt")]
+             if f.startswith(PREFIX) and (f.endswith(".pt") or os.path.exists(
+                 os.path.join(ckpt_dir, f, MANIFEST)))]
     if not cands:
         return None
-    cands.sort(key=lambda f: int(f[len(PREFIX):-3]))
+    cands.sort(key=lambda f: int(re.sub(r"\.pt$", "", f[len(PREFIX):])))
     return os.path.join(ckpt_dir, cands[-1])
+
+
+def _safe(name):
+    return re.sub(r"[^A-Za-z0-9_.-]", "_", name)
+
+
+def save_sharded(engine, path, is_chief):
+    """Write the sharded format into directory `path` (collective)."""
+    comm = engine.comm
+    if is_chief:
+        os.makedirs(path, exist_ok=True)
+    comm.barrier()
+    torch.cuda.synchronize(comm.device)
+    manifest = {"format": 2, "global_step": engine.global_step, "world": comm.world,
+                "run_option": engine.run_option, "sparse": {}}
+    for name, t in sorted(engine.tables.items()):
+        writers = [0] if t.replicated else list(range(comm.world))
+        files = ["sparse-%s-rank%d.pt" % (_safe(name), r) for r in writers]
+        manifest["sparse"][name] = {
+            "V": t.V, "D": t.D, "nslots": t.nslots, "files": files,
+            "placement": [t.layout.P, t.layout.strategy, t.layout.world, t.layout.owners,
+                          bool(t.replicated)]}
+        if comm.rank in writers:
+            ids, w = t.local_rows("weight")
+            slots = [t.local_rows(str(i))[1] for i in range(t.nslots)]
+            fn = os.path.join(path, files[writers.index(comm.rank)])
+            torch.save({"ids": ids, "weight": w, "slots": slots}, fn + ".tmp")
+            os.replace(fn + ".tmp", fn)
+    dense = engine.dense.state_dict() if engine.dense is not None else None   # collective
+    if is_chief:
+        bufs = {n: b.detach().cpu().clone() for n, b in engine.model.named_buffers()}
+        torch.save({"global_step": engine.global_step, "dense": dense, "buffers": bufs},
+                   os.path.join(path, "dense.pt"))
+        with open(os.path.join(path, MANIFEST + ".tmp"), "w") as f:
+            json.dump(manifest, f, indent=1)
+        os.replace(os.path.join(path, MANIFEST + ".tmp"), os.path.join(path, MANIFEST))
+    comm.barrier()
+    return path
+
+
+def load_sharded(engine, path):
+    """Restore from a sharded checkpoint directory (any source world / partitioning)."""
+    comm = engine.comm
+    with open(os.path.join(path, MANIFEST)) as f:
+        manifest = json.load(f)
+    d = torch.load(os.path.join(path, "dense.pt"), map_location="cpu", weights_only=False)
+    engine.global_step = int(d["global_step"])
+    if engine.dense is not None and d.get("dense") is not None:
+        engine.dense.load_state_dict(d["dense"])
+    bufs = dict(engine.model.named_buffers())
+    for n, v in d.get("buffers", {}).items():
+        if n in bufs:
+            with torch.no_grad():
+                bufs[n].copy_(v)
+    for name, t in engine.tables.items():
+        ent = manifest["sparse"].get(name)
+        if ent is None:
+            continue
+        if ent["V"] != t.V or ent["D"] != t.D:
+            raise RuntimeError("checkpoint variable %r has shape (%d, %d), the model (%d, %d)"
+                               % (name, ent["V"], ent["D"], t.V, t.D))
+        same = ent["placement"] == [t.layout.P, t.layout.strategy, t.layout.world,
+                                    t.layout.owners, bool(t.replicated)]
+        files = ent["files"]
+        if same and not t.replicated:
+            files = [files[comm.rank]]          # my rows are exactly my old shard
+        for fn in files:
+            sh = torch.load(os.path.join(path, fn), map_location="cpu", weights_only=False)
+            if hasattr(t, "load_rows"):
+                t.load_rows(sh["ids"], sh["weight"], "weight")
+                for i, srows in enumerate(sh["slots"][:t.nslots]):
+                    t.load_rows(sh["ids"], srows, str(i))
+            else:               # host / library tables: scatter through the logical view
+                w, sl = t.full_weight(), t.full_slots()
+                w[sh["ids"]] = sh["weight"]
+                for i, srows in enumerate(sh["slots"][:len(sl)]):
+                    sl[i][sh["ids"]] = srows
+                t.load_full(w, sl)
+        if hasattr(t, "refresh_shadow"):
+            t.refresh_shadow()
+    if comm.is_cuda:
+        torch.cuda.synchronize(comm.device)
+    comm.barrier()
+    return manifest
 
 
 class CheckpointSaver(object):
@@ -56,6 +153,8 @@ class CheckpointSaver(object):
         self._last_time = time.time()
         self._last_step = None
         self.enabled = bool(self.dir) and (self.save_steps or self.save_secs)
+        self.sharded = (getattr(engine, "backend", None) == "nvlink" and
+                        bool(engine.config.sess_option("sharded_checkpoint", True)))
 
     def restore_if_present(self):
         """Restore-on-start; every rank loads the same logical state and keeps
@@ -68,10 +167,14 @@ class CheckpointSaver(object):
         path = self.engine.comm.broadcast_object(path, 0)
         if path is None:
             return None
-        sd = torch.load(path, map_location="cpu", weights_only=False)
-        self.engine.load_state_dict(sd)
-        parallax_log.info("restored checkpoint %s (global_step=%d)",
-                          path, sd["global_step"])
+        if os.path.isdir(path):
+            man = load_sharded(self.engine, path)
+            step = man["global_step"]
+        else:
+            sd = torch.load(path, map_location="cpu", weights_only=False)
+            self.engine.load_state_dict(sd)
+            step = sd["global_step"]
+        parallax_log.info("restored checkpoint %s (global_step=%d)", path, step)
         return path
 
     def _due(self, step):
@@ -90,6 +193,16 @@ class CheckpointSaver(object):
 
     def save(self, step=None):
         step = self.engine.global_step if step is None else step
+        if self.sharded:
+            name = "%s%d" % (PREFIX, step)
+            path = save_sharded(self.engine, os.path.join(self.dir, name), self.is_chief)
+            if self.is_chief:
+                with open(os.path.join(self.dir, INDEX), "w") as f:
+                    f.write(name)
+                parallax_log.info("saved sharded checkpoint %s", path)
+            self._last_time = time.time()
+            self._last_step = step
+            return path if self.is_chief else None
         sd = self.engine.state_dict()          # collective
         path = None
         if self.is_chief:

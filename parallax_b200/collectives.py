@@ -25,6 +25,8 @@ once and cached (`registry` — the analogue of the response cache,
 `response_cache.{h,cc}`); later calls with the same name skip the exchange.
 """
 import ctypes
+import functools
+import os
 import threading
 
 import torch
@@ -140,6 +142,7 @@ def _validate(name, kind, tensor, extra=()):
     shape = tuple(tensor.shape[1:]) if kind == "allgather" else tuple(tensor.shape)
     sig = (kind, str(tensor.dtype), shape, tensor.device.type) + tuple(extra)
     L = _registry_lib()
+    _coordinate_cache(st, L)
     h = _sig_hash(sig)
     state = L.px_registry_lookup(name.encode(), h)
     if state == 1:
@@ -153,6 +156,36 @@ def _validate(name, kind, tensor, extra=()):
     L.px_registry_put(name.encode(), h)
 
 
+def _coordinate_cache(st, L, force=False):
+    """Horovod's `CacheCoordinator::sync` (`response_cache.cc:303-432`): a local cache HIT
+    skips a *collective* exchange, which is only safe while every rank holds the same cache.
+    Every `PARALLAX_CACHE_SYNC_EVERY` named ops (same count on all ranks — collectives are
+    issued in one program order) the ranks exchange a digest of their cache plus its bit
+    vector; on any disagreement every rank drops its cache, so the next use of each name
+    is validated by all ranks together instead of hanging."""
+    if not st.comm.distributed:
+        return
+    st.validate_calls = getattr(st, "validate_calls", 0) + 1
+    every = int(os.environ.get("PARALLAX_CACHE_SYNC_EVERY", "64"))
+    if not force and (every <= 0 or st.validate_calls % every):
+        return
+    words = max(1, L.px_registry_bits(None, 0))
+    bits = (ctypes.c_uint64 * words)()
+    L.px_registry_bits(bits, words)
+    mine = (int(L.px_registry_digest()), tuple(int(b) for b in bits))
+    everyone = st.comm.all_gather_object(mine)
+    st.cache_syncs = getattr(st, "cache_syncs", 0) + 1
+    if len({d for d, _ in everyone}) != 1:
+        n = min(len(b) for _, b in everyone)
+        common = sum(bin(functools.reduce(lambda a, c: a & c, [b[i] for _, b in everyone]))
+                     .count("1") for i in range(n))
+        parallax_log.warning(
+            "collective signature caches diverged across ranks (%d entries in common): "
+            "resetting them; every name is re-validated on next use", common)
+        L.px_registry_reset(0)
+        st.cache_resets = getattr(st, "cache_resets", 0) + 1
+
+
 def _registry_lib():
     from . import ops
     global _reg_ready
@@ -164,6 +197,7 @@ def _registry_lib():
             "px_registry_put": (ctypes.c_int, [ctypes.c_char_p, u64]),
             "px_registry_erase": (ctypes.c_int, [ctypes.c_char_p]),
             "px_registry_bits": (ctypes.c_int, [ctypes.POINTER(u64), ctypes.c_int]),
+            "px_registry_digest": (u64, []),
             "px_registry_stats": (None, [ctypes.POINTER(ctypes.c_long)] * 5),
         })
         _reg_ready = True
@@ -201,10 +235,21 @@ def _allreduce_cuda(x, out, scale):
     st = _st()
     heap, W = st.fabric.heap, st.comm.world
     dt = x.dtype
-    if dt not in nvops.DT:
+    if dt == torch.float16:
+        # widened on the way in: an fp16 sum of W addends is exact in fp32
         y = torch.empty_like(x, dtype=torch.float32)
         _allreduce_cuda(x.float(), y, scale)
         out.copy_(y.to(dt))
+        return out
+    if dt not in nvops.DT:
+        # int32 / int64 / fp64 / uint8 …: exact reduction through the library (Horovod
+        # reduces these dtypes natively, `nccl_operations.cc:22-38`); an fp32 detour would
+        # corrupt counts above 2^24 and truncate float64
+        y = x.clone()
+        dist.all_reduce(y, group=st.comm.group)
+        if scale != 1.0:
+            y = y / W if dt.is_floating_point else torch.div(y, W, rounding_mode="floor")
+        out.copy_(y.view(out.shape))
         return out
     es = x.element_size()
     n = x.numel()
@@ -312,7 +357,7 @@ def _allreduce_impl(tensor, average=True, name=None, out=None):
     W = st.comm.world
     scale = (1.0 / W) if average else 1.0
     if out is None:
-        out = torch.empty_like(tensor)
+        out = torch.empty_like(tensor, memory_format=torch.contiguous_format)
     if not tensor.is_cuda or not st.cuda:
         out.copy_(tensor)
         if W > 1:
@@ -323,6 +368,13 @@ def _allreduce_impl(tensor, average=True, name=None, out=None):
     x = tensor.contiguous()
     if W == 1:
         out.copy_(x)
+        return out
+    if not out.is_contiguous():
+        # `out.reshape(-1)` of a transposed / channels_last tensor is a copy: reduce into a
+        # contiguous temporary and lay the result out afterwards
+        tmp = torch.empty_like(x)
+        _allreduce_cuda(x, tmp, scale)
+        out.copy_(tmp.view(out.shape))
         return out
     return _allreduce_cuda(x, out, scale)
 
@@ -565,13 +617,13 @@ class DistributedOptimizer(object):
         self.optimizer = optimizer
         self.sparse_as_dense = sparse_as_dense
         # `compression`: gradients travel in the compressed dtype
-        # (`horovod/torch/compression.py`); `backward_passes_per_step`: gradients of
-        # that many backward passes accumulate locally in `.grad` and are reduced
-        # once, by the `step()` that follows the last pass
+        # (`horovod/torch/compression.py`); `backward_passes_per_step` = N: the gradients
+        # of up to N backward passes accumulate locally in `.grad`; `step()` — called ONCE
+        # after them — always reduces and applies (`horovod/torch/__init__.py:79-154`: the
+        # per-parameter hooks count passes, `step()` synchronizes)
         self.compression = compression
         self.backward_passes_per_step = int(backward_passes_per_step)
         assert self.backward_passes_per_step >= 1
-        self._passes = 0
         params = [p for g in optimizer.param_groups for p in g["params"]]
         if named_parameters is not None:
             names = {id(p): n for n, p in named_parameters}
@@ -584,6 +636,17 @@ class DistributedOptimizer(object):
             raise ValueError("parameter names must be unique")
         self._params = params
         self._synchronized = False
+        self._delay = {id(p): self.backward_passes_per_step for p in params}
+        self._hooks = [p.register_post_accumulate_grad_hook(self._count_pass)
+                       for p in params if p.requires_grad]
+
+    def _count_pass(self, p):
+        if self._delay[id(p)] <= 0:
+            raise AssertionError(
+                "Gradients were computed more than backward_passes_per_step times before "
+                "call to step(). Increase backward_passes_per_step to accumulate gradients "
+                "locally.")
+        self._delay[id(p)] -= 1
 
     def synchronize(self):
         dense = [p for p in self._params if p.grad is not None and not p.grad.is_sparse]
@@ -610,15 +673,13 @@ class DistributedOptimizer(object):
         self._synchronized = True
 
     def step(self, closure=None):
-        """With `backward_passes_per_step` = N only every N-th call reduces and
-        applies; the calls in between return None and keep accumulating."""
-        self._passes += 1
-        if self._passes < self.backward_passes_per_step:
-            return None
-        self._passes = 0
+        """Reduce whatever accumulated in `.grad` since the last step (1..N backward
+        passes) and apply it."""
         if not self._synchronized:
             self.synchronize()
         self._synchronized = False
+        for k in self._delay:
+            self._delay[k] = self.backward_passes_per_step
         return self.optimizer.step(closure)
 
     def zero_grad(self, set_to_none=True):

@@ -20,7 +20,8 @@ import sys
 
 from . import consts
 from .log import parallax_log
-from .resource import (is_local_host, serialize_resource_info, worker_layout,
+from .resource import (is_local_host, routable_address, serialize_resource_info,
+                       worker_layout,
                        get_empty_port)
 
 
@@ -31,21 +32,39 @@ def remote_copy(remote_machine, local_path, remote_path, port=22):
     return subprocess.call(cmd)
 
 
-def remote_exec(bash_script, remote_machine, stdout=None, stderr=None,
-                env=None, python_venv=None, port=22):
-    """Run `bash_script` on `remote_machine` over ssh with `env` exported."""
+def remote_command(bash_script, remote_machine, env=None, python_venv=None, port=22,
+                   secret_names=()):
+    """The ssh argv for `remote_exec`.  Variables named in `secret_names` are NOT put on
+    the command line (visible in `ps` on both machines): the remote shell reads them from
+    stdin, one line each, with terminal echo off."""
     full = ""
+    for k in secret_names:
+        full += "stty -echo 2>/dev/null; IFS= read -r %s; stty echo 2>/dev/null; export %s; " \
+            % (k, k)
     if env:
         full += " ".join("export %s=%s;" % (k, shlex.quote(str(v)))
-                         for k, v in env.items())
+                         for k, v in env.items() if k not in secret_names)
     if python_venv:
         full += " source %s/bin/activate;" % python_venv
     full += " " + bash_script
-    cmd = ["ssh", "-tt", "-p", str(port), remote_machine, "bash -c %s"
-           % shlex.quote(full)]
+    return ["ssh", "-tt", "-p", str(port), remote_machine, "bash -c %s" % shlex.quote(full)]
+
+
+def remote_exec(bash_script, remote_machine, stdout=None, stderr=None,
+                env=None, python_venv=None, port=22, secret_names=()):
+    """Run `bash_script` on `remote_machine` over ssh with `env` exported."""
+    secret_names = [k for k in secret_names if env and k in env]
+    cmd = remote_command(bash_script, remote_machine, env, python_venv, port, secret_names)
     parallax_log.warning("\033[91m%s\033[0m", " ".join(cmd))
-    return subprocess.Popen(cmd, stdout=stdout, stderr=stderr,
-                            preexec_fn=os.setsid)
+    p = subprocess.Popen(cmd, stdout=stdout, stderr=stderr, preexec_fn=os.setsid,
+                         stdin=subprocess.PIPE if secret_names else None)
+    if secret_names:
+        p.stdin.write(("".join("%s\n" % env[k] for k in secret_names)).encode())
+        p.stdin.flush()
+    return p
+
+
+SECRET_ENV = (consts.PARALLAX_SEARCH_AUTHKEY,)
 
 
 def _redirect(redirect_path, role, idx):
@@ -65,7 +84,11 @@ def launch_workers(run_option, resource_info, config, extra_env=None,
     layout = worker_layout(resource_info)
     world = len(layout)
     master_host = resource_info["master"][0]["hostname"]
-    master_addr = "127.0.0.1" if is_local_host(master_host) else master_host
+    # loopback only when EVERY worker runs on this machine; a worker started over ssh on
+    # another host must be told an address it can actually reach
+    everything_local = all(is_local_host(h) for h, _, _, _ in layout)
+    master_addr = "127.0.0.1" if (everything_local and is_local_host(master_host)) \
+        else routable_address(master_host)
     master_port = resource_info["master"][0]["port"][0] \
         if resource_info["master"][0]["port"] else get_empty_port(1)[0]
     serialized = serialize_resource_info(resource_info)
@@ -103,7 +126,8 @@ def launch_workers(run_option, resource_info, config, extra_env=None,
                 shlex.quote(os.getcwd()), shlex.quote(sys.executable),
                 " ".join(shlex.quote(a) for a in argv))
             p = remote_exec(script, host, stdout=out, stderr=err, env=env,
-                            python_venv=os.environ.get("VIRTUAL_ENV"))
+                            python_venv=os.environ.get("VIRTUAL_ENV"),
+                            secret_names=SECRET_ENV)
         procs.append(p)
     return procs
 

@@ -92,7 +92,7 @@ _SIGS = {
     "px_sparse_owner": (c_int, [ctypes.POINTER(PxOwnerTable), c_int, c_int, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 ctypes.POINTER(PxGroupGeom), c_void_p, c_int, c_int, c_int,
-                                c_void_p]),
+                                c_int, c_void_p]),
     "px_stamp": (c_int, [c_void_p, c_void_p]),
 }
 

@@ -512,6 +512,8 @@ struct OwnerArgs {
   int32_t* slotmap;             // [rows_local], -1 when idle
   int32_t* next;                // [W_src * cap]
   int cap, rank, use_merge;
+  int fixed_cnt;                // >= 0: library-collective arm — every source delivered exactly this
+                                // many entries (negative row id = not mine), no flags involved
 };
 
 // ONE launch: wait for every source, merge rows that several sources touched, apply the sparse
@@ -523,11 +525,13 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
   __shared__ bool s_last;
   const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
   if (stamp) ctl->t_own[0] = px_globaltimer();
-  if (threadIdx.x < g.W) {
-    const uint32_t need = ctl->step + 1;
-    while ((int32_t)(ld_acquire_sys(a.hdr + threadIdx.x) - need) < 0) { }
+  if (a.fixed_cnt < 0) {
+    if (threadIdx.x < g.W) {
+      const uint32_t need = ctl->step + 1;
+      while ((int32_t)(ld_acquire_sys(a.hdr + threadIdx.x) - need) < 0) { }
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (stamp) ctl->t_own[1] = px_globaltimer();
   const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const uint32_t* cnt = a.hdr + 2 * PX_MAX_RANKS;
@@ -535,10 +539,11 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
     // link: every entry pushes itself on the list of its row (at most one entry per source when
     // the senders aggregate locally, so lists are <= W long)
     for (int s = 0; s < g.W; ++s) {
-      const int c = (int)ld_volatile_u32(cnt + s);
+      const int c = a.fixed_cnt >= 0 ? a.fixed_cnt : (int)ld_volatile_u32(cnt + s);
       for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < c; j += gridDim.x * blockDim.x) {
         const int e = s * a.cap + j;
-        a.next[e] = atomicExch(&a.slotmap[a.ring_ids[e]], e);
+        const int r = a.ring_ids[e];
+        if (r >= 0) a.next[e] = atomicExch(&a.slotmap[r], e);
       }
     }
     // grid barrier (all CTAs are co-resident: cooperative launch)
@@ -552,10 +557,11 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
     __syncthreads();
   }
   for (int s = 0; s < g.W; ++s) {
-    const int c = (int)ld_volatile_u32(cnt + s);
+    const int c = a.fixed_cnt >= 0 ? a.fixed_cnt : (int)ld_volatile_u32(cnt + s);
     for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < c; j += gridDim.x * warps) {
       const int e = s * a.cap + j;
       const int r = a.ring_ids[e];
+      if (r < 0) continue;
       if (a.use_merge) {
         if (__ldcg(a.slotmap + r) != e) continue;          // not the list head
       }
@@ -590,7 +596,8 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
   if (!s_last) return;
   __threadfence_system();
   const uint32_t step = ctl->step + 1;
-  if (threadIdx.x < g.W) st_release_sys(a.hdrs[threadIdx.x] + PX_MAX_RANKS + a.rank, step);
+  if (a.fixed_cnt < 0 && threadIdx.x < g.W)
+    st_release_sys(a.hdrs[threadIdx.x] + PX_MAX_RANKS + a.rank, step);
   __syncthreads();
   if (threadIdx.x == 0) {
     ctl->step = step; ctl->apply_done = 0; ctl->bar = 0;
@@ -729,10 +736,11 @@ int px_sparse_push(const int32_t* pend_ids, int n, const PxPushTable* tabs, int 
 int px_sparse_owner(const PxOwnerTable* tabs, int nt, int wire_dtype, const int32_t* ring_ids,
                     void* hdr, void* hdrs_dev, int32_t* slotmap, int32_t* next, int cap,
                     const PxGroupGeom* g, void* ctl, int rank, int use_merge, int blocks,
-                    cudaStream_t stream) {
+                    int fixed_cnt, cudaStream_t stream) {
   if (nt < 1 || nt > PX_GRP_MAX) return -4;
   GroupGeom G = to_geom(g);
   OwnerArgs a{};
+  a.fixed_cnt = fixed_cnt;
   a.nt = nt; a.ring_ids = ring_ids; a.hdr = (uint32_t*)hdr; a.hdrs = (uint32_t* const*)hdrs_dev;
   a.slotmap = slotmap; a.next = next; a.cap = cap; a.rank = rank; a.use_merge = use_merge;
   int fam = 0;

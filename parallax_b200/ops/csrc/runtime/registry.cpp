@@ -97,6 +97,20 @@ int px_registry_bits(uint64_t* out, int max_words) {
   return words;
 }
 
+// order-independent digest of the whole cache (names + signatures): equal digests on all ranks
+// <=> every rank will take the same HIT / MISS decisions from here on
+uint64_t px_registry_digest() {
+  std::lock_guard<std::mutex> lk(R.mu);
+  uint64_t d = 0x9E3779B97F4A7C15ull * (R.lru.size() + 1);
+  for (auto& e : R.lru) {
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : e.name) { h ^= c; h *= 1099511628211ull; }
+    h ^= e.sig + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    d += h * 0xD6E8FEB86659FD93ull;
+  }
+  return d;
+}
+
 void px_registry_stats(long* hits, long* misses, long* invalid, long* evictions, long* size) {
   std::lock_guard<std::mutex> lk(R.mu);
   *hits = R.hits; *misses = R.misses; *invalid = R.invalid; *evictions = R.evictions;

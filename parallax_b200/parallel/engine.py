@@ -282,6 +282,12 @@ class TrainEngine(object):
         ev = getattr(self, "_comm_events", None)
         if ev is not None:
             ev["start"].record()
+        st = getattr(self, "_stamps", None)        # device timestamps (graph-capturable)
+        if st is not None:
+            from . import nvops
+            nvops.stamp(st.data_ptr() + 0)
+            if self.dense is not None:
+                self.dense.stamp_before = st.data_ptr() + 40
         out = self.forward(feeds)
         loss = out[self.graph.loss]
         if self.graph.loss_scale != 1.0:
@@ -290,21 +296,29 @@ class TrainEngine(object):
             loss.backward()
         if ev is not None:
             ev["bwd"].record()
+        if st is not None:
+            nvops.stamp(st.data_ptr() + 8)
         # sparse groups not yet pushed from inside backward, then the held-back last dense
         # bucket: the embedding push/apply is what the next step's lookup waits for
         for t in self._table_order():
             t.finish_step(step)
         if ev is not None:
             ev["sparse"].record(self.fabric.comm_stream)
+        if st is not None:
+            nvops.stamp(st.data_ptr() + 16, self.fabric.comm_stream)
         if self.dense is not None:
             self.dense.finish_step(step)
         if ev is not None:
             ev["dense"].record(self.fabric.comm_stream)
+        if st is not None:
+            nvops.stamp(st.data_ptr() + 24, self.fabric.comm_stream)
         if self.backend == "nvlink":
             torch.cuda.current_stream(self.comm.device).wait_stream(
                 self.fabric.comm_stream)
         if ev is not None:
             ev["end"].record()
+        if st is not None:
+            nvops.stamp(st.data_ptr() + 32)
         return {k: (v.detach() if torch.is_tensor(v) else v)
                 for k, v in out.items()}
 
@@ -370,6 +384,58 @@ class TrainEngine(object):
             acc["exposed_sparse_ms"] += max(0.0, t_s - max(t_d, t_b))
         self._comm_events = None
         return {k: v / steps for k, v in acc.items()}
+
+    def comm_breakdown_replayed(self, feeds, steps=20):
+        """Exposed (non-overlapped) communication per step measured INSIDE the CUDA-graph
+        replay (BASELINE.json metric): `%globaltimer` probes are captured into the step
+        graph — at the step start / after backward / before the first kernel of the last
+        dense bucket (on the comm stream, after its inputs are complete) / after the last
+        sparse group / after the last dense bucket / at the step end — and the push / owner
+        kernels stamp themselves.  Returns per-step averages in ms:
+
+        * ``exposed_sparse_ms``  comm-stream sparse work still running after backward ended
+        * ``exposed_dense_ms``   the held-back dense bucket(s): fused reduce + optimizer +
+          parameter all-gather, from "inputs complete" to done (at N=1 this is the fused
+          optimizer alone — the N>1 minus N=1 difference is the communication)
+        * ``owner_wait_ms``      time the owner kernels spent waiting for other ranks' rows
+        * ``tail_ms``            backward end → step end (everything that is not overlapped)
+        """
+        assert self.backend == "nvlink"
+        dev = self.comm.device
+        self._stamps = torch.zeros(8, dtype=torch.int64, device=dev)
+        self._graph_state = None
+        warm = int(self.config.sess_option("graph_warmup", 3))
+        self._graph_not_before = self.global_step + warm
+        for _ in range(warm + 2):
+            self.train_step(feeds)
+        acc = {"step_ms": 0.0, "fwd_bwd_ms": 0.0, "exposed_sparse_ms": 0.0,
+               "exposed_dense_ms": 0.0, "owner_wait_ms": 0.0, "tail_ms": 0.0}
+        for _ in range(steps):
+            self.train_step(feeds)
+            torch.cuda.synchronize(dev)
+            t = self._stamps.tolist()
+            t0, t_bwd, t_sp, t_de, t_end, t_db = t[0], t[1], t[2], t[3], t[4], t[5]
+            acc["step_ms"] += (t_end - t0) / 1e6
+            acc["fwd_bwd_ms"] += (t_bwd - t0) / 1e6
+            acc["exposed_sparse_ms"] += max(0, t_sp - t_bwd) / 1e6
+            if self.dense is not None and t_db:
+                acc["exposed_dense_ms"] += max(0, t_de - max(t_db, t_bwd)) / 1e6
+            acc["tail_ms"] += max(0, t_end - t_bwd) / 1e6
+            for grp in getattr(self, "sparse_groups", ()):
+                if self.route.sync:
+                    d = grp.device_times()
+                    acc["owner_wait_ms"] += max(0, d["arrived"] - d["owner_start"]) / 1e6
+        self._stamps = None
+        if self.dense is not None:
+            self.dense.stamp_before = None
+        self._graph_state = None
+        self._graph_not_before = self.global_step + warm
+        out = {k: v / steps for k, v in acc.items()}
+        out["graph_replay"] = bool(self._use_graph_possible())
+        return out
+
+    def _use_graph_possible(self):
+        return self.backend == "nvlink" and bool(self.config.sess_option("cuda_graph", False))
 
     # ------------------------------------------------------------ CUDA graph
     def _use_graph(self):

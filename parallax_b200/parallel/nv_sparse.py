@@ -340,6 +340,10 @@ class NVSparseGroup(object):
         self.local_aggregation = t0.local_aggregation
         self.boundary = t0.boundary
         opts = t0.options
+        # PSConfig.protocol == "nccl": the in-engine library baseline — same engine, same
+        # kernels for the optimizer, but every byte that crosses GPUs goes through NCCL
+        # collectives (Horovod's IndexedSlices path: all-gather of ids and rows)
+        self.protocol = opts.get("_protocol", "nvlink")
         self.max_blocks = int(opts.get("sparse_blocks", 148 * 2))
         self.early_push = bool(opts.get("sparse_early_push", True))
         hints = [t.capacity_hint for t in tables if t.capacity_hint]
@@ -377,6 +381,96 @@ class NVSparseGroup(object):
         NVSparseGroup._seq += 1
 
     # ---------------------------------------------------------------- forward
+    # ------------------------------------------------- library-collective (NCCL) arm
+    def _nccl(self):
+        return (self.protocol == "nccl" and self.world > 1 and self.comm.distributed and
+                self.route.sync)
+
+    def _place(self, ids):
+        """(valid, owner, local row) of global ids — device tensor arithmetic."""
+        lay = self.layout
+        valid = (ids >= 0) & (ids < lay.V)
+        idc = ids.clamp(0, lay.V - 1).to(torch.int64)
+        if lay.replicated:
+            return valid, torch.zeros_like(idc), idc
+        if lay.strategy == "mod":
+            p, idx = idc % lay.P, idc // lay.P
+        else:
+            thr = lay._extras * (lay._base + 1)
+            p = torch.where(idc < thr, idc // (lay._base + 1),
+                            (idc - lay._extras) // max(lay._base, 1))
+            start = torch.where(p < lay._extras, p * (lay._base + 1),
+                                p * lay._base + lay._extras)
+            idx = idc - start
+        owner = self._owners_dev[p].to(torch.int64)
+        local = self._slots_dev[p].to(torch.int64) * lay.rows_per_part + idx
+        return valid, owner, local
+
+    def _lookup_nccl(self, members, ids, n, record):
+        import torch.distributed as dist
+        W, grp = self.world, self.comm.group
+        ids64 = ids.to(torch.int64)
+        all_ids = torch.empty(W * n, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(all_ids, ids64, group=grp)
+        valid, owner, local = self._place(all_ids)
+        mine = valid & (owner == self.rank)
+        rows = torch.where(mine, local, torch.zeros_like(local))
+        outs = []
+        for t in members:
+            src = t.shadow[:, :t.Dp] if t.use_shadow else t.table
+            part = src.index_select(0, rows).to(t.out_dtype) * mine[:, None].to(t.out_dtype)
+            out = torch.empty(n, t.Dp, dtype=t.out_dtype, device=self.device)
+            dist.reduce_scatter_tensor(out, part, group=grp)
+            outs.append(out if t.Dp == t.D else out[:, :t.D])
+        pend = None
+        if record:
+            v0, _, _ = self._place(ids64)
+            pend = torch.where(v0, ids64, torch.full_like(ids64, -1)).to(torch.int32)
+            self._fwd_calls += 1
+        _count()
+        return outs, pend
+
+    def _push_apply_nccl(self, pend_ids, grads, n, cs):
+        """all-gather (ids, rows) from every rank, then the owner kernel applies the rows
+        this rank owns (entries of other owners are marked -1)."""
+        import torch.distributed as dist
+        from .. import ops
+        L = _lib()
+        W, grp = self.world, self.comm.group
+        nt = len(self.tables)
+        with torch.cuda.stream(cs):
+            all_ids = torch.empty(W * n, dtype=torch.int32, device=self.device)
+            dist.all_gather_into_tensor(all_ids, pend_ids, group=grp)
+            valid, owner, local = self._place(all_ids.to(torch.int64))
+            mine = valid if self.replicated else (valid & (owner == self.rank))
+            ring_ids = torch.where(mine, local, torch.full_like(local, -1)).to(torch.int32)
+            nxt = torch.empty(W * n, dtype=torch.int32, device=self.device)
+            descs = (ops.PxOwnerTable * nt)()
+            keep = [all_ids, ring_ids, nxt]
+            for d, t, g in zip(descs, self.tables, grads):
+                all_g = torch.empty(W * n, t.Dp, dtype=g.dtype, device=self.device)
+                dist.all_gather_into_tensor(all_g, g, group=grp)
+                keep.append(all_g)
+                d.ring, d.table = all_g.data_ptr(), t.table.data_ptr()
+                d.slot0 = t.slots[0].data_ptr() if t.nslots > 0 else 0
+                d.slot1 = t.slots[1].data_ptr() if t.nslots > 1 else 0
+                d.slot2 = t.slots[2].data_ptr() if t.nslots > 2 else 0
+                d.shadow = t.shadow.data_ptr() if t.use_shadow else 0
+                d.hp, d.D4, d.kind = self.hp.dev.data_ptr(), t.D4, _optim.KIND_ID[t.kind]
+                d.avg = ((1.0 / W) if t.average else 1.0) * t.scale
+            if not torch.cuda.is_current_stream_capturing():
+                for k_ in keep:
+                    k_.record_stream(cs)
+            self._keep_n = (keep, descs)
+            blocks = max(1, min(self.max_blocks, (n * W + 7) // 8))
+            _count()
+            ops.check(L.px_sparse_owner(
+                descs, nt, _DT[grads[0].dtype], _vp(ring_ids.data_ptr()),
+                _vp(self.hdr_buf.local_ptr), _vp(self.hdrs_dev.data_ptr()),
+                _vp(self.slotmap.data_ptr()), _vp(nxt.data_ptr()), n,
+                ctypes.byref(self.geom), _vp(self.ctl.data_ptr()), self.rank, 1, blocks, n,
+                _sp(cs)), "sparse_owner(nccl)")
+
     def lookup(self, flat_ids, record=True, members=None):
         from .. import ops
         L = _lib()
@@ -386,6 +480,8 @@ class NVSparseGroup(object):
         if ids.dtype not in (torch.int64, torch.int32):
             ids = ids.to(torch.int64)
         ids = ids.contiguous()
+        if self._nccl() and not self.replicated and n > 0:
+            return self._lookup_nccl(members, ids, n, record)
         descs = (ops.PxLookupTable * len(members))()
         outs = []
         for d, t in zip(descs, members):
@@ -408,7 +504,7 @@ class NVSparseGroup(object):
                 len(members), _vp(pend.data_ptr()) if pend is not None else _vp(0),
                 ctypes.byref(self.geom), _vp(self.hdr_buf.local_ptr),
                 _vp(self.ctl.data_ptr()),
-                1 if (self.route.sync and self.world > 1) else 0,
+                1 if (self.route.sync and self.world > 1 and not self._nccl()) else 0,
                 _sp(torch.cuda.current_stream(self.device))), "sparse_lookup")
         return outs, pend
 
@@ -432,6 +528,8 @@ class NVSparseGroup(object):
 
     def ring_ready(self):
         """Early push needs every lazy allocation done (first step runs at the end)."""
+        if self._nccl():
+            return True
         return self.scratch_n > 0 and (not self.route.sync or self.ids_buf is not None)
 
     # ----------------------------------------------------------------- capacity
@@ -530,6 +628,21 @@ class NVSparseGroup(object):
     def _run_step(self, step, stream=None):
         from ..utils import timeline
         self._done_step = step
+        if self._nccl():
+            cs = stream if stream is not None else self.fabric.comm_stream
+            calls, self.calls = self.calls, []
+            if not calls:
+                raise RuntimeError("protocol='nccl': every rank must look the group %s up in "
+                                   "every step (collective)" % self.name)
+            nt = len(self.tables)
+            pend_ids = calls[0][0] if len(calls) == 1 else torch.cat([c[0] for c in calls])
+            grads = [calls[0][1][k] if len(calls) == 1 else
+                     torch.cat([c[1][k] for c in calls]) for k in range(nt)]
+            cur = torch.cuda.current_stream(self.device)
+            if cs is not cur:
+                cs.wait_stream(cur)
+            self._push_apply_nccl(pend_ids, grads, int(pend_ids.numel()), cs)
+            return
         if timeline.enabled():
             cs = stream if stream is not None else self.fabric.comm_stream
             with timeline.activity(self.name, "SPARSE_PUSH_APPLY", gpu=True, stream=cs,
@@ -637,7 +750,7 @@ class NVSparseGroup(object):
             _vp(self.hdr_buf.local_ptr), _vp(self.hdrs_dev.data_ptr()),
             _vp(self.slotmap.data_ptr()), _vp(self.next.data_ptr()), self.cap,
             ctypes.byref(self.geom), _vp(self.ctl.data_ptr()), self.rank,
-            1 if use_merge else 0, blocks, _sp(cs)), "sparse_owner")
+            1 if use_merge else 0, blocks, -1, _sp(cs)), "sparse_owner")
 
     # ---------------------------------------------------------------- inspection
     def device_times(self):

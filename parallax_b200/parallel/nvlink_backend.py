@@ -338,6 +338,8 @@ class NVDenseGroup(object):
         cs.wait_event(b.event)
         for ev in b.async_events:        # side-stream producers of in-place gradients
             cs.wait_event(ev)
+        if getattr(self, "stamp_before", None) and b.index == len(self.buckets) - 1:
+            nvops.stamp(self.stamp_before, cs)
         W = self.world
         mb = fab.max_blocks
         ema_decay = self.ema_rule.decay if self.ema_rule is not None else 0.0

@@ -27,6 +27,31 @@ def is_local_host(hostname):
         return False
 
 
+def routable_address(hostname):
+    """An address of `hostname` that OTHER machines can connect to: the name as written
+    in the resource file, unless it is a loopback alias of this machine — then this
+    machine's own name / primary address."""
+    if hostname not in LOCAL_NAMES:
+        return hostname
+    try:
+        name = socket.getfqdn()
+        addr = socket.gethostbyname(name)
+        if not addr.startswith("127."):
+            return addr
+        s = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+        try:
+            s.connect(("10.255.255.255", 1))        # no packet is sent
+            return s.getsockname()[0]
+        finally:
+            s.close()
+    except Exception:  # pragma: no cover
+        return socket.gethostname()
+
+
+def all_local(resource_info):
+    return all(is_local_host(w["hostname"]) for w in resource_info["worker"])
+
+
 def _get_available_gpus(hostname):
     """GPU ordinals on `hostname` (reference `common/lib.py:101-103`)."""
     if is_local_host(hostname):

@@ -79,9 +79,16 @@ def _parallax_run_master(graph, config, resource_info):
     extra_env = {}
     if search:
         min_p = int(os.environ[consts.PARALLAX_MIN_PARTITIONS])
-        addr = "127.0.0.1:%d" % get_empty_port(1)[0]
+        port = get_empty_port(1)[0]
         secret = os.urandom(16).hex()
-        collector = PartitionStatCollector(max(min_p, n_machines), addr, min_p, authkey=secret)
+        # workers on other hosts report their step times too: listen on every interface
+        # and advertise an address they can reach
+        from .resource import all_local, routable_address
+        local_job = all_local(resource_info)
+        bind = "127.0.0.1:%d" % port if local_job else "0.0.0.0:%d" % port
+        addr = "127.0.0.1:%d" % port if local_job else "%s:%d" % (
+            routable_address(resource_info["master"][0]["hostname"]), port)
+        collector = PartitionStatCollector(max(min_p, n_machines), bind, min_p, authkey=secret)
         collector.setup_manager()
         extra_env[consts.PARALLAX_SEARCH_ADDR] = addr
         extra_env[consts.PARALLAX_SEARCH_AUTHKEY] = secret

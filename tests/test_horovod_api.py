@@ -24,9 +24,19 @@ def _worker(rank, world):
                                    compression=hvd.Compression.fp16, backward_passes_per_step=2)
     w0 = model.weight.detach().clone()
     xs = [torch.full((3, 4), float(rank + 1)), torch.full((3, 4), float(rank + 3))]
+    # the Horovod idiom: N backward passes, then ONE step() that reduces and applies
     model(xs[0]).sum().backward()
-    assert opt.step() is None and torch.equal(model.weight, w0)        # still accumulating
     model(xs[1]).sum().backward()
+    assert torch.equal(model.weight, w0)                               # nothing applied yet
+    try:
+        model(xs[1]).sum().backward()                                  # a third pass: error
+        out["third_pass_raises"] = False
+    except AssertionError as e:
+        out["third_pass_raises"] = "more than backward_passes_per_step" in str(e)
+        opt.zero_grad()                                                # redo the two passes
+        opt._delay = {k: 2 for k in opt._delay}
+        model(xs[0]).sum().backward()
+        model(xs[1]).sum().backward()
     opt.step()
     # gradient of sum(Wx+b) wrt W = Σ_rows x; accumulated over 2 passes, averaged over ranks
     per_rank = [3.0 * ((r + 1) + (r + 3)) for r in range(world)]
@@ -98,6 +108,7 @@ def _worker(rank, world):
 def test_horovod_surface_two_ranks():
     r0, r1 = run_distributed(_worker, 2)
     assert r0["accum_ok"] and r1["accum_ok"]
+    assert r0["third_pass_raises"] and r1["third_pass_raises"]
     # rank 1's fresh Adam now mirrors rank 0's: hyper-parameters, step, slots, weights
     assert r1["opt_lr"] == r0["opt_lr"] == 0.01 and r1["opt_step"] == r0["opt_step"] == 3.0
     assert torch.equal(r0["opt_exp_avg"], r1["opt_exp_avg"]) and torch.equal(r0["m2_w"], r1["m2_w"])

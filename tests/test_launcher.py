@@ -97,3 +97,45 @@ def test_run_cli_like_horovodrun(tmp_path):
     r = subprocess.run(base + ["-np", "3", "-H", "localhost:2", str(script)], env=env, cwd=ROOT,
                        capture_output=True, text=True)
     assert r.returncode != 0 and "not enough slots" in r.stderr
+
+
+def test_multi_host_launch_uses_routable_master_and_keeps_secrets_off_argv(monkeypatch):
+    """A worker started over ssh on another host must not be told MASTER_ADDR=127.0.0.1,
+    and the search authkey must not appear on any command line."""
+    import parallax_b200 as parallax
+    from parallax_b200 import consts, launcher
+    from parallax_b200.resource import parse_resource_info
+    ri = parse_resource_info("localhost:0\nfarawayhost:0,1\n")
+    seen = {"local": [], "remote": []}
+
+    class _P(object):
+        pid = 1
+
+        def poll(self):
+            return 0
+
+    def fake_popen(cmd, env=None, **kw):
+        seen["local"].append((cmd, env))
+        return _P()
+
+    def fake_remote(script, host, stdout=None, stderr=None, env=None, python_venv=None,
+                    port=22, secret_names=()):
+        seen["remote"].append((launcher.remote_command(script, host, env, python_venv, port,
+                                                       [k for k in secret_names if k in env]),
+                               env))
+        return _P()
+    monkeypatch.setattr(launcher.subprocess, "Popen", fake_popen)
+    monkeypatch.setattr(launcher, "remote_exec", fake_remote)
+    launcher.launch_workers("HYBRID", ri, parallax.Config(),
+                            extra_env={consts.PARALLAX_SEARCH_AUTHKEY: "s3cr3t",
+                                       consts.PARALLAX_SEARCH_ADDR: "x:1"})
+    assert len(seen["local"]) == 1 and len(seen["remote"]) == 2
+    addrs = {e["MASTER_ADDR"] for _, e in seen["local"]} | \
+        {e["MASTER_ADDR"] for _, e in seen["remote"]}
+    assert len(addrs) == 1 and not addrs.pop().startswith("127.")
+    for cmd, env in seen["remote"]:
+        assert "s3cr3t" not in " ".join(cmd) and "read -r PARALLAX_SEARCH_AUTHKEY" in cmd[-1]
+    # a purely local job keeps loopback
+    seen["local"].clear()
+    launcher.launch_workers("HYBRID", parse_resource_info("localhost:0,1\n"), parallax.Config())
+    assert {e["MASTER_ADDR"] for _, e in seen["local"]} == {"127.0.0.1"}
