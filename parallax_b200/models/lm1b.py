@@ -156,9 +156,9 @@ class LM1B(nn.Module):
         def work():
             sampled, tries = log_uniform_sample_unique(S, V, dev)
             ids = torch.cat([targets.to(torch.int64), sampled])
-            w_all, b_all = pnn.lookup_many([self.softmax_w, self.softmax_b], ids)
+            rows = pnn.lookup_many([self.softmax_w, self.softmax_b], ids, defer=True)
             logq = log_uniform_logq_unique(ids, tries, V)
-            return sampled, w_all, b_all.squeeze(-1), logq
+            return sampled, rows, logq
         if dev.type != "cuda":
             return work() + (None,)
         from ..ops import sinks
@@ -172,13 +172,17 @@ class LM1B(nn.Module):
     def sampled_softmax_loss(self, inputs, targets, pre=None):
         from ..ops.fused import sampled_softmax_loss
         N = targets.numel()
-        sampled, w_all, b_all, logq, side = pre if pre is not None \
+        sampled, rows, logq, side = pre if pre is not None \
             else self.prefetch_softmax(targets)
         if side is not None:
             cur = torch.cuda.current_stream(inputs.device)
             cur.wait_stream(side)
-            for t in (sampled, w_all, b_all, logq):
+            for t in [sampled, logq] + list(rows._rows):
                 t.record_stream(cur)
+        # the rows enter the autograd graph HERE (late), so their gradients are handed to
+        # the sparse group first thing in the backward pass, underneath the LSTM backward
+        w_all, b_all = rows.rows()
+        b_all = b_all.squeeze(-1)
         return sampled_softmax_loss(inputs, w_all[:N], w_all[N:], b_all[:N], b_all[N:],
                                     logq[:N], logq[N:], targets, sampled)
 

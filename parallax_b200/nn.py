@@ -115,10 +115,12 @@ def partition(module, partitioner):
     return module
 
 
-def lookup_many(modules, ids):
+def lookup_many(modules, ids, defer=False):
     """Rows of several embedding modules for the SAME ids (e.g. a softmax weight table
     and its bias table).  Declare the modules as a group on the model
     (``co_lookup_groups = [("softmax_w", "softmax_b")]``) and the NVLink fabric serves
-    them with one lookup kernel, one push kernel and one owner kernel per step."""
+    them with one lookup kernel, one push kernel and one owner kernel per step.
+    ``defer=True`` returns a handle whose ``.rows()`` yields the tensors: issue the lookup
+    early (e.g. on a side stream) and call ``.rows()`` where the rows are consumed."""
     from .parallel.engine import lookup_many as _lm
-    return _lm(list(modules), ids)
+    return _lm(list(modules), ids, defer=defer)

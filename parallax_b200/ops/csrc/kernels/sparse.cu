@@ -232,6 +232,37 @@ __device__ __forceinline__ void px_row_apply4(int kind, const PxHP& h, const flo
   }
 }
 
+// same for 8 consecutive elements (two float4 groups 2*c2, 2*c2+1): every load is issued
+// before the first store (table / slot pointers may alias as far as the compiler knows, so
+// two back-to-back px_row_apply4 calls would serialise load -> store -> load)
+template <int FAM>
+__device__ __forceinline__ void px_row_apply8(int kind, const PxHP& h, const float* g,
+                                              float* table, float* slot0, float* slot1,
+                                              float* slot2, __nv_bfloat16* shadow, size_t row,
+                                              int D4, int c2) {
+  const size_t off = row * D4 + 2 * c2;
+  float4* pw = reinterpret_cast<float4*>(table) + off;
+  float4* p0 = slot0 ? reinterpret_cast<float4*>(slot0) + off : nullptr;
+  float4* p1 = slot1 ? reinterpret_cast<float4*>(slot1) + off : nullptr;
+  float4* p2 = (FAM == 1 && slot2) ? reinterpret_cast<float4*>(slot2) + off : nullptr;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 w[2] = {pw[0], pw[1]}, s0[2] = {z, z}, s1[2] = {z, z}, s2[2] = {z, z};
+  if (p0) { s0[0] = p0[0]; s0[1] = p0[1]; }
+  if (p1) { s1[0] = p1[0]; s1[1] = p1[1]; }
+  if (p2) { s2[0] = p2[0]; s2[1] = p2[1]; }
+  px_rule4<FAM>(kind, h, make_float4(g[0], g[1], g[2], g[3]), w[0], s0[0], s1[0], s2[0]);
+  px_rule4<FAM>(kind, h, make_float4(g[4], g[5], g[6], g[7]), w[1], s0[1], s1[1], s2[1]);
+  pw[0] = w[0]; pw[1] = w[1];
+  if (p0) { p0[0] = s0[0]; p0[1] = s0[1]; }
+  if (p1) { p1[0] = s1[0]; p1[1] = s1[1]; }
+  if (p2) { p2[0] = s2[0]; p2[1] = s2[1]; }
+  if (shadow) {
+    const float f[8] = {w[0].x, w[0].y, w[0].z, w[0].w, w[1].x, w[1].y, w[1].z, w[1].w};
+    st_v4(reinterpret_cast<uint4*>(shadow) + row * ((D4 + 1) / 2) + c2,
+          Vec16<__nv_bfloat16>::pack(f));
+  }
+}
+
 struct PushTable {
   const void* grads;            // [n, D4*4] gradient rows (GradT)
   float* staging;               // [n/2+1, D4*4] fp32 rows for ids carried by several positions
@@ -286,6 +317,16 @@ __device__ __forceinline__ void emit_id(const PushArgs& a, const GroupGeom& g, i
   }
 }
 
+// 4 consecutive ids with one 16-byte load (tail: -1 = "no id")
+__device__ __forceinline__ int4 ld_ids4(const int32_t* __restrict__ ids, int i, int n) {
+  if (i + 3 < n) return __ldg(reinterpret_cast<const int4*>(ids + i));
+  int4 v = make_int4(-1, -1, -1, -1);
+  if (i < n) v.x = __ldg(ids + i);
+  if (i + 1 < n) v.y = __ldg(ids + i + 1);
+  if (i + 2 < n) v.z = __ldg(ids + i + 2);
+  return v;
+}
+
 // ONE launch: local aggregation + push + flag.
 // The id space is partitioned over the CTAs by a hash, so every CTA owns all positions of "its"
 // ids: it deduplicates them in a shared-memory hash table ("local aggregation dedups indices in
@@ -316,17 +357,29 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
   __syncthreads();
   // ---- pass 1: insert my ids, count positions per id
   if (dedup) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int id = pend_ids[i];
-      if (id < 0) continue;
-      if ((int)(((unsigned long long)hash_cta(id) * (unsigned)G) >> 32) != c_me) continue;
-      uint32_t h = hash_slot(id) & (H - 1);
-      int probes = 0;
-      while (true) {
-        const int old = atomicCAS(&keys[h], -1, id);
-        if (old == -1 || old == id) { atomicAdd(&cnt[h], 1); break; }
-        h = (h + 1) & (H - 1);
-        if (++probes >= H) { atomicAdd(&s_overflow, 1); break; }   // table full: raw entry later
+    // every CTA scans all ids: 16 ids per thread and trip, the four 16-byte loads issued
+    // back to back (a one-id-per-trip loop is bound by the L2 latency of each load)
+    for (int i0 = threadIdx.x * 4; i0 < n; i0 += blockDim.x * 16) {
+      int4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = ld_ids4(pend_ids, i0 + u * blockDim.x * 4, n);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int four[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const int id = four[w];
+          if (id < 0) continue;
+          if ((int)(((unsigned long long)hash_cta(id) * (unsigned)G) >> 32) != c_me) continue;
+          uint32_t h = hash_slot(id) & (H - 1);
+          int probes = 0;
+          while (true) {
+            const int old = atomicCAS(&keys[h], -1, id);
+            if (old == -1 || old == id) { atomicAdd(&cnt[h], 1); break; }
+            h = (h + 1) & (H - 1);
+            if (++probes >= H) { atomicAdd(&s_overflow, 1); break; }   // full: raw entry later
+          }
+        }
       }
     }
     __syncthreads();
@@ -385,12 +438,17 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
     __syncthreads();
   }
   // ---- pass 3: ship unique rows, stage duplicated ones (warp per position)
-  for (int i0 = wid * 32; i0 < n; i0 += nwarps * 32) {
-    const int i = i0 + lane;
-    int id = -1, h_found = -1;
-    bool mine = false, raw = false;
-    if (i < n) {
-      id = pend_ids[i];
+  int4 nxt = ld_ids4(pend_ids, wid * 128 + lane * 4, n);
+  for (int i0 = wid * 128; i0 < n; i0 += nwarps * 128) {
+    const int4 cur4 = nxt;
+    nxt = ld_ids4(pend_ids, i0 + nwarps * 128 + lane * 4, n);      // prefetch the next trip
+    const int four[4] = {cur4.x, cur4.y, cur4.z, cur4.w};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int i = i0 + lane * 4 + w;
+      const int id = four[w];
+      int h_found = -1;
+      bool mine = false, raw = false;
       if (id >= 0) {
         if (raw_all) { mine = (i % G) == c_me; raw = mine; }
         else if ((int)(((unsigned long long)hash_cta(id) * (unsigned)G) >> 32) == c_me) {
@@ -401,45 +459,72 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
           if (keys[h] == id) h_found = (int)h; else raw = true;
         }
       }
-    }
-    unsigned m = __ballot_sync(0xffffffffu, mine);
-    while (m) {
-      const int src_lane = __ffs(m) - 1;
-      m &= m - 1;
-      const int pi = i0 + src_lane;
-      const int pid = __shfl_sync(0xffffffffu, id, src_lane);
-      const int ph = __shfl_sync(0xffffffffu, h_found, src_lane);
-      const bool praw = __shfl_sync(0xffffffffu, (int)raw, src_lane) != 0;
-      int owner, local;
-      geom_map(g, pid, owner, local);
-      int k = 0, pcnt = 1;
-      if (praw) {
-        if (lane == 0) k = s_base_k[owner] + atomicAdd(&s_owner_cnt[owner], 1);
-        k = __shfl_sync(0xffffffffu, k, 0);
-      } else {
-        k = s_base_k[owner] + kk[ph];
-        pcnt = cnt[ph];
-      }
-      if (pcnt == 1) {
-        for (int t = 0; t < a.nt; ++t) {
-          const PushTable& T = a.t[t];
-          const float mul = ASYNC ? T.scale * T.hp[HP_GSCALE] : T.scale;
-          for (int c = lane; c < T.D4; c += 32) {
-            float4 v = ld_grad4<GradT>(reinterpret_cast<const GradT*>(T.grads),
-                                       (size_t)pi * T.D4 + c);
-            v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
-            emit_row<WireT, ASYNC, FAM>(a, g, t, owner, local, k, c, v);
-          }
+      unsigned m = __ballot_sync(0xffffffffu, mine);
+      while (m) {
+        const int src_lane = __ffs(m) - 1;
+        m &= m - 1;
+        const int pi = i0 + src_lane * 4 + w;
+        const int pid = __shfl_sync(0xffffffffu, id, src_lane);
+        const int ph = __shfl_sync(0xffffffffu, h_found, src_lane);
+        const bool praw = __shfl_sync(0xffffffffu, (int)raw, src_lane) != 0;
+        int owner, local;
+        geom_map(g, pid, owner, local);
+        int k = 0, pcnt = 1;
+        if (praw) {
+          if (lane == 0) k = s_base_k[owner] + atomicAdd(&s_owner_cnt[owner], 1);
+          k = __shfl_sync(0xffffffffu, k, 0);
+        } else {
+          k = s_base_k[owner] + kk[ph];
+          pcnt = cnt[ph];
         }
-        if (!ASYNC && lane == 0) emit_id(a, g, owner, local, k);
-      } else {
-        const int d = s_base_dup + dup[ph];
-        for (int t = 0; t < a.nt; ++t) {
-          const PushTable& T = a.t[t];
-          float4* dst = reinterpret_cast<float4*>(T.staging) + (size_t)d * T.D4;
-          for (int c = lane; c < T.D4; c += 32)
-            atomicAdd(dst + c, ld_grad4<GradT>(reinterpret_cast<const GradT*>(T.grads),
-                                               (size_t)pi * T.D4 + c));
+        if (pcnt == 1) {
+          for (int t = 0; t < a.nt; ++t) {
+            const PushTable& T = a.t[t];
+            const float mul = ASYNC ? T.scale * T.hp[HP_GSCALE] : T.scale;
+            if (!ASYNC && sizeof(GradT) == 2 && sizeof(WireT) == 2 && (T.D4 & 1) == 0 &&
+                !g.replicated) {
+              // bf16 gradient -> bf16 wire: 16-byte copies, two per lane in flight
+              const int nv = T.D4 / 2;
+              const uint4* src = reinterpret_cast<const uint4*>(T.grads) + (size_t)pi * nv;
+              uint4* dst = reinterpret_cast<uint4*>(
+                  T.rings[owner] + ((size_t)a.rank * a.cap + k) * ((size_t)T.D4 * 8));
+              for (int c = lane; c < nv; c += 64) {
+                const bool two = c + 32 < nv;
+                uint4 v0 = ld_v4_stream(src + c);
+                uint4 v1 = two ? ld_v4_stream(src + c + 32) : make_uint4(0, 0, 0, 0);
+                if (mul != 1.f) {
+                  float f[8];
+                  Vec16<__nv_bfloat16>::unpack(v0, f);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) f[q] *= mul;
+                  v0 = Vec16<__nv_bfloat16>::pack(f);
+                  Vec16<__nv_bfloat16>::unpack(v1, f);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) f[q] *= mul;
+                  v1 = Vec16<__nv_bfloat16>::pack(f);
+                }
+                st_v4_stream(dst + c, v0);
+                if (two) st_v4_stream(dst + c + 32, v1);
+              }
+              continue;
+            }
+            for (int c = lane; c < T.D4; c += 32) {
+              float4 v = ld_grad4<GradT>(reinterpret_cast<const GradT*>(T.grads),
+                                         (size_t)pi * T.D4 + c);
+              v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
+              emit_row<WireT, ASYNC, FAM>(a, g, t, owner, local, k, c, v);
+            }
+          }
+          if (!ASYNC && lane == 0) emit_id(a, g, owner, local, k);
+        } else {
+          const int d = s_base_dup + dup[ph];
+          for (int t = 0; t < a.nt; ++t) {
+            const PushTable& T = a.t[t];
+            float4* dst = reinterpret_cast<float4*>(T.staging) + (size_t)d * T.D4;
+            for (int c = lane; c < T.D4; c += 32)
+              atomicAdd(dst + c, ld_grad4<GradT>(reinterpret_cast<const GradT*>(T.grads),
+                                                 (size_t)pi * T.D4 + c));
+          }
         }
       }
     }
@@ -467,10 +552,14 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
       if (!ASYNC && lane == 0) emit_id(a, g, owner, local, k);
     }
   }
-  // ---- completion: last CTA publishes counts + `pushed` (sync) / bumps the step (async)
-  __threadfence_system();
+  // ---- completion: last CTA publishes counts + `pushed` (sync) / bumps the step (async).
+  // One fence per CTA: the barrier orders every thread's stores before thread 0's
+  // system-scope fence (cumulativity), which orders them before the ticket and the flag.
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&ctl->push_done, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(&ctl->push_done, 1u) == gridDim.x - 1);
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence_system();
@@ -571,6 +660,28 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
         const size_t row_bytes = (size_t)T.D4 * 4 * sizeof(WireT);
         const float gmul = T.avg * T.hp[HP_GSCALE];
         const PxHP hp = px_load_hp(T.hp);
+        if (sizeof(WireT) == 2 && (T.D4 & 1) == 0) {
+          // bf16 wire rows: one 16-byte load carries 8 elements = two float4 groups
+          for (int c2 = lane; c2 < T.D4 / 2; c2 += 32) {
+            float f[8];
+            Vec16<__nv_bfloat16>::unpack(
+                ld_v4_stream(reinterpret_cast<const uint4*>(T.ring + (size_t)e * row_bytes) + c2), f);
+            if (a.use_merge) {
+              for (int x = __ldcg(a.next + e); x != -1; x = __ldcg(a.next + x)) {
+                float o[8];
+                Vec16<__nv_bfloat16>::unpack(
+                    ld_v4_stream(reinterpret_cast<const uint4*>(T.ring + (size_t)x * row_bytes) + c2), o);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) f[q] += o[q];
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] *= gmul;
+            px_row_apply8<FAM>(T.kind, hp, f, T.table, T.slot0, T.slot1, T.slot2, T.shadow,
+                               (size_t)r, T.D4, c2);
+          }
+          continue;
+        }
         for (int cidx = lane; cidx < T.D4; cidx += 32) {
           float4 gv = ld_wire4<WireT>(T.ring + (size_t)e * row_bytes, cidx);
           if (a.use_merge) {
@@ -588,10 +699,12 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
       if (a.use_merge && lane == 0) a.slotmap[r] = -1;
     }
   }
-  // ---- completion: publish applied[me] = step to every rank
-  __threadfence_system();
+  // ---- completion: publish applied[me] = step to every rank (one fence per CTA, see push)
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&ctl->apply_done, 1u) == gridDim.x - 1);
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(&ctl->apply_done, 1u) == gridDim.x - 1);
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence_system();
@@ -774,7 +887,7 @@ int px_sparse_owner(const PxOwnerTable* tabs, int nt, int wire_dtype, const int3
   if (use_merge) {
     // one grid barrier inside: every CTA must be resident
     if (blocks > max_coop) blocks = max_coop;
-    if (blocks > 148 * 2) blocks = 148 * 2;
+    if (blocks > 148 * 4) blocks = 148 * 4;
     e = cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, 0, stream);
   } else {
     e = cudaLaunchKernel(fn, dim3(blocks), dim3(256), args, 0, stream);

@@ -90,6 +90,20 @@ def gate_interleave_perm(S, device):
     return _perm_cache[key]
 
 
+def _bwd_fused_w():
+    """Backward chain with the combined weight `Wc = W_P @ Wh` ([S, 4S]):
+    ``dm_{t-1} = dH_{t-1} W_P^T + dgates_t Wc^T`` — ONE product per time step on the
+    critical path instead of two (``dh = dH + dgates Wh^T`` then ``dm = dh W_P^T``); the
+    per-step `dh` values (needed only for dW_P) are produced afterwards by one batched GEMM
+    off the critical path.  "tc": tcgen05 split-K kernel, "cublas": torch.addmm, "0": off.
+    Measured on B200 at the LM1B shape (tools/bench_lstm_gemms.py): the combined product
+    (128 x 2048 x 8192, 32 MB of weights per step from L2) costs 13.5 us (cuBLAS) / 16.2 us
+    (tcgen05 split-K) against 2.8 + 11.7 us for the two it replaces — no gain (1.46 / 1.52
+    vs 1.43 ms per training step), so it stays OFF by default."""
+    import os
+    return os.environ.get("PARALLAX_LSTM_BWD_FUSEDW", "0")
+
+
 def _wgrad_chunks(T):
     """How many pieces the weight-gradient GEMMs are cut into along time so that the
     earlier pieces run on the side stream underneath the (latency-bound) recurrent
@@ -146,9 +160,11 @@ class _LSTMLayerFn(torch.autograd.Function):
                                           float(forget_bias), st), "lstm_gates_tc")
                 torch.mm(m_all[t], W_P, out=h_all[t + 1])
         else:
-            gpre = torch.empty(Bsz, 4 * S, dtype=dt, device=dev)
             for t in range(T):
-                torch.addmm(xw[t], h_all[t], Wh_l, out=gpre)
+                # accumulate straight into xw[t] (an `out=` different from the addend makes
+                # torch copy the 2 MB addend first — one more launch per step on the
+                # critical path)
+                gpre = xw[t].addmm_(h_all[t], Wh_l)
                 _check(L.px_lstm_cell_fwd(_p(gpre), _p(c_all[t]), _p(act[t]),
                                           _p(c_all[t + 1]), _p(m_all[t]), Bsz, S,
                                           float(forget_bias), _DT[dt], st), "lstm_cell_fwd")
@@ -157,6 +173,19 @@ class _LSTMLayerFn(torch.autograd.Function):
         ctx.save_for_backward(x, Wx_l, Wh_l, W_P, act, c_all, m_all, h_all)
         ctx.dims = (T, Bsz, E, S, P)
         ctx.tc = tc
+        ctx.Wc = None
+        if (_bwd_fused_w() != "0" and dt == torch.bfloat16 and T > 1 and
+                torch.is_grad_enabled() is False and any(ctx.needs_input_grad)):
+            # combined weight for the backward chain, computed underneath the forward chain
+            from . import sinks
+            cur = torch.cuda.current_stream(dev)
+            ws = sinks.side_stream(dev)
+            ws.wait_stream(cur)
+            with torch.cuda.stream(ws):
+                ctx.Wc = torch.mm(W_P.detach(), Wh_l.detach())          # [S, 4S]
+                ctx.Wc_ev = torch.cuda.Event()
+                ctx.Wc_ev.record(ws)
+            ctx.Wc.record_stream(cur)
         return h_all[1:], c_all[T].clone(), h_all[T].clone()
 
     @staticmethod
@@ -230,27 +259,72 @@ class _LSTMLayerFn(torch.autograd.Function):
                     dbias_o.add_(dg.sum(0))
                     dWP_o.addmm_(mT, dh2)
         pending_hi = T
+        Wc = ctx.Wc
+        mode = _bwd_fused_w()
         if dh_rec is None:
             dh_tot[T - 1].copy_(dH[T - 1])
         else:
             torch.add(dH[T - 1], dh_rec, out=dh_tot[T - 1])
-        for t in range(T - 1, -1, -1):
-            torch.mm(dh_tot[t], WPT, out=dm)
-            _check(L.px_lstm_cell_bwd(_p(dm), _p(dc), _p(act[t]), _p(c_all[t]),
-                                      _p(c_all[t + 1]), _p(dgates[t]), Bsz, S, _DT[dt],
-                                      1 if tc else 0, st), "lstm_cell_bwd")
-            if t > 0:
-                if use_tc:
-                    _gemm.gemm_tn(dgates[t], Wh, addend=dH[t - 1], splits=16, bn=64,
-                                  out=dh_tot[t - 1])
+        if Wc is not None:
+            cur.wait_event(ctx.Wc_ev)
+            fused_tc = (mode == "tc" and Bsz % 128 == 0 and S % 64 == 0 and (4 * S) % 512 == 0)
+            WcT = None if fused_tc else Wc.t()
+            WhT_v = Wh.t()
+            # DMH[t] = dH[t] W_P^T for every step at once (dh_tot[T-1] carries dhT)
+            DMH = torch.empty(T, Bsz, S, dtype=dt, device=dev)
+            torch.mm(dH[:T - 1].reshape(-1, P), WPT, out=DMH[:T - 1].view(-1, S))
+            torch.mm(dh_tot[T - 1], WPT, out=DMH[T - 1])
+
+            def dh_chunk(lo, hi):
+                """dh_tot[lo:hi] (off the critical path; steps whose dgates[t+1] is final)"""
+                top = min(hi, T - 1)
+                if top > lo:
+                    torch.addmm(dH[lo:top].reshape(-1, P),
+                                dgates[lo + 1:top + 1].view(-1, 4 * S), WhT_v,
+                                out=dh_tot[lo:top].view(-1, P))
+            dm_t = DMH[T - 1]
+            for t in range(T - 1, -1, -1):
+                _check(L.px_lstm_cell_bwd(_p(dm_t), _p(dc), _p(act[t]), _p(c_all[t]),
+                                          _p(c_all[t + 1]), _p(dgates[t]), Bsz, S, _DT[dt],
+                                          1 if tc else 0, st), "lstm_cell_bwd")
+                if t > 0:
+                    if fused_tc:
+                        _gemm.gemm_tn(dgates[t], Wc, addend=DMH[t - 1], splits=4, bn=64,
+                                      out=dm)
+                    else:
+                        torch.addmm(DMH[t - 1], dgates[t], WcT, out=dm)
+                    dm_t = dm
+                if t in bounds[1:-1]:
+                    ws.wait_stream(cur)
+                    with torch.cuda.stream(ws):
+                        dh_chunk(t, pending_hi)
+                    wgrad(t, pending_hi)
+                    pending_hi = t
+            dh_rec = _gemm.gemm_tn(dgates[0], Wh, splits=16, bn=64) if use_tc \
+                else torch.mm(dgates[0], WhT_v)
+            ws.wait_stream(cur)
+            with torch.cuda.stream(ws):
+                dh_chunk(0, pending_hi)
+            for t_ in (DMH, dH):
+                t_.record_stream(ws)
+        else:
+            for t in range(T - 1, -1, -1):
+                torch.mm(dh_tot[t], WPT, out=dm)
+                _check(L.px_lstm_cell_bwd(_p(dm), _p(dc), _p(act[t]), _p(c_all[t]),
+                                          _p(c_all[t + 1]), _p(dgates[t]), Bsz, S, _DT[dt],
+                                          1 if tc else 0, st), "lstm_cell_bwd")
+                if t > 0:
+                    if use_tc:
+                        _gemm.gemm_tn(dgates[t], Wh, addend=dH[t - 1], splits=16, bn=64,
+                                      out=dh_tot[t - 1])
+                    else:
+                        torch.addmm(dH[t - 1], dgates[t], WhT, out=dh_tot[t - 1])
                 else:
-                    torch.addmm(dH[t - 1], dgates[t], WhT, out=dh_tot[t - 1])
-            else:
-                dh_rec = _gemm.gemm_tn(dgates[0], Wh, splits=16, bn=64) if use_tc \
-                    else torch.mm(dgates[0], WhT)
-            if t in bounds[1:-1]:
-                wgrad(t, pending_hi)
-                pending_hi = t
+                    dh_rec = _gemm.gemm_tn(dgates[0], Wh, splits=16, bn=64) if use_tc \
+                        else torch.mm(dgates[0], WhT)
+                if t in bounds[1:-1]:
+                    wgrad(t, pending_hi)
+                    pending_hi = t
         _count(T)
         dg2 = dgates.view(T * Bsz, 4 * S)
         # dx first: the embedding gradient is what the rest of backward (and the sparse

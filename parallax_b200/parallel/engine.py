@@ -68,19 +68,59 @@ class _GroupLookupFn(torch.autograd.Function):
         return None, None, None
 
 
-def lookup_many(modules, ids):
+class _AttachFn(torch.autograd.Function):
+    """Gives the rows of an already-executed lookup their place in the autograd graph
+    *now*.  Autograd runs backward nodes in reverse creation order, so a lookup that was
+    prefetched at the top of the forward pass would hand its gradients over last; attaching
+    where the rows are consumed keeps the push of that group early in the backward pass
+    (underneath whatever was computed between the prefetch and the use)."""
+
+    @staticmethod
+    def forward(ctx, anchor, pending, *rows):
+        ctx.pending = pending
+        return tuple(r.view_as(r) for r in rows)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        p = ctx.pending
+        p.group.add_pending(p.token, list(grads))
+        return (None, None) + (None,) * len(grads)
+
+
+class PendingLookup(object):
+    """Result of `lookup_many(..., defer=True)`: the lookup kernel has been issued (on the
+    current stream); `rows()` returns the tensors and, when gradients are enabled, attaches
+    them to the autograd graph at that point."""
+
+    def __init__(self, rows, group=None, token=None, anchor=None):
+        self._rows, self.group, self.token, self._anchor = rows, group, token, anchor
+
+    def rows(self):
+        if self.group is None or self.token is None:
+            return self._rows
+        return list(_AttachFn.apply(self._anchor, self, *self._rows))
+
+
+def lookup_many(modules, ids, defer=False):
     """rows of several embedding modules for the SAME ids.  On the NVLink fabric, when
     the modules form a co-lookup group (`Model.co_lookup_groups`), this is one lookup
     kernel forward and one push / one owner kernel backward for all of them; anywhere
-    else it is the plain sequence of lookups."""
+    else it is the plain sequence of lookups.  `defer=True` returns a `PendingLookup`
+    (prefetch now, attach to autograd where the rows are used)."""
     tabs = [getattr(m, "table", None) for m in modules]
     grp = getattr(tabs[0], "group", None) if tabs[0] is not None else None
     if grp is not None and len(modules) > 1 and list(grp.tables) == tabs:
         if torch.is_grad_enabled():
+            if defer:
+                outs, token = grp.lookup(ids.reshape(-1))
+                outs = [o.reshape(*ids.shape, t.D) for o, t in zip(outs, grp.tables)]
+                return PendingLookup(outs, grp, token, modules[0]._anchor)
             return list(_GroupLookupFn.apply(modules[0]._anchor, ids, grp))
         outs, _ = grp.lookup(ids.reshape(-1), record=False)
-        return [o.reshape(*ids.shape, t.D) for o, t in zip(outs, grp.tables)]
-    return [m(ids) for m in modules]
+        outs = [o.reshape(*ids.shape, t.D) for o, t in zip(outs, grp.tables)]
+        return PendingLookup(outs) if defer else outs
+    outs = [m(ids) for m in modules]
+    return PendingLookup(outs) if defer else outs
 
 
 class ShardedEmbedding(tnn.Module):
@@ -342,9 +382,9 @@ class TrainEngine(object):
             self.timeline.instant("CYCLE_START", args="step %d" % step)
             self.timeline.begin("step", "STEP", "global_step %d" % step)
         self._begin_step(step)
-        # traced / tuned steps run eagerly (CUDA-event ranges and changing grid
-        # sizes cannot live inside a captured graph)
-        if self._use_graph() and not tl and not tuning:
+        # traced steps run eagerly (CUDA-event ranges cannot live inside a captured graph);
+        # the autotuner re-captures the graph for every candidate setting
+        if self._use_graph() and not tl:
             out = self._graph_step(feeds, step)
         else:
             out = self._step_body(feeds, step)

@@ -727,9 +727,11 @@ class NVSparseGroup(object):
         cs = stream if stream is not None else self.fabric.comm_stream
         n = max(self._last_n, 1)
         nt = len(self.tables)
-        # 8 warps per CTA, one row per warp; bounded by the configured cap
-        blocks = max(1, min(self.max_blocks, (n * (self.world if self.replicated else 1)
-                                              + 7) // 8))
+        # 8 warps per CTA, one row per warp: as many CTAs as fit on the device at once
+        # (4 per SM at 64 registers; the merge variant is a cooperative launch)
+        blocks = max(1, min(max(self.max_blocks, 148 * 4) if self.max_blocks >= 148
+                            else self.max_blocks,
+                            (n * (self.world if self.replicated else 1) + 7) // 8))
         use_merge = self.world > 1 or not self.local_aggregation
         descs = (ops.PxOwnerTable * nt)()
         for d, t in zip(descs, self.tables):

@@ -70,17 +70,33 @@ class BayesianTuner(object):
 
 
 class EngineAutotuner(object):
-    """Tunes `comm_blocks` (CTAs of the dense comm kernels) and `sparse_blocks`
-    (CTA cap of the sparse kernels) from per-step throughput."""
+    """Tunes the engine's communication knobs in the regime production runs in.
+
+    Horovod's parameter manager scores a setting by bytes/µs over a few cycles of the
+    running job (`horovod/common/parameter_manager.cc:155-181`) and tunes the fusion
+    threshold x cycle time jointly plus categorical switches (`:45-56`).  Here every
+    candidate setting is applied, the training step is RE-CAPTURED into a CUDA graph
+    (after the usual eager warm-up steps) and scored by the device time of `MEASURE`
+    graph replays — so the numbers the tuner sees are the numbers the job will run at.
+    Knobs: CTAs of the dense comm kernels, CTA cap of the sparse kernels (continuous,
+    GP/EI), then the schedule switches one by one (categorical): sparse push from inside
+    backward vs after it, last dense bucket held back behind the sparse push or not,
+    time-chunking of the weight-gradient GEMMs on the side stream.  Rank 0 decides; values
+    are broadcast so every rank applies the same setting at the same step."""
+    MEASURE = 8
 
     def __init__(self, engine):
         self.engine = engine
-        self.tuner = BayesianTuner({"comm_blocks": (4.0, 64.0),
-                                    "sparse_blocks": (32.0, 592.0)},
-                                   max_points=12) if engine.comm.rank == 0 else None
+        self.tuner = BayesianTuner(
+            {"comm_blocks": (4.0, 128.0), "sparse_blocks": (16.0, 296.0)},
+            categorical={"early_push": [True, False], "defer_last": [True, False],
+                         "wgrad_chunks": [2, 1, 4]},
+            samples_per_point=1, warmups=0, max_points=10) if engine.comm.rank == 0 else None
         self.log = os.environ.get(PARALLAX_AUTOTUNE_LOG)
-        self._t = None
         self.done = False
+        self.best = None
+        self._since = 0
+        self._ev = None
         self._apply(self._decide())
 
     @staticmethod
@@ -91,35 +107,61 @@ class EngineAutotuner(object):
         vals = None
         if self.tuner is not None:
             cur = self.tuner.current()
-            vals = (int(round(cur["comm_blocks"])), int(round(cur["sparse_blocks"])),
-                    self.tuner.done)
+            vals = dict(cur, comm_blocks=int(round(cur["comm_blocks"])),
+                        sparse_blocks=int(round(cur["sparse_blocks"])), done=self.tuner.done)
         return self.engine.comm.broadcast_object(vals, 0)
 
     def _apply(self, vals):
-        cb, sb, done = vals
         eng = self.engine
-        eng.fabric.max_blocks = max(1, min(128, cb))
+        eng.fabric.max_blocks = max(1, min(128, vals["comm_blocks"]))
         for grp in getattr(eng, "sparse_groups", ()):
-            grp.max_blocks = max(1, sb)
-        self.done = done
+            grp.max_blocks = max(1, vals["sparse_blocks"])
+            grp.early_push = bool(vals["early_push"])
+        if eng.dense is not None:
+            eng.dense.defer_last = bool(vals["defer_last"])
+        os.environ["PARALLAX_LSTM_WGRAD_CHUNKS"] = str(vals["wgrad_chunks"])
+        self.current = {k: v for k, v in vals.items() if k != "done"}
+        self.done = bool(vals["done"])
+        # the captured graph (if any) bakes the old grids / schedule in: capture again
+        eng._graph_state = None
+        self._warm = int(eng.config.sess_option("graph_warmup", 3)) if eng._use_graph_possible() \
+            else 1
+        eng._graph_not_before = eng.global_step + self._warm
+        self._since = 0
         if self.log and eng.comm.rank == 0:
             with open(self.log, "a") as f:
-                f.write("%d,%d,%d,%s\n" % (eng.global_step, cb, sb, done))
+                f.write("%d,%s\n" % (eng.global_step, ",".join(
+                    "%s=%s" % kv for kv in sorted(vals.items()))))
 
     def step_begin(self):
         import torch
-        torch.cuda.synchronize(self.engine.comm.device)
-        self._t = time.perf_counter()
+        # steps 0..warm-1: eager warm-up; step warm: capture (+ first replay); then MEASURE
+        # replays timed on the device
+        if not self.done and self._since == self._warm + 1:
+            self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self._ev[0].record()
 
     def step_end(self):
-        import torch
         if self.done:
             return
-        torch.cuda.synchronize(self.engine.comm.device)
-        dt = time.perf_counter() - self._t
-        changed = 0
+        self._since += 1
+        if self._since < self._warm + 1 + self.MEASURE:
+            return
+        self._ev[1].record()
+        self._ev[1].synchronize()
+        ms = self._ev[0].elapsed_time(self._ev[1]) / self.MEASURE
+        import torch
+        t = torch.tensor([ms], device=self.engine.comm.device)
+        if self.engine.comm.distributed:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.engine.comm.group)
+        ms = float(t.item())
+        if self.best is None or ms < self.best[0]:
+            self.best = (ms, dict(self.current))
         if self.tuner is not None:
-            changed = self.tuner.report(1.0 / max(dt, 1e-9))
-        changed = self.engine.comm.broadcast_object(changed, 0)
-        if changed:
-            self._apply(self._decide())
+            self.tuner.report(1.0 / max(ms, 1e-6))
+        vals = self._decide()
+        if vals["done"] and self.best is not None:
+            vals = dict(self.best[1], done=True)      # settle on the best setting seen
+            vals = self.engine.comm.broadcast_object(vals, 0)
+        self._apply(vals)

@@ -128,3 +128,37 @@ def test_engine_repartition_in_place_nvlink():
     losses = [sess.run(["loss", "train_op"], feed())[0][0] for _ in range(5)]
     assert np.isfinite(losses).all()
     sess.close()
+
+
+def test_autotuner_scores_candidates_under_graph_replay(monkeypatch, tmp_path):
+    """PARALLAX_AUTOTUNE=1: every candidate setting is applied, the step re-captured and
+    scored by device-timed graph replays; the job settles on the best setting and keeps
+    training correctly."""
+    log = tmp_path / "autotune.csv"
+    monkeypatch.setenv("PARALLAX_AUTOTUNE", "1")
+    monkeypatch.setenv("PARALLAX_AUTOTUNE_LOG", str(log))
+    model = MLPWithEmbedding(64, partitioner=parallax.get_partitioner(3))
+    graph = parallax.Graph(model, optimizer=optim.Adagrad(0.2, 1.0))
+    cfg = parallax.Config(run_option="HYBRID",
+                          sess_config={"fabric": "nvlink", "cuda_graph": True})
+    sess, *_ = parallax.parallel_run(graph, "localhost:0", sync=True, parallax_config=cfg)
+    tuner = sess.engine.autotuner
+    assert tuner is not None
+    g = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, 64, (8, 3), generator=g)
+    labels = torch.randint(0, 4, (8,), generator=g)
+    losses = []
+    for s in range(400):
+        loss, _ = sess.run(["loss", "train_op"], {"ids": [ids], "labels": [labels]})
+        losses.append(loss[0])
+        if tuner.done and s > 30:
+            break
+    assert tuner.done and tuner.best is not None and tuner.best[0] > 0
+    assert sess.engine.fabric.max_blocks == tuner.best[1]["comm_blocks"]
+    for _ in range(8):
+        loss, _ = sess.run(["loss", "train_op"], {"ids": [ids], "labels": [labels]})
+    assert getattr(sess.engine, "graph_captured", False)
+    assert loss[0] < losses[0]
+    lines = log.read_text().strip().splitlines()
+    assert len(lines) >= 5 and "comm_blocks=" in lines[0] and "early_push=" in lines[0]
+    sess.close()

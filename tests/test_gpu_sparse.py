@@ -252,6 +252,8 @@ def test_co_lookup_group_shares_one_push_and_owner_kernel(world):
                                auto_group=False)
             groups.append(NVSparseGroup([ta, tb]))
         for grp in groups:
+            grp._ensure_capacity(n)
+        for grp in groups:
             grp.warm(n)
         torch.cuda.synchronize()
         ref = [Wa.clone(), Wb.clone()]

@@ -16,6 +16,7 @@ ap.add_argument("--model", default="lm1b")
 ap.add_argument("--graph", action="store_true")
 ap.add_argument("--out", default="gpurun_out/profile_step.txt")
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--trace", default=None, help="also write a per-stream kernel timeline (text)")
 a = ap.parse_args()
 
 class A: pass
@@ -44,4 +45,22 @@ with open(a.out, "w") as f:
     f.write("model=%s graph=%s steps=%d\n" % (a.model, a.graph, a.steps))
     f.write(tab)
 print(tab[-6000:])
+if a.trace:
+    # one line per kernel of the LAST profiled step: start (us, relative), duration, stream, name
+    ks = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    ks.sort(key=lambda e: e.time_range.start)
+    t_end = ks[-1].time_range.end
+    per_step = (t_end - ks[0].time_range.start) / float(a.steps)
+    t0 = t_end - per_step * 1.02
+    with open(a.trace, "w") as f:
+        f.write("# start_us dur_us stream name   (last step of %d; step ~%.0f us)\n"
+                % (a.steps, per_step))
+        for e in ks:
+            if e.time_range.start < t0:
+                continue
+            stream = getattr(e, "stream", None)
+            if stream is None:
+                stream = getattr(e, "device_resource_id", -1)
+            f.write("%9.1f %8.1f %4s %s\n" % (e.time_range.start - t0, e.time_range.elapsed_us(),
+                                              stream, e.name[:90]))
 sess.close()
