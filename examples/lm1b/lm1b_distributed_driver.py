@@ -18,7 +18,7 @@ import torch
 import parallax_b200 as parallax
 from parallax_b200.models.lm1b import LM1B, lm1b_graph
 import parallax_config
-from data_utils import Vocabulary, Dataset
+from parallax_b200.models.lm1b_data import Vocabulary, Dataset
 
 ap = parallax_config.add_flags(argparse.ArgumentParser())
 ap.add_argument("--datadir", default=None)

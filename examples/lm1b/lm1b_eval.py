@@ -21,7 +21,7 @@ import torch
 import parallax_b200 as parallax
 from parallax_b200.checkpoint import latest_checkpoint
 from parallax_b200.models.lm1b import LM1B, lm1b_graph
-from data_utils import Vocabulary, Dataset
+from parallax_b200.models.lm1b_data import Vocabulary, Dataset
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--ckpt_dir", required=True)

@@ -317,16 +317,6 @@ __device__ __forceinline__ void emit_id(const PushArgs& a, const GroupGeom& g, i
   }
 }
 
-// 4 consecutive ids with one 16-byte load (tail: -1 = "no id")
-__device__ __forceinline__ int4 ld_ids4(const int32_t* __restrict__ ids, int i, int n) {
-  if (i + 3 < n) return __ldg(reinterpret_cast<const int4*>(ids + i));
-  int4 v = make_int4(-1, -1, -1, -1);
-  if (i < n) v.x = __ldg(ids + i);
-  if (i + 1 < n) v.y = __ldg(ids + i + 1);
-  if (i + 2 < n) v.z = __ldg(ids + i + 2);
-  return v;
-}
-
 // ONE launch: local aggregation + push + flag.
 // The id space is partitioned over the CTAs by a hash, so every CTA owns all positions of "its"
 // ids: it deduplicates them in a shared-memory hash table ("local aggregation dedups indices in
@@ -334,7 +324,34 @@ __device__ __forceinline__ int4 ld_ids4(const int32_t* __restrict__ ids, int i, 
 // whose id is unique in the batch straight from the gradient buffer, sums rows sharing an id with
 // vector atomics into a local fp32 staging row (O(1) depth for Zipfian batches) and flushes those
 // once.  No grid-wide phase is needed; the last CTA publishes the counts and the `pushed` flag.
-// SMEM layout: keys[H] | cnt[H] | kk[H] (k inside the owner bucket; bit 31 clear) | dup[H]
+// Every CTA scans all ids twice; the scans read them from a shared-memory staging chunk filled
+// with 16-byte loads issued back to back (a one-id-per-trip global loop is bound by L2 latency,
+// and unrolling it instead makes the kernel instruction-fetch bound).
+// SMEM layout: keys[H] | cnt[H] | kk[H] (k inside the owner bucket) | dup[H] | ids[PX_ID_CHUNK]
+#define PX_ID_CHUNK 4096
+
+// stage ids[base, base+m) into shared memory: 16 ids (4 x int4) per thread in flight
+__device__ __forceinline__ void stage_ids(const int32_t* __restrict__ ids, int base, int m,
+                                          int32_t* ids_s) {
+  int4 q[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = (u * blockDim.x + threadIdx.x) * 4;
+    q[u] = make_int4(-1, -1, -1, -1);
+    if (j + 3 < m) q[u] = __ldg(reinterpret_cast<const int4*>(ids + base + j));
+    else {
+      if (j < m) q[u].x = __ldg(ids + base + j);
+      if (j + 1 < m) q[u].y = __ldg(ids + base + j + 1);
+      if (j + 2 < m) q[u].z = __ldg(ids + base + j + 2);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = (u * blockDim.x + threadIdx.x) * 4;
+    if (j < PX_ID_CHUNK) *reinterpret_cast<int4*>(ids_s + j) = q[u];
+  }
+}
+
 template <typename GradT, typename WireT, bool ASYNC, int FAM>
 __global__ void __launch_bounds__(256)
 px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, GroupGeom g,
@@ -345,44 +362,48 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
   int32_t* cnt = smem + H;
   int32_t* kk = smem + 2 * H;
   int32_t* dup = smem + 3 * H;
+  int32_t* ids_s = smem + 4 * H;
   __shared__ int s_owner_cnt[PX_MAX_RANKS], s_base_k[PX_MAX_RANKS];
   __shared__ int s_ndup, s_base_dup, s_overflow;
   __shared__ bool s_last;
   const int G = gridDim.x, c_me = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const bool raw_all = !dedup;
   if (c_me == 0 && threadIdx.x == 0) ctl->t_push[0] = px_globaltimer();
   for (int h = threadIdx.x; h < H; h += blockDim.x) { keys[h] = -1; cnt[h] = 0; }
   if (threadIdx.x < PX_MAX_RANKS) s_owner_cnt[threadIdx.x] = 0;
   if (threadIdx.x == 0) { s_ndup = 0; s_overflow = 0; }
   __syncthreads();
-  // ---- pass 1: insert my ids, count positions per id
-  if (dedup) {
-    // every CTA scans all ids: 16 ids per thread and trip, the four 16-byte loads issued
-    // back to back (a one-id-per-trip loop is bound by the L2 latency of each load)
-    for (int i0 = threadIdx.x * 4; i0 < n; i0 += blockDim.x * 16) {
-      int4 q[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) q[u] = ld_ids4(pend_ids, i0 + u * blockDim.x * 4, n);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int four[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const int id = four[w];
-          if (id < 0) continue;
-          if ((int)(((unsigned long long)hash_cta(id) * (unsigned)G) >> 32) != c_me) continue;
-          uint32_t h = hash_slot(id) & (H - 1);
-          int probes = 0;
-          while (true) {
-            const int old = atomicCAS(&keys[h], -1, id);
-            if (old == -1 || old == id) { atomicAdd(&cnt[h], 1); break; }
-            h = (h + 1) & (H - 1);
-            if (++probes >= H) { atomicAdd(&s_overflow, 1); break; }   // full: raw entry later
-          }
+  // ---- pass 1: insert my ids, count positions per id (raw mode: count my positions per owner)
+  for (int base = 0; base < n; base += PX_ID_CHUNK) {
+    const int m = min(PX_ID_CHUNK, n - base);
+    stage_ids(pend_ids, base, m, ids_s);
+    __syncthreads();
+#pragma unroll 1
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+      const int id = ids_s[j];
+      if (id < 0) continue;
+      if (raw_all) {
+        if ((base + j) % G == c_me) {
+          int owner, local;
+          geom_map(g, id, owner, local);
+          atomicAdd(&s_owner_cnt[owner], 1);
         }
+        continue;
+      }
+      if ((int)(((unsigned long long)hash_cta(id) * (unsigned)G) >> 32) != c_me) continue;
+      uint32_t h = hash_slot(id) & (H - 1);
+      int probes = 0;
+      while (true) {
+        const int old = atomicCAS(&keys[h], -1, id);
+        if (old == -1 || old == id) { atomicAdd(&cnt[h], 1); break; }
+        h = (h + 1) & (H - 1);
+        if (++probes >= H) { atomicAdd(&s_overflow, 1); break; }   // table full: raw entry later
       }
     }
     __syncthreads();
+  }
+  if (dedup) {
     // ---- pass 2: one ring slot per unique id, one staging row per duplicated id
     for (int h = threadIdx.x; h < H; h += blockDim.x) {
       const int id = keys[h];
@@ -393,29 +414,24 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
       dup[h] = cnt[h] > 1 ? atomicAdd(&s_ndup, 1) : -1;
     }
     __syncthreads();
-  }
-  // raw (un-deduplicated) entries: local_aggregation off → every position i % G == c_me;
-  // or the (statistically never hit) SMEM overflow
-  const bool raw_all = !dedup;
-  if (raw_all || s_overflow > 0) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int id = pend_ids[i];
-      if (id < 0) continue;
-      bool raw = false;
-      if (raw_all) raw = (i % G) == c_me;
-      else if ((int)(((unsigned long long)hash_cta(id) * (unsigned)G) >> 32) == c_me) {
+    if (s_overflow > 0) {
+      // the (statistically never hit) SMEM overflow: positions whose id did not fit travel
+      // as raw entries after the deduplicated ones; count them per owner
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int id = pend_ids[i];
+        if (id < 0) continue;
+        if ((int)(((unsigned long long)hash_cta(id) * (unsigned)G) >> 32) != c_me) continue;
         uint32_t h = hash_slot(id) & (H - 1);
         int probes = 0;
         while (keys[h] != id && keys[h] != -1 && ++probes <= H) h = (h + 1) & (H - 1);
-        raw = keys[h] != id;
+        if (keys[h] != id) {
+          int owner, local;
+          geom_map(g, id, owner, local);
+          atomicAdd(&s_owner_cnt[owner], 1);
+        }
       }
-      if (raw) {
-        int owner, local;
-        geom_map(g, id, owner, local);
-        atomicAdd(&s_owner_cnt[owner], 1);
-      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   if (threadIdx.x < PX_MAX_RANKS) {
     const int m = s_owner_cnt[threadIdx.x];
@@ -438,19 +454,18 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
     __syncthreads();
   }
   // ---- pass 3: ship unique rows, stage duplicated ones (warp per position)
-  int4 nxt = ld_ids4(pend_ids, wid * 128 + lane * 4, n);
-  for (int i0 = wid * 128; i0 < n; i0 += nwarps * 128) {
-    const int4 cur4 = nxt;
-    nxt = ld_ids4(pend_ids, i0 + nwarps * 128 + lane * 4, n);      // prefetch the next trip
-    const int four[4] = {cur4.x, cur4.y, cur4.z, cur4.w};
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const int i = i0 + lane * 4 + w;
-      const int id = four[w];
+  for (int base = 0; base < n; base += PX_ID_CHUNK) {
+    const int m = min(PX_ID_CHUNK, n - base);
+    stage_ids(pend_ids, base, m, ids_s);
+    __syncthreads();
+#pragma unroll 1
+    for (int j0 = wid * 32; j0 < m; j0 += nwarps * 32) {
+      const int j = j0 + lane;
+      const int id = j < m ? ids_s[j] : -1;
       int h_found = -1;
       bool mine = false, raw = false;
       if (id >= 0) {
-        if (raw_all) { mine = (i % G) == c_me; raw = mine; }
+        if (raw_all) { mine = (base + j) % G == c_me; raw = mine; }
         else if ((int)(((unsigned long long)hash_cta(id) * (unsigned)G) >> 32) == c_me) {
           mine = true;
           uint32_t h = hash_slot(id) & (H - 1);
@@ -459,11 +474,12 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
           if (keys[h] == id) h_found = (int)h; else raw = true;
         }
       }
-      unsigned m = __ballot_sync(0xffffffffu, mine);
-      while (m) {
-        const int src_lane = __ffs(m) - 1;
-        m &= m - 1;
-        const int pi = i0 + src_lane * 4 + w;
+      unsigned mask = __ballot_sync(0xffffffffu, mine);
+#pragma unroll 1
+      while (mask) {
+        const int src_lane = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int pi = base + j0 + src_lane;
         const int pid = __shfl_sync(0xffffffffu, id, src_lane);
         const int ph = __shfl_sync(0xffffffffu, h_found, src_lane);
         const bool praw = __shfl_sync(0xffffffffu, (int)raw, src_lane) != 0;
@@ -478,6 +494,7 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
           pcnt = cnt[ph];
         }
         if (pcnt == 1) {
+#pragma unroll 1
           for (int t = 0; t < a.nt; ++t) {
             const PushTable& T = a.t[t];
             const float mul = ASYNC ? T.scale * T.hp[HP_GSCALE] : T.scale;
@@ -488,6 +505,7 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
               const uint4* src = reinterpret_cast<const uint4*>(T.grads) + (size_t)pi * nv;
               uint4* dst = reinterpret_cast<uint4*>(
                   T.rings[owner] + ((size_t)a.rank * a.cap + k) * ((size_t)T.D4 * 8));
+#pragma unroll 1
               for (int c = lane; c < nv; c += 64) {
                 const bool two = c + 32 < nv;
                 uint4 v0 = ld_v4_stream(src + c);
@@ -508,6 +526,7 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
               }
               continue;
             }
+#pragma unroll 1
             for (int c = lane; c < T.D4; c += 32) {
               float4 v = ld_grad4<GradT>(reinterpret_cast<const GradT*>(T.grads),
                                          (size_t)pi * T.D4 + c);
@@ -518,6 +537,7 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
           if (!ASYNC && lane == 0) emit_id(a, g, owner, local, k);
         } else {
           const int d = s_base_dup + dup[ph];
+#pragma unroll 1
           for (int t = 0; t < a.nt; ++t) {
             const PushTable& T = a.t[t];
             float4* dst = reinterpret_cast<float4*>(T.staging) + (size_t)d * T.D4;
@@ -528,8 +548,9 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
         }
       }
     }
+    __syncthreads();
   }
-  __syncthreads();        // every position of my duplicated ids is staged (they are all mine)
+  // every position of my duplicated ids is staged now (they are all mine)
   // ---- pass 4: flush duplicated ids (warp per id), re-zero the staging rows
   if (dedup && s_ndup > 0) {
     for (int h = wid; h < H; h += nwarps) {
@@ -538,6 +559,7 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
       geom_map(g, keys[h], owner, local);
       const int k = s_base_k[owner] + kk[h];
       const int d = s_base_dup + dup[h];
+#pragma unroll 1
       for (int t = 0; t < a.nt; ++t) {
         const PushTable& T = a.t[t];
         const float mul = ASYNC ? T.scale * T.hp[HP_GSCALE] : T.scale;
@@ -650,6 +672,29 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
     for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < c; j += gridDim.x * warps) {
       const int e = s * a.cap + j;
       const int r = a.ring_ids[e];
+      {
+        // the rows of a batch are scattered over a multi-GB table: every touch is a DRAM
+        // (and usually a TLB) miss.  Prefetch this warp's NEXT entry's table / slot rows into
+        // L2 now, so that miss overlaps the work on the current entry.
+        const int jn = j + gridDim.x * warps;
+        if (jn < c) {
+          const int rn = a.ring_ids[s * a.cap + jn];
+          if (rn >= 0) {
+            for (int t = 0; t < a.nt; ++t) {
+              const OwnerTable& T = a.t[t];
+              const size_t off = (size_t)rn * T.D4 * 16;             // row offset in bytes
+              const int lines = (T.D4 * 16 + 127) / 128;
+              for (int l = lane; l < lines; l += 32) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(T.table) + off + l * 128));
+                if (T.slot0)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(T.slot0) + off + l * 128));
+                if (T.slot1)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(T.slot1) + off + l * 128));
+              }
+            }
+          }
+        }
+      }
       if (r < 0) continue;
       if (a.use_merge) {
         if (__ldcg(a.slotmap + r) != e) continue;          // not the list head
@@ -726,7 +771,8 @@ static void launch_push(int blocks, size_t smem, cudaStream_t stream, const int3
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(px_sparse_push_kernel<GT, WT, AS, FAM>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 4 * 8192);
+                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         4 * 4 * 8192 + PX_ID_CHUNK * 4);
     attr = true;
   }
   px_sparse_push_kernel<GT, WT, AS, FAM><<<blocks, 256, smem, stream>>>(pend_ids, n, a, G, ctl,
@@ -829,7 +875,7 @@ int px_sparse_push(const int32_t* pend_ids, int n, const PxPushTable* tabs, int 
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   const int hbits = push_hbits(n, blocks);
-  const size_t smem = (size_t)4 * sizeof(int32_t) << hbits;
+  const size_t smem = ((size_t)4 * sizeof(int32_t) << hbits) + PX_ID_CHUNK * sizeof(int32_t);
   SparseCtl* C = (SparseCtl*)ctl;
 #define PUSH(GT, WT, AS, FAM) launch_push<GT, WT, AS, FAM>(blocks, smem, stream, pend_ids, n, a, G, C, hbits, dedup)
   if (async) {

@@ -38,6 +38,10 @@ struct Watchdog {
   std::atomic<int> stalls{0};
   bool warned = false;
   int exit_code = 17;
+  // stall-path resources are created up front: cudaMallocHost / cudaFreeHost synchronise the
+  // device, which never completes while a kernel is spinning on a dead peer's flag
+  cudaStream_t rd_stream = nullptr;
+  uint32_t* rd_host = nullptr;
 };
 Watchdog W;
 
@@ -47,11 +51,9 @@ long long now_us() {
 }
 
 void report_missing() {
-  if (!W.pad_dev || W.pad_words == 0) return;
-  cudaStream_t s;
-  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return; }
-  uint32_t* host = nullptr;
-  if (cudaMallocHost(&host, W.pad_words * 4) != cudaSuccess) { cudaStreamDestroy(s); cudaGetLastError(); return; }
+  if (!W.pad_dev || W.pad_words == 0 || !W.rd_stream || !W.rd_host) return;
+  cudaStream_t s = W.rd_stream;
+  uint32_t* host = W.rd_host;
   if (cudaMemcpyAsync(host, W.pad_dev, W.pad_words * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
       cudaStreamSynchronize(s) == cudaSuccess) {
     // layout [channel][block][src]: for block 0 of every channel report lagging peers
@@ -70,8 +72,6 @@ void report_missing() {
     }
   }
   cudaGetLastError();
-  cudaFreeHost(host);
-  cudaStreamDestroy(s);
 }
 
 void loop() {
@@ -119,6 +119,11 @@ int px_watchdog_start(int rank, int world, double warn_s, double shutdown_s, con
   W.rank = rank; W.world = world; W.warn_s = warn_s; W.shutdown_s = shutdown_s;
   W.pad_dev = (const uint32_t*)pad_dev; W.pad_words = pad_words;
   W.last_beat_us = now_us(); W.warned = false; W.stalls = 0; W.armed = false;
+  if (W.pad_dev && pad_words > 0 && !W.rd_host) {
+    if (cudaStreamCreateWithFlags(&W.rd_stream, cudaStreamNonBlocking) != cudaSuccess) W.rd_stream = nullptr;
+    if (cudaMallocHost(&W.rd_host, pad_words * 4) != cudaSuccess) W.rd_host = nullptr;
+    cudaGetLastError();
+  }
   W.on.store(true, std::memory_order_release);
   W.th = std::thread(loop);
   return 0;

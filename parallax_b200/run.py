@@ -57,7 +57,10 @@ def main(argv=None):
     hosts = parse_hosts(a.hosts, a.num_proc)
     if sum(s for _, s in hosts) < a.num_proc:
         ap.error("not enough slots for -np %d" % a.num_proc)
-    master = "127.0.0.1" if is_local_host(hosts[0][0]) else hosts[0][0]
+    # loopback only when every rank runs here; ranks on other hosts need a reachable address
+    from .resource import routable_address
+    everything_local = all(is_local_host(h) for h, _ in hosts)
+    master = "127.0.0.1" if everything_local else routable_address(hosts[0][0])
     port = a.master_port or get_empty_port(1)[0]
     cmd = a.command if a.command[0] != "--" else a.command[1:]
     if cmd[0].endswith(".py"):
