@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the secondary blocks (same-engine NCCL arm, fp32 LM1B, "
                          "ResNet-50, sustained run, self-check)")
+    ap.add_argument("--comm", action="store_true",
+                    help="with --no-extras: still report the graph-replayed comm probes")
     ap.add_argument("--sustained-s", type=float, default=3.0,
                     help="length of the additional sustained-clock run (seconds)")
     return ap.parse_args()
@@ -413,7 +415,8 @@ def main():
             return 1
 
     main_blk = measure(args, args.model, args.dtype, K, Wm, world, rank,
-                       protocol=args.protocol, e2e=not args.no_e2e, comm_stamps=extras,
+                       protocol=args.protocol, e2e=not args.no_e2e,
+                       comm_stamps=extras or args.comm,
                        sustained_s=args.sustained_s if extras else 0.0, sampler=sampler)
     clocks = sampler.window(*main_blk["_window"]) if rank == 0 else None
     blocks = {}

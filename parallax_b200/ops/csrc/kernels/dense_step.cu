@@ -77,12 +77,40 @@ __device__ __forceinline__ void st_f32(float* p, const float* f) {
                                 __float_as_uint(f[4 * i + 2]), __float_as_uint(f[4 * i + 3])));
 }
 
+// Rank-level (not CTA-paired) synchronisation, so the grid is not limited to the
+// PX_MAX_BLOCKS barrier slots of `px_block_barrier` and the optimizer phase can use the whole
+// GPU's HBM bandwidth:
+//  * start: CTA 0 announces "this rank reached the kernel" (all earlier work on the stream —
+//    the gradients — is complete) in slot 0 of `ch_start`; EVERY CTA waits until every peer has.
+//  * end: the last CTA to finish (ticket) fences, announces "all my parameter stores are out"
+//    in slot 0 of `ch_end` and waits for the same from every peer; the kernel — and with it the
+//    stream — completes only then.  Slot 1 of `ch_end` holds the ticket counter.
+__device__ __forceinline__ void px_rank_signal(uint32_t* const* pads, int slot, int rank, int world,
+                                               uint32_t e) {
+  if (threadIdx.x < world)
+    st_release_sys(pads[threadIdx.x] + (size_t)slot * PX_MAX_RANKS + rank, e);
+}
+__device__ __forceinline__ void px_rank_wait(uint32_t* const* pads, int slot, int rank, int world,
+                                             uint32_t e) {
+  if (threadIdx.x < world) {
+    const uint32_t* mine = pads[rank] + (size_t)slot * PX_MAX_RANKS + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(mine) - e) < 0) { }
+  }
+  __syncthreads();
+}
+
 template <typename T, int W, int FAM>
 __global__ void __launch_bounds__(512)
 px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr) {
   constexpr int VN = Vec16<T>::N;
   const int mode = a.mode, kind = a.kind;
-  if (W > 1 && mode != 2) px_block_barrier(pads, epoch_ctr, a.ch_start, a.rank, W);
+  const int slot_s = a.ch_start * PX_MAX_BLOCKS, slot_e = a.ch_end * PX_MAX_BLOCKS;
+  uint32_t e_start = 0;
+  if (W > 1 && mode != 2) {
+    e_start = ld_volatile_u32(epoch_ctr + slot_s) + 1;
+    if (blockIdx.x == 0) px_rank_signal(pads, slot_s, a.rank, W, e_start);
+    px_rank_wait(pads, slot_s, a.rank, W, e_start);
+  }
   const size_t slice = a.n / W;
   const size_t nvec = slice / VN;
   const size_t base = (size_t)a.rank * slice;
@@ -154,7 +182,27 @@ px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr
     }
   }
   if (mode == 1 && a.sumsq != nullptr) block_atomic_sum(ss, a.sumsq);
-  if (W > 1 && mode != 1) px_block_barrier(pads, epoch_ctr, a.ch_end, a.rank, W);
+  if (W > 1) {
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();          // one fence per CTA (cumulative over the barrier)
+      s_last = atomicAdd(epoch_ctr + slot_e + 1, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+      if (mode != 1) {
+        const uint32_t e_end = ld_volatile_u32(epoch_ctr + slot_e) + 1;
+        px_rank_signal(pads, slot_e, a.rank, W, e_end);
+        px_rank_wait(pads, slot_e, a.rank, W, e_end);
+        if (threadIdx.x == 0) epoch_ctr[slot_e] = e_end;
+      }
+      if (threadIdx.x == 0) {
+        if (mode != 2) epoch_ctr[slot_s] = e_start;
+        epoch_ctr[slot_e + 1] = 0;
+      }
+    }
+  }
 }
 
 // device timestamp (ns) — a graph-capturable probe for "exposed communication" measurements
@@ -268,11 +316,10 @@ int px_dense_step(const void* const* grads, const void* const* params, float* ma
   a.hp = hp; a.clip = clip; a.sumsq = sumsq; a.n = n; a.avg = avg; a.ema_decay = ema_decay;
   a.rank = rank; a.ch_start = ch_start; a.ch_end = ch_end; a.kind = kind; a.mode = mode;
   const int threads = 512;
-  int blocks = px_clamp_blocks(n / world / vn, threads, world == 1 ? 0x7fffffff : max_blocks);
-  if (world == 1) {
-    size_t b = (n / vn + threads - 1) / threads;
-    blocks = (int)(b < 1 ? 1 : (b > 148 * 4 ? 148 * 4 : b));
-  }
+  // rank-level barriers: the grid is sized for HBM bandwidth, not by barrier slots
+  size_t b = (n / world / vn + threads - 1) / threads;
+  const size_t cap = world == 1 ? 148 * 4 : (size_t)(max_blocks > 0 ? max_blocks : 148 * 2);
+  int blocks = (int)(b < 1 ? 1 : (b > cap ? cap : b));
 #define LAUNCH(T, W)                                                                       \
   do {                                                                                     \
     if (PX_KIND_FAMILY(kind) == 0)                                                         \

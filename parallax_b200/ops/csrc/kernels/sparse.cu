@@ -58,6 +58,7 @@ struct SparseCtl {
   int32_t owner_cnt[PX_MAX_RANKS];
   unsigned long long t_push[2]; // %globaltimer at push start / flag publication
   unsigned long long t_own[3];  // owner kernel: start / all sources arrived / applied published
+  unsigned long long t_dbg[8];  // push kernel, CTA 0: end of each internal phase (profiling aid)
 };
 
 // group header (symmetric): [pushed[R] | applied[R] | cnt[R]]
@@ -69,15 +70,21 @@ __device__ __forceinline__ unsigned long long px_globaltimer() {
   return t;
 }
 
-__device__ __forceinline__ void geom_map(const GroupGeom& g, int id, int& owner, int& local) {
-  if (g.replicated) { owner = 0; local = id; return; }
-  int p, idx;
+#define PX_SMEM_PARTS 1024
+
+__device__ __forceinline__ void geom_part(const GroupGeom& g, int id, int& p, int& idx) {
   if (g.strategy == 0) { p = id % g.P; idx = id / g.P; }
   else {
     const int thr = g.extras * (g.base + 1);
     if (id < thr) { p = id / (g.base + 1); idx = id - p * (g.base + 1); }
     else { p = (id - g.extras) / max(g.base, 1); idx = id - (p * g.base + g.extras); }
   }
+}
+
+__device__ __forceinline__ void geom_map(const GroupGeom& g, int id, int& owner, int& local) {
+  if (g.replicated) { owner = 0; local = id; return; }
+  int p, idx;
+  geom_part(g, id, p, idx);
   owner = __ldg(g.part_owner + p);
   local = __ldg(g.part_slot + p) * g.rows_per_part + idx;
 }
@@ -328,6 +335,7 @@ __device__ __forceinline__ void emit_id(const PushArgs& a, const GroupGeom& g, i
 // with 16-byte loads issued back to back (a one-id-per-trip global loop is bound by L2 latency,
 // and unrolling it instead makes the kernel instruction-fetch bound).
 // SMEM layout: keys[H] | cnt[H] | kk[H] (k inside the owner bucket) | dup[H] | ids[PX_ID_CHUNK]
+//              | work[PX_ID_CHUNK] (positions of the current chunk that belong to this CTA)
 #define PX_ID_CHUNK 4096
 
 // stage ids[base, base+m) into shared memory: 16 ids (4 x int4) per thread in flight
@@ -366,9 +374,33 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
   __shared__ int s_owner_cnt[PX_MAX_RANKS], s_base_k[PX_MAX_RANKS];
   __shared__ int s_ndup, s_base_dup, s_overflow;
   __shared__ bool s_last;
+  // placement maps and ring bases are read for every row: keep them in shared memory (a
+  // global load each would put two more memory latencies on every row's critical path)
+  __shared__ short s_part_owner[PX_SMEM_PARTS], s_part_slot[PX_SMEM_PARTS];
+  __shared__ char* s_ring[PX_GRP_MAX][PX_MAX_RANKS];
+  const bool parts_in_smem = !g.replicated && g.P <= PX_SMEM_PARTS;
+  if (parts_in_smem)
+    for (int p = threadIdx.x; p < g.P; p += blockDim.x) {
+      s_part_owner[p] = (short)__ldg(g.part_owner + p);
+      s_part_slot[p] = (short)__ldg(g.part_slot + p);
+    }
+  if (!ASYNC && threadIdx.x < a.nt * PX_MAX_RANKS) {
+    const int t = threadIdx.x / PX_MAX_RANKS, r = threadIdx.x % PX_MAX_RANKS;
+    s_ring[t][r] = r < g.W ? a.t[t].rings[r] : nullptr;
+  }
+#define GEOM_MAP(id, owner, local)                                                     \
+  do {                                                                                 \
+    if (parts_in_smem) {                                                               \
+      int p_, idx_;                                                                    \
+      geom_part(g, (id), p_, idx_);                                                    \
+      owner = s_part_owner[p_];                                                        \
+      local = s_part_slot[p_] * g.rows_per_part + idx_;                                \
+    } else geom_map(g, (id), owner, local);                                            \
+  } while (0)
   const int G = gridDim.x, c_me = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const bool raw_all = !dedup;
+#define PX_DBG(i) do { if (c_me == 0 && threadIdx.x == 0) ctl->t_dbg[i] = px_globaltimer(); } while (0)
   if (c_me == 0 && threadIdx.x == 0) ctl->t_push[0] = px_globaltimer();
   for (int h = threadIdx.x; h < H; h += blockDim.x) { keys[h] = -1; cnt[h] = 0; }
   if (threadIdx.x < PX_MAX_RANKS) s_owner_cnt[threadIdx.x] = 0;
@@ -386,7 +418,7 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
       if (raw_all) {
         if ((base + j) % G == c_me) {
           int owner, local;
-          geom_map(g, id, owner, local);
+          GEOM_MAP(id, owner, local);
           atomicAdd(&s_owner_cnt[owner], 1);
         }
         continue;
@@ -403,13 +435,14 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
     }
     __syncthreads();
   }
+  PX_DBG(0);
   if (dedup) {
     // ---- pass 2: one ring slot per unique id, one staging row per duplicated id
     for (int h = threadIdx.x; h < H; h += blockDim.x) {
       const int id = keys[h];
       if (id < 0) continue;
       int owner, local;
-      geom_map(g, id, owner, local);
+      GEOM_MAP(id, owner, local);
       kk[h] = atomicAdd(&s_owner_cnt[owner], 1);
       dup[h] = cnt[h] > 1 ? atomicAdd(&s_ndup, 1) : -1;
     }
@@ -426,7 +459,7 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
         while (keys[h] != id && keys[h] != -1 && ++probes <= H) h = (h + 1) & (H - 1);
         if (keys[h] != id) {
           int owner, local;
-          geom_map(g, id, owner, local);
+          GEOM_MAP(id, owner, local);
           atomicAdd(&s_owner_cnt[owner], 1);
         }
       }
@@ -448,132 +481,145 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
     for (int h = threadIdx.x; h < H; h += blockDim.x) {
       if (keys[h] < 0) continue;
       int owner, local;
-      geom_map(g, keys[h], owner, local);
+      GEOM_MAP(keys[h], owner, local);
       atomicMax(&s_owner_cnt[owner], kk[h] + 1);
     }
     __syncthreads();
   }
-  // ---- pass 3: ship unique rows, stage duplicated ones (warp per position)
+  PX_DBG(1);
+  // ---- pass 3: ship unique rows, stage duplicated ones.  Per chunk: (a) every thread scans
+  // the staged ids and appends its CTA's positions to a work list in shared memory, (b) the
+  // list is processed round-robin by half-warps (16 lanes per row, four 16-byte accesses in
+  // flight per lane) — balanced whatever the id distribution is.
+  int32_t* work = ids_s + PX_ID_CHUNK;
+  __shared__ int s_nwork;
+  const int sub = lane & 15, half = lane >> 4;
+  const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
   for (int base = 0; base < n; base += PX_ID_CHUNK) {
     const int m = min(PX_ID_CHUNK, n - base);
+    if (threadIdx.x == 0) s_nwork = 0;
     stage_ids(pend_ids, base, m, ids_s);
     __syncthreads();
 #pragma unroll 1
-    for (int j0 = wid * 32; j0 < m; j0 += nwarps * 32) {
-      const int j = j0 + lane;
-      const int id = j < m ? ids_s[j] : -1;
-      int h_found = -1;
-      bool mine = false, raw = false;
-      if (id >= 0) {
-        if (raw_all) { mine = (base + j) % G == c_me; raw = mine; }
-        else if ((int)(((unsigned long long)hash_cta(id) * (unsigned)G) >> 32) == c_me) {
-          mine = true;
-          uint32_t h = hash_slot(id) & (H - 1);
-          int probes = 0;
-          while (keys[h] != id && keys[h] != -1 && ++probes <= H) h = (h + 1) & (H - 1);
-          if (keys[h] == id) h_found = (int)h; else raw = true;
-        }
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+      const int id = ids_s[j];
+      if (id < 0) continue;
+      const bool mine = raw_all ? ((base + j) % G == c_me)
+          : ((int)(((unsigned long long)hash_cta(id) * (unsigned)G) >> 32) == c_me);
+      if (mine) work[atomicAdd(&s_nwork, 1)] = j;
+    }
+    __syncthreads();
+    if (base == 0) PX_DBG(2);
+    const int nwork = s_nwork;
+#pragma unroll 1
+    for (int wi = wid * 2 + half; wi < nwork; wi += nwarps * 2) {
+      const int j = work[wi];
+      const int pi = base + j;
+      const int pid = ids_s[j];
+      int ph = -1;
+      if (!raw_all) {
+        uint32_t h = hash_slot(pid) & (H - 1);
+        int probes = 0;
+        while (keys[h] != pid && keys[h] != -1 && ++probes <= H) h = (h + 1) & (H - 1);
+        if (keys[h] == pid) ph = (int)h;
       }
-      unsigned mask = __ballot_sync(0xffffffffu, mine);
+      int owner, local;
+      GEOM_MAP(pid, owner, local);
+      int k = 0, pcnt = 1;
+      if (ph < 0) {                       // raw entry: its own ring slot
+        if (sub == 0) k = s_base_k[owner] + atomicAdd(&s_owner_cnt[owner], 1);
+        k = __shfl_sync(hmask, k, half * 16);
+      } else {
+        k = s_base_k[owner] + kk[ph];
+        pcnt = cnt[ph];
+      }
+      if (pcnt == 1) {
 #pragma unroll 1
-      while (mask) {
-        const int src_lane = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int pi = base + j0 + src_lane;
-        const int pid = __shfl_sync(0xffffffffu, id, src_lane);
-        const int ph = __shfl_sync(0xffffffffu, h_found, src_lane);
-        const bool praw = __shfl_sync(0xffffffffu, (int)raw, src_lane) != 0;
-        int owner, local;
-        geom_map(g, pid, owner, local);
-        int k = 0, pcnt = 1;
-        if (praw) {
-          if (lane == 0) k = s_base_k[owner] + atomicAdd(&s_owner_cnt[owner], 1);
-          k = __shfl_sync(0xffffffffu, k, 0);
-        } else {
-          k = s_base_k[owner] + kk[ph];
-          pcnt = cnt[ph];
-        }
-        if (pcnt == 1) {
+        for (int t = 0; t < a.nt; ++t) {
+          const PushTable& T = a.t[t];
+          const float mul = ASYNC ? T.scale * T.hp[HP_GSCALE] : T.scale;
+          if (!ASYNC && sizeof(GradT) == 2 && sizeof(WireT) == 2 && (T.D4 & 1) == 0 &&
+              !g.replicated) {
+            // bf16 gradient -> bf16 wire: 16-byte copies, four per lane in flight
+            const int nv = T.D4 / 2;
+            const uint4* src = reinterpret_cast<const uint4*>(T.grads) + (size_t)pi * nv;
+            uint4* dst = reinterpret_cast<uint4*>(
+                s_ring[t][owner] + ((size_t)a.rank * a.cap + k) * ((size_t)T.D4 * 8));
 #pragma unroll 1
-          for (int t = 0; t < a.nt; ++t) {
-            const PushTable& T = a.t[t];
-            const float mul = ASYNC ? T.scale * T.hp[HP_GSCALE] : T.scale;
-            if (!ASYNC && sizeof(GradT) == 2 && sizeof(WireT) == 2 && (T.D4 & 1) == 0 &&
-                !g.replicated) {
-              // bf16 gradient -> bf16 wire: 16-byte copies, two per lane in flight
-              const int nv = T.D4 / 2;
-              const uint4* src = reinterpret_cast<const uint4*>(T.grads) + (size_t)pi * nv;
-              uint4* dst = reinterpret_cast<uint4*>(
-                  T.rings[owner] + ((size_t)a.rank * a.cap + k) * ((size_t)T.D4 * 8));
-#pragma unroll 1
-              for (int c = lane; c < nv; c += 64) {
-                const bool two = c + 32 < nv;
-                uint4 v0 = ld_v4_stream(src + c);
-                uint4 v1 = two ? ld_v4_stream(src + c + 32) : make_uint4(0, 0, 0, 0);
-                if (mul != 1.f) {
+            for (int c = sub; c < nv; c += 64) {
+              uint4 v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                v[u] = c + 16 * u < nv ? ld_v4_stream(src + c + 16 * u) : make_uint4(0, 0, 0, 0);
+              if (mul != 1.f) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
                   float f[8];
-                  Vec16<__nv_bfloat16>::unpack(v0, f);
+                  Vec16<__nv_bfloat16>::unpack(v[u], f);
 #pragma unroll
                   for (int q = 0; q < 8; ++q) f[q] *= mul;
-                  v0 = Vec16<__nv_bfloat16>::pack(f);
-                  Vec16<__nv_bfloat16>::unpack(v1, f);
-#pragma unroll
-                  for (int q = 0; q < 8; ++q) f[q] *= mul;
-                  v1 = Vec16<__nv_bfloat16>::pack(f);
+                  v[u] = Vec16<__nv_bfloat16>::pack(f);
                 }
-                st_v4_stream(dst + c, v0);
-                if (two) st_v4_stream(dst + c + 32, v1);
               }
-              continue;
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (c + 16 * u < nv) st_v4_stream(dst + c + 16 * u, v[u]);
             }
-#pragma unroll 1
-            for (int c = lane; c < T.D4; c += 32) {
-              float4 v = ld_grad4<GradT>(reinterpret_cast<const GradT*>(T.grads),
-                                         (size_t)pi * T.D4 + c);
-              v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
-              emit_row<WireT, ASYNC, FAM>(a, g, t, owner, local, k, c, v);
-            }
+            continue;
           }
-          if (!ASYNC && lane == 0) emit_id(a, g, owner, local, k);
-        } else {
-          const int d = s_base_dup + dup[ph];
 #pragma unroll 1
-          for (int t = 0; t < a.nt; ++t) {
-            const PushTable& T = a.t[t];
-            float4* dst = reinterpret_cast<float4*>(T.staging) + (size_t)d * T.D4;
-            for (int c = lane; c < T.D4; c += 32)
-              atomicAdd(dst + c, ld_grad4<GradT>(reinterpret_cast<const GradT*>(T.grads),
-                                                 (size_t)pi * T.D4 + c));
+          for (int c = sub; c < T.D4; c += 16) {
+            float4 v = ld_grad4<GradT>(reinterpret_cast<const GradT*>(T.grads),
+                                       (size_t)pi * T.D4 + c);
+            v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
+            emit_row<WireT, ASYNC, FAM>(a, g, t, owner, local, k, c, v);
           }
+        }
+        if (!ASYNC && sub == 0) emit_id(a, g, owner, local, k);
+      } else {
+        const int d = s_base_dup + dup[ph];
+#pragma unroll 1
+        for (int t = 0; t < a.nt; ++t) {
+          const PushTable& T = a.t[t];
+          float4* dst = reinterpret_cast<float4*>(T.staging) + (size_t)d * T.D4;
+          for (int c = sub; c < T.D4; c += 16)
+            atomicAdd(dst + c, ld_grad4<GradT>(reinterpret_cast<const GradT*>(T.grads),
+                                               (size_t)pi * T.D4 + c));
         }
       }
     }
     __syncthreads();
   }
+  PX_DBG(3);
   // every position of my duplicated ids is staged now (they are all mine)
   // ---- pass 4: flush duplicated ids (warp per id), re-zero the staging rows
   if (dedup && s_ndup > 0) {
-    for (int h = wid; h < H; h += nwarps) {
-      if (keys[h] < 0 || cnt[h] <= 1) continue;
-      int owner, local;
-      geom_map(g, keys[h], owner, local);
-      const int k = s_base_k[owner] + kk[h];
-      const int d = s_base_dup + dup[h];
+    for (int h0 = wid * 32; h0 < H; h0 += nwarps * 32) {
+      unsigned dm = __ballot_sync(0xffffffffu, keys[h0 + lane] >= 0 && cnt[h0 + lane] > 1);
+      while (dm) {
+        const int h = h0 + __ffs(dm) - 1;
+        dm &= dm - 1;
+        int owner, local;
+        GEOM_MAP(keys[h], owner, local);
+        const int k = s_base_k[owner] + kk[h];
+        const int d = s_base_dup + dup[h];
 #pragma unroll 1
-      for (int t = 0; t < a.nt; ++t) {
-        const PushTable& T = a.t[t];
-        const float mul = ASYNC ? T.scale * T.hp[HP_GSCALE] : T.scale;
-        float4* src = reinterpret_cast<float4*>(T.staging) + (size_t)d * T.D4;
-        for (int c = lane; c < T.D4; c += 32) {
-          float4 v = __ldcg(src + c);
-          __stcg(src + c, make_float4(0.f, 0.f, 0.f, 0.f));
-          v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
-          emit_row<WireT, ASYNC, FAM>(a, g, t, owner, local, k, c, v);
+        for (int t = 0; t < a.nt; ++t) {
+          const PushTable& T = a.t[t];
+          const float mul = ASYNC ? T.scale * T.hp[HP_GSCALE] : T.scale;
+          float4* src = reinterpret_cast<float4*>(T.staging) + (size_t)d * T.D4;
+          for (int c = lane; c < T.D4; c += 32) {
+            float4 v = __ldcg(src + c);
+            __stcg(src + c, make_float4(0.f, 0.f, 0.f, 0.f));
+            v.x *= mul; v.y *= mul; v.z *= mul; v.w *= mul;
+            emit_row<WireT, ASYNC, FAM>(a, g, t, owner, local, k, c, v);
+          }
         }
+        if (!ASYNC && lane == 0) emit_id(a, g, owner, local, k);
       }
-      if (!ASYNC && lane == 0) emit_id(a, g, owner, local, k);
     }
   }
+  PX_DBG(4);
   // ---- completion: last CTA publishes counts + `pushed` (sync) / bumps the step (async).
   // One fence per CTA: the barrier orders every thread's stores before thread 0's
   // system-scope fence (cumulativity), which orders them before the ticket and the flag.
@@ -583,6 +629,7 @@ px_sparse_push_kernel(const int32_t* __restrict__ pend_ids, int n, PushArgs a, G
     s_last = (atomicAdd(&ctl->push_done, 1u) == gridDim.x - 1);
   }
   __syncthreads();
+  PX_DBG(5);
   if (!s_last) return;
   __threadfence_system();
   const uint32_t step = ctl->step + 1;
@@ -631,7 +678,7 @@ struct OwnerArgs {
 // optimizer once per touched row, publish `applied`.  Launched cooperatively when use_merge (one
 // grid barrier between linking and applying).
 template <typename WireT, int FAM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, FAM == 0 ? 4 : 2)
 px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
   __shared__ bool s_last;
   const bool stamp = blockIdx.x == 0 && threadIdx.x == 0;
@@ -644,7 +691,9 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
     __syncthreads();
   }
   if (stamp) ctl->t_own[1] = px_globaltimer();
-  const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  // apply phase: 16 lanes per entry (two entries per warp in flight)
+  const int lane = threadIdx.x & 15, warps = blockDim.x >> 4;
+  const unsigned hmask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
   const uint32_t* cnt = a.hdr + 2 * PX_MAX_RANKS;
   if (a.use_merge) {
     // link: every entry pushes itself on the list of its row (at most one entry per source when
@@ -669,7 +718,7 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
   }
   for (int s = 0; s < g.W; ++s) {
     const int c = a.fixed_cnt >= 0 ? a.fixed_cnt : (int)ld_volatile_u32(cnt + s);
-    for (int j = blockIdx.x * warps + (threadIdx.x >> 5); j < c; j += gridDim.x * warps) {
+    for (int j = blockIdx.x * warps + (threadIdx.x >> 4); j < c; j += gridDim.x * warps) {
       const int e = s * a.cap + j;
       const int r = a.ring_ids[e];
       {
@@ -684,7 +733,7 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
               const OwnerTable& T = a.t[t];
               const size_t off = (size_t)rn * T.D4 * 16;             // row offset in bytes
               const int lines = (T.D4 * 16 + 127) / 128;
-              for (int l = lane; l < lines; l += 32) {
+              for (int l = lane; l < lines; l += 16) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(T.table) + off + l * 128));
                 if (T.slot0)
                   asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(T.slot0) + off + l * 128));
@@ -707,7 +756,7 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
         const PxHP hp = px_load_hp(T.hp);
         if (sizeof(WireT) == 2 && (T.D4 & 1) == 0) {
           // bf16 wire rows: one 16-byte load carries 8 elements = two float4 groups
-          for (int c2 = lane; c2 < T.D4 / 2; c2 += 32) {
+          for (int c2 = lane; c2 < T.D4 / 2; c2 += 16) {
             float f[8];
             Vec16<__nv_bfloat16>::unpack(
                 ld_v4_stream(reinterpret_cast<const uint4*>(T.ring + (size_t)e * row_bytes) + c2), f);
@@ -727,7 +776,7 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
           }
           continue;
         }
-        for (int cidx = lane; cidx < T.D4; cidx += 32) {
+        for (int cidx = lane; cidx < T.D4; cidx += 16) {
           float4 gv = ld_wire4<WireT>(T.ring + (size_t)e * row_bytes, cidx);
           if (a.use_merge) {
             for (int x = __ldcg(a.next + e); x != -1; x = __ldcg(a.next + x)) {
@@ -740,7 +789,7 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
                              (size_t)r, T.D4, cidx);
         }
       }
-      __syncwarp();
+      __syncwarp(hmask);
       if (a.use_merge && lane == 0) a.slotmap[r] = -1;
     }
   }
@@ -772,7 +821,7 @@ static void launch_push(int blocks, size_t smem, cudaStream_t stream, const int3
   if (!attr) {
     cudaFuncSetAttribute(px_sparse_push_kernel<GT, WT, AS, FAM>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         4 * 4 * 8192 + PX_ID_CHUNK * 4);
+                         4 * 4 * 8192 + 2 * PX_ID_CHUNK * 4);
     attr = true;
   }
   px_sparse_push_kernel<GT, WT, AS, FAM><<<blocks, 256, smem, stream>>>(pend_ids, n, a, G, ctl,
@@ -871,11 +920,11 @@ int px_sparse_push(const int32_t* pend_ids, int n, const PxPushTable* tabs, int 
     if (t == 0) fam = PX_KIND_FAMILY(T.kind);
     else if (fam != PX_KIND_FAMILY(T.kind)) return -6;
   }
-  int blocks = (n + 31) / 32;
+  int blocks = (n + 15) / 16;
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   const int hbits = push_hbits(n, blocks);
-  const size_t smem = ((size_t)4 * sizeof(int32_t) << hbits) + PX_ID_CHUNK * sizeof(int32_t);
+  const size_t smem = ((size_t)4 * sizeof(int32_t) << hbits) + 2 * PX_ID_CHUNK * sizeof(int32_t);
   SparseCtl* C = (SparseCtl*)ctl;
 #define PUSH(GT, WT, AS, FAM) launch_push<GT, WT, AS, FAM>(blocks, smem, stream, pend_ids, n, a, G, C, hbits, dedup)
   if (async) {

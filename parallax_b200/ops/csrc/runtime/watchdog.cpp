@@ -54,8 +54,19 @@ void report_missing() {
   if (!W.pad_dev || W.pad_words == 0 || !W.rd_stream || !W.rd_host) return;
   cudaStream_t s = W.rd_stream;
   uint32_t* host = W.rd_host;
-  if (cudaMemcpyAsync(host, W.pad_dev, W.pad_words * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
-      cudaStreamSynchronize(s) == cudaSuccess) {
+  // never block here: poll the copy for at most one second (a wedged device must not keep the
+  // watchdog from reaching its shutdown limit)
+  bool have = false;
+  if (cudaMemcpyAsync(host, W.pad_dev, W.pad_words * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess) {
+    for (int i = 0; i < 100 && !have; ++i) {
+      if (cudaStreamQuery(s) == cudaSuccess) have = true;
+      else { cudaGetLastError(); std::this_thread::sleep_for(std::chrono::milliseconds(10)); }
+    }
+  }
+  if (!have)
+    fprintf(stderr, "[parallax watchdog] rank %d: device did not return the signal pad within 1 s\n",
+            W.rank);
+  if (have) {
     // layout [channel][block][src]: for block 0 of every channel report lagging peers
     const int MAXR = 16, MAXB = 128;
     for (int ch = 0; ch < 8; ++ch) {
@@ -98,8 +109,10 @@ void loop() {
               "[parallax watchdog] rank %d: no progress for %.1f s at step %lld. One or more "
               "ranks may have died or are not calling the same collectives in the same order.\n",
               W.rank, idle, W.step.load());
-      report_missing();
       fflush(stderr);
+      // best-effort diagnosis on its own thread: whatever the device does, this loop goes on
+      // to enforce the shutdown limit
+      std::thread(report_missing).detach();
     }
     if (W.shutdown_s > 0 && idle > W.shutdown_s) {
       fprintf(stderr, "[parallax watchdog] rank %d: stalled for %.1f s > shutdown limit %.1f s; "

@@ -727,11 +727,11 @@ class NVSparseGroup(object):
         cs = stream if stream is not None else self.fabric.comm_stream
         n = max(self._last_n, 1)
         nt = len(self.tables)
-        # 8 warps per CTA, one row per warp: as many CTAs as fit on the device at once
+        # 16 half-warps per CTA, one entry per half-warp: as many CTAs as fit on the device at once
         # (4 per SM at 64 registers; the merge variant is a cooperative launch)
         blocks = max(1, min(max(self.max_blocks, 148 * 4) if self.max_blocks >= 148
                             else self.max_blocks,
-                            (n * (self.world if self.replicated else 1) + 7) // 8))
+                            (n * (self.world if self.replicated else 1) + 15) // 16))
         use_merge = self.world > 1 or not self.local_aggregation
         descs = (ops.PxOwnerTable * nt)()
         for d, t in zip(descs, self.tables):
@@ -759,9 +759,11 @@ class NVSparseGroup(object):
         """%globaltimer stamps (ns) written by the last push / owner kernels:
         push start, pushed flag published, owner start, all sources arrived, applied
         published.  Valid under CUDA-graph replay (the kernels write them every run)."""
-        raw = self.ctl.view(torch.uint8)[self._t_off:self._t_off + 40].clone() \
+        raw = self.ctl.view(torch.uint8)[self._t_off:self._t_off + 104].clone() \
             .view(torch.int64).tolist()
-        return dict(zip(("push_start", "pushed", "owner_start", "arrived", "applied"), raw))
+        d = dict(zip(("push_start", "pushed", "owner_start", "arrived", "applied"), raw))
+        d["push_phases"] = raw[5:13]        # CTA 0 of the push kernel: end of each phase
+        return d
 
     def overflow_count(self):
         return int(self.ctl.view(torch.uint8)[self._ovf_off:self._ovf_off + 4]

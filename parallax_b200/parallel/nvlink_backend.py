@@ -54,6 +54,11 @@ class NVFabric(object):
         # double-buffered staging for the one-shot all-reduce (norms, scalars)
         self.small_stage = self.heap.alloc(2 * 65536, "oneshot_stage")
         self.max_blocks = int(self.options.get("comm_blocks", 32))
+        # CTAs of the fused dense step: its barriers are rank-level, so the grid is sized for
+        # HBM bandwidth (2 per SM); an explicit comm_blocks (tests simulating several ranks on
+        # one GPU need small grids) applies to it as well
+        self.dense_blocks = int(self.options.get(
+            "dense_blocks", self.options.get("comm_blocks", 148 * 2)))
         if isinstance(ex, IpcExchange):
             self.heap.pads_dev()        # eager: no lazy H2D inside a step
         if comm.distributed:
@@ -341,7 +346,7 @@ class NVDenseGroup(object):
         if getattr(self, "stamp_before", None) and b.index == len(self.buckets) - 1:
             nvops.stamp(self.stamp_before, cs)
         W = self.world
-        mb = fab.max_blocks
+        mb = fab.dense_blocks
         ema_decay = self.ema_rule.decay if self.ema_rule is not None else 0.0
         s0 = b.slots[0] if self.nslots > 0 else None
         s1 = b.slots[1] if self.nslots > 1 else None

@@ -90,7 +90,7 @@ class EngineAutotuner(object):
         self.tuner = BayesianTuner(
             {"comm_blocks": (4.0, 128.0), "sparse_blocks": (16.0, 296.0)},
             categorical={"early_push": [True, False], "defer_last": [True, False],
-                         "wgrad_chunks": [2, 1, 4]},
+                         "wgrad_chunks": [1, 2, 4]},
             samples_per_point=1, warmups=0, max_points=10) if engine.comm.rank == 0 else None
         self.log = os.environ.get(PARALLAX_AUTOTUNE_LOG)
         self.done = False
@@ -114,6 +114,7 @@ class EngineAutotuner(object):
     def _apply(self, vals):
         eng = self.engine
         eng.fabric.max_blocks = max(1, min(128, vals["comm_blocks"]))
+        eng.fabric.dense_blocks = max(1, 4 * vals["comm_blocks"])      # 16 .. 512 CTAs
         for grp in getattr(eng, "sparse_groups", ()):
             grp.max_blocks = max(1, vals["sparse_blocks"])
             grp.early_push = bool(vals["early_push"])

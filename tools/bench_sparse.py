@@ -21,6 +21,9 @@ from gpu_utils import FakeComm
 
 ITERS = 3 if "--ncu" in sys.argv else 50
 V = 793470
+for a_ in sys.argv:
+    if a_.startswith("--V="):
+        V = int(a_[4:])          # a small V makes every row L2 / TLB resident (latency probe)
 fab = NVFabric(FakeComm(0, 1, "cuda:0"), exchange=LocalWorld(1).exchange_for(0))
 opt = optim.Adagrad(0.2, 1.0)
 route = modes.route_for("HYBRID", True)
@@ -62,6 +65,14 @@ def bench(grp, n, name):
         torch.cuda.synchronize()
         if it >= 2:
             tl += e[0].elapsed_time(e[1]); tp += e[1].elapsed_time(e[2]); to += e[2].elapsed_time(e[3])
+    d = grp.device_times()
+    ph = d["push_phases"]
+    print("   push kernel (device timer, CTA 0): total %.1f us; phases scan1 %.1f | slots %.1f | "
+          "scan3a(chunk0) %.1f | ship %.1f | flush %.1f | fence+ticket %.1f ; owner %.1f us" % (
+              (d["pushed"] - d["push_start"]) / 1e3, (ph[0] - d["push_start"]) / 1e3,
+              (ph[1] - ph[0]) / 1e3, (ph[2] - ph[1]) / 1e3, (ph[3] - ph[2]) / 1e3,
+              (ph[4] - ph[3]) / 1e3, (ph[5] - ph[4]) / 1e3,
+              (d["applied"] - d["owner_start"]) / 1e3), flush=True)
     rowb = sum(t.Dp for t in grp.tables)
     print("%-10s n=%-6d lookup %6.1f us  push %6.1f us  owner %6.1f us   "
           "(push moves %.1f MB bf16, owner %.1f MB)" %
