@@ -695,18 +695,32 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
   const int lane = threadIdx.x & 15, warps = blockDim.x >> 4;
   const unsigned hmask = (threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu;
   const uint32_t* cnt = a.hdr + 2 * PX_MAX_RANKS;
+  // entries of all sources form ONE index space [0, total): a (source, j) double loop would
+  // hand every half-warp one entry per source — W entries in sequence for the first few
+  // half-warps and nothing for the rest
+  __shared__ int s_pre[PX_MAX_RANKS + 1];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int s = 0; s < g.W; ++s) {
+      s_pre[s] = acc;
+      acc += a.fixed_cnt >= 0 ? a.fixed_cnt : (int)ld_volatile_u32(cnt + s);
+    }
+    s_pre[g.W] = acc;
+  }
+  __syncthreads();
+  const int total = s_pre[g.W];
   if (a.use_merge) {
     // link: every entry pushes itself on the list of its row (at most one entry per source when
     // the senders aggregate locally, so lists are <= W long)
-    for (int s = 0; s < g.W; ++s) {
-      const int c = a.fixed_cnt >= 0 ? a.fixed_cnt : (int)ld_volatile_u32(cnt + s);
-      for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < c; j += gridDim.x * blockDim.x) {
-        const int e = s * a.cap + j;
-        const int r = a.ring_ids[e];
-        if (r >= 0) a.next[e] = atomicExch(&a.slotmap[r], e);
-      }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      int s = 0;
+      while (i >= s_pre[s + 1]) ++s;
+      const int e = s * a.cap + (i - s_pre[s]);
+      const int r = a.ring_ids[e];
+      if (r >= 0) a.next[e] = atomicExch(&a.slotmap[r], e);
     }
     // grid barrier (all CTAs are co-resident: cooperative launch)
+    if (stamp) ctl->t_dbg[6] = px_globaltimer();
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -715,19 +729,23 @@ px_sparse_owner_kernel(OwnerArgs a, GroupGeom g, SparseCtl* ctl) {
       __threadfence();
     }
     __syncthreads();
+    if (stamp) ctl->t_dbg[7] = px_globaltimer();
   }
-  for (int s = 0; s < g.W; ++s) {
-    const int c = a.fixed_cnt >= 0 ? a.fixed_cnt : (int)ld_volatile_u32(cnt + s);
-    for (int j = blockIdx.x * warps + (threadIdx.x >> 4); j < c; j += gridDim.x * warps) {
-      const int e = s * a.cap + j;
+  {
+    for (int i = blockIdx.x * warps + (threadIdx.x >> 4); i < total; i += gridDim.x * warps) {
+      int s = 0;
+      while (i >= s_pre[s + 1]) ++s;
+      const int e = s * a.cap + (i - s_pre[s]);
       const int r = a.ring_ids[e];
       {
         // the rows of a batch are scattered over a multi-GB table: every touch is a DRAM
-        // (and usually a TLB) miss.  Prefetch this warp's NEXT entry's table / slot rows into
-        // L2 now, so that miss overlaps the work on the current entry.
-        const int jn = j + gridDim.x * warps;
-        if (jn < c) {
-          const int rn = a.ring_ids[s * a.cap + jn];
+        // (and usually a TLB) miss.  Prefetch this half-warp's NEXT entry's table / slot rows
+        // into L2 now, so that miss overlaps the work on the current entry.
+        const int in = i + gridDim.x * warps;
+        if (in < total) {
+          int sn = s;
+          while (in >= s_pre[sn + 1]) ++sn;
+          const int rn = a.ring_ids[sn * a.cap + (in - s_pre[sn])];
           if (rn >= 0) {
             for (int t = 0; t < a.nt; ++t) {
               const OwnerTable& T = a.t[t];

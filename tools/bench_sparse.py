@@ -28,6 +28,9 @@ fab = NVFabric(FakeComm(0, 1, "cuda:0"), exchange=LocalWorld(1).exchange_for(0))
 opt = optim.Adagrad(0.2, 1.0)
 route = modes.route_for("HYBRID", True)
 cfg = parallax.Config(run_option="HYBRID")
+if "--merge" in sys.argv:       # force the owner's cross-source merge path on one GPU
+    cfg.communication_config = parallax.CommunicationConfig(
+        parallax.PSConfig(local_aggregation=False))
 graph = Graph(torch.nn.Linear(1, 1), optimizer=opt)
 meta = lambda d: torch.empty(V, d, device="meta")
 init = {"seed": 1, "scale": 0.05}
@@ -73,6 +76,10 @@ def bench(grp, n, name):
               (ph[1] - ph[0]) / 1e3, (ph[2] - ph[1]) / 1e3, (ph[3] - ph[2]) / 1e3,
               (ph[4] - ph[3]) / 1e3, (ph[5] - ph[4]) / 1e3,
               (d["applied"] - d["owner_start"]) / 1e3), flush=True)
+    if ph[6] and ph[7] >= ph[6] > d["owner_start"]:
+        print("   owner (merge): link %.1f us | grid barrier %.1f us | apply+publish %.1f us" % (
+            (ph[6] - d["owner_start"]) / 1e3, (ph[7] - ph[6]) / 1e3,
+            (d["applied"] - ph[7]) / 1e3), flush=True)
     rowb = sum(t.Dp for t in grp.tables)
     print("%-10s n=%-6d lookup %6.1f us  push %6.1f us  owner %6.1f us   "
           "(push moves %.1f MB bf16, owner %.1f MB)" %
