@@ -85,6 +85,11 @@ __device__ __forceinline__ void st_f32(float* p, const float* f) {
 //  * end: the last CTA to finish (ticket) fences, announces "all my parameter stores are out"
 //    in slot 0 of `ch_end` and waits for the same from every peer; the kernel — and with it the
 //    stream — completes only then.  Slot 1 of `ch_end` holds the ticket counter.
+__device__ __forceinline__ unsigned long long px_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void px_rank_signal(uint32_t* const* pads, int slot, int rank, int world,
                                                uint32_t e) {
   if (threadIdx.x < world)
@@ -100,17 +105,25 @@ __device__ __forceinline__ void px_rank_wait(uint32_t* const* pads, int slot, in
 }
 
 template <typename T, int W, int FAM>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, (W == 1 && FAM == 0) ? 2 : 1)
 px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr) {
   constexpr int VN = Vec16<T>::N;
   const int mode = a.mode, kind = a.kind;
   const int slot_s = a.ch_start * PX_MAX_BLOCKS, slot_e = a.ch_end * PX_MAX_BLOCKS;
+  // profiling aid: %globaltimer stamps of the last launch in the (otherwise unused) epoch slots
+  // of the last channel: [0] CTA 0 start, [1] CTA 0 past the start wait, [2] CTA 0 loop done,
+  // [3] last CTA fenced, [4] last CTA past the end wait
+  unsigned long long* dbg = reinterpret_cast<unsigned long long*>(
+      epoch_ctr + (PX_NUM_CHANNELS - 1) * PX_MAX_BLOCKS);
+  const bool stamp0 = blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamp0) dbg[0] = px_timer();
   uint32_t e_start = 0;
   if (W > 1 && mode != 2) {
     e_start = ld_volatile_u32(epoch_ctr + slot_s) + 1;
     if (blockIdx.x == 0) px_rank_signal(pads, slot_s, a.rank, W, e_start);
     px_rank_wait(pads, slot_s, a.rank, W, e_start);
   }
+  if (stamp0) dbg[1] = px_timer();
   const size_t slice = a.n / W;
   const size_t nvec = slice / VN;
   const size_t base = (size_t)a.rank * slice;
@@ -122,25 +135,45 @@ px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr
   float ss = 0.f;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
     const size_t e = v * VN;                        // element offset inside the slice
+    // ---- issue EVERY load of this vector before touching any loaded value: the helpers are
+    // volatile asm (program order), so a dependent FADD between the peer loads and the
+    // master/slot loads would serialise two memory latencies (one of them an NVLink round
+    // trip) per vector
     float g[VN];
+    uint4 in[W];
+    uint4 mcv = make_uint4(0, 0, 0, 0);
     if (mode == 2) {
       ld_f32<VN>(a.red + e, g);
     } else if (a.use_mc) {
       // one switch-side reduction instead of W peer loads
-      Vec16<T>::unpack(ds_mm_ld_reduce<T>(reinterpret_cast<const T*>(a.grads.p[0]) + base + e), g);
+      mcv = ds_mm_ld_reduce<T>(reinterpret_cast<const T*>(a.grads.p[0]) + base + e);
     } else {
-      uint4 in[W];
 #pragma unroll
       for (int p = 0; p < W; ++p)
         in[p] = ld_v4_stream(reinterpret_cast<const T*>(a.grads.p[p]) + base + e);
+    }
+    float w[VN], s0[VN], s1[VN], s2[FAM == 1 ? VN : 1], m[VN];
+    if (mode != 1) {
+      ld_f32<VN>(a.master + e, w);
+      if (a.slot0) ld_f32<VN>(a.slot0 + e, s0);
+      if (a.slot1) ld_f32<VN>(a.slot1 + e, s1);
+      if (FAM == 1 && a.slot2) ld_f32<VN>(a.slot2 + e, s2);
+      if (a.ema) ld_f32<VN>(a.ema + e, m);
+    }
+    // ---- math
+    if (mode != 2) {
+      if (a.use_mc) {
+        Vec16<T>::unpack(mcv, g);
+      } else {
 #pragma unroll
-      for (int i = 0; i < VN; ++i) g[i] = 0.f;
+        for (int i = 0; i < VN; ++i) g[i] = 0.f;
 #pragma unroll
-      for (int p = 0; p < W; ++p) {
-        float f[VN];
-        Vec16<T>::unpack(in[p], f);
+        for (int p = 0; p < W; ++p) {
+          float f[VN];
+          Vec16<T>::unpack(in[p], f);
 #pragma unroll
-        for (int i = 0; i < VN; ++i) g[i] += f[i];
+          for (int i = 0; i < VN; ++i) g[i] += f[i];
+        }
       }
     }
 #pragma unroll
@@ -151,11 +184,6 @@ px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr
       st_f32<VN>(a.red + e, g);
       continue;
     }
-    float w[VN], s0[VN], s1[VN], s2[FAM == 1 ? VN : 1];
-    ld_f32<VN>(a.master + e, w);
-    if (a.slot0) ld_f32<VN>(a.slot0 + e, s0);
-    if (a.slot1) ld_f32<VN>(a.slot1 + e, s1);
-    if (FAM == 1 && a.slot2) ld_f32<VN>(a.slot2 + e, s2);
 #pragma unroll
     for (int i = 0; i < VN; ++i) {
       const float gi = h.wd != 0.f ? fmaf(h.wd, w[i], g[i]) : g[i];
@@ -166,8 +194,6 @@ px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr
     if (a.slot1) st_f32<VN>(a.slot1 + e, s1);
     if (FAM == 1 && a.slot2) st_f32<VN>(a.slot2 + e, s2);
     if (a.ema) {
-      float m[VN];
-      ld_f32<VN>(a.ema + e, m);
 #pragma unroll
       for (int i = 0; i < VN; ++i) m[i] -= (1.f - a.ema_decay) * (m[i] - w[i]);
       st_f32<VN>(a.ema + e, m);
@@ -182,6 +208,7 @@ px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr
     }
   }
   if (mode == 1 && a.sumsq != nullptr) block_atomic_sum(ss, a.sumsq);
+  if (stamp0) dbg[2] = px_timer();
   if (W > 1) {
     __shared__ bool s_last;
     __syncthreads();
@@ -191,12 +218,14 @@ px_dense_step_kernel(DenseStepArgs a, uint32_t* const* pads, uint32_t* epoch_ctr
     }
     __syncthreads();
     if (s_last) {
+      if (threadIdx.x == 0) dbg[3] = px_timer();
       if (mode != 1) {
         const uint32_t e_end = ld_volatile_u32(epoch_ctr + slot_e) + 1;
         px_rank_signal(pads, slot_e, a.rank, W, e_end);
         px_rank_wait(pads, slot_e, a.rank, W, e_end);
         if (threadIdx.x == 0) epoch_ctr[slot_e] = e_end;
       }
+      if (threadIdx.x == 0) dbg[4] = px_timer();
       if (threadIdx.x == 0) {
         if (mode != 2) epoch_ctr[slot_s] = e_start;
         epoch_ctr[slot_e + 1] = 0;
@@ -318,7 +347,7 @@ int px_dense_step(const void* const* grads, const void* const* params, float* ma
   const int threads = 512;
   // rank-level barriers: the grid is sized for HBM bandwidth, not by barrier slots
   size_t b = (n / world / vn + threads - 1) / threads;
-  const size_t cap = world == 1 ? 148 * 4 : (size_t)(max_blocks > 0 ? max_blocks : 148 * 2);
+  const size_t cap = world == 1 ? 148 * 4 : (size_t)(max_blocks > 0 ? max_blocks : 148);
   int blocks = (int)(b < 1 ? 1 : (b > cap ? cap : b));
 #define LAUNCH(T, W)                                                                       \
   do {                                                                                     \

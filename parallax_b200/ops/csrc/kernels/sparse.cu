@@ -674,6 +674,18 @@ struct OwnerArgs {
                                 // many entries (negative row id = not mine), no flags involved
 };
 
+// One warp that waits for every source's `pushed` flag.  Launched right before the owner kernel
+// on the comm stream: the owner's (cooperative, whole-GPU) grid then starts with its inputs
+// complete instead of spinning with every register file of the device allocated while the
+// backward pass on the main stream is starved — measured at N=2: 31 us of owner spinning cost
+// 65 us of forward/backward time.
+__global__ void px_sparse_wait_kernel(const uint32_t* hdr, const SparseCtl* ctl, int W) {
+  if (threadIdx.x < W) {
+    const uint32_t need = ctl->step + 1;
+    while ((int32_t)(ld_acquire_sys(hdr + threadIdx.x) - need) < 0) { __nanosleep(200); }
+  }
+}
+
 // ONE launch: wait for every source, merge rows that several sources touched, apply the sparse
 // optimizer once per touched row, publish `applied`.  Launched cooperatively when use_merge (one
 // grid barrier between linking and applying).
@@ -979,6 +991,8 @@ int px_sparse_owner(const PxOwnerTable* tabs, int nt, int wire_dtype, const int3
     else if (fam != PX_KIND_FAMILY(T.kind)) return -6;
   }
   if (blocks < 1) blocks = 1;
+  if (fixed_cnt < 0 && G.W > 1)
+    px_sparse_wait_kernel<<<1, 32, 0, stream>>>((const uint32_t*)hdr, (const SparseCtl*)ctl, G.W);
   static int max_coop = 0;
   if (max_coop == 0) {
     int per_sm = 0, dev = 0, sms = 0;

@@ -54,11 +54,12 @@ class NVFabric(object):
         # double-buffered staging for the one-shot all-reduce (norms, scalars)
         self.small_stage = self.heap.alloc(2 * 65536, "oneshot_stage")
         self.max_blocks = int(self.options.get("comm_blocks", 32))
-        # CTAs of the fused dense step: its barriers are rank-level, so the grid is sized for
-        # HBM bandwidth (2 per SM); an explicit comm_blocks (tests simulating several ranks on
-        # one GPU need small grids) applies to it as well
+        # CTAs of the fused dense step: its barriers are rank-level, so the grid is not tied to
+        # the barrier slots — one CTA of 512 threads per SM (at 110 registers more would run as
+        # a second wave behind the first one's system-scope fence); an explicit comm_blocks
+        # (tests simulating several ranks on one GPU need small grids) applies to it as well
         self.dense_blocks = int(self.options.get(
-            "dense_blocks", self.options.get("comm_blocks", 148 * 2)))
+            "dense_blocks", self.options.get("comm_blocks", 148)))
         if isinstance(ex, IpcExchange):
             self.heap.pads_dev()        # eager: no lazy H2D inside a step
         if comm.distributed:

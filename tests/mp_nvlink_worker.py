@@ -88,7 +88,7 @@ def main():
         every = comm.all_gather_object([float(x) for x in losses])
         mean = np.mean(np.asarray(every), axis=0)
         return bool(np.isfinite(every).all() and mean[-4:].mean() < mean[:2].mean())
-    losses, _, _ = sc.train(world, rank, "PS", "sgd", 24, False, sync=False)
+    losses, _, _ = sc.train(world, rank, "PS", "adagrad", 24, False, sync=False)
     check("async PS trains (finite, mean loss over ranks decreases)", trains(losses))
     losses, _, _ = sc.train(world, rank, "HYBRID", "adagrad", 24, True,
                             sess_config={"compute_dtype": "bf16", "cuda_graph": True})

@@ -102,12 +102,17 @@ def dense(use_mc):
                                         None, n, 1.0 / W, 0.999, "adagrad", 0, torch.bfloat16,
                                         CH_COMM, max_blocks=fab.dense_blocks,
                                         use_mc=use_mc), args.iters)
+    torch.cuda.synchronize()
+    st_ = heap.epoch[7 * 128:7 * 128 + 10].clone().view(torch.int64).tolist()
+    phases = {"start_wait_us": (st_[1] - st_[0]) / 1e3, "loop_cta0_us": (st_[2] - st_[1]) / 1e3,
+              "to_last_cta_fenced_us": (st_[3] - st_[2]) / 1e3,
+              "end_wait_us": (st_[4] - st_[3]) / 1e3}
     link_in = (W - 1) / W * sl * 2 if not use_mc else sl * 2      # bytes pulled per rank
     link_out = (W - 1) * sl * 2 if not use_mc else sl * 2         # parameter stores leaving
     hbm = sl * (2 + 8 + 8 + 8 + 2) + (0 if use_mc else 0)
     t_link = max(link_in, link_out) / (NVLINK * 1e3)              # us
     t_hbm = hbm / (HBM * 1e3)
-    return {"us": us, "n_params": n, "nvlink_bytes_in": link_in, "nvlink_bytes_out": link_out,
+    return {"us": us, "phases_last_launch": phases, "n_params": n, "nvlink_bytes_in": link_in, "nvlink_bytes_out": link_out,
             "hbm_bytes": hbm, "roofline_us": max(t_link, t_hbm),
             "bound": "nvlink" if t_link > t_hbm else "hbm",
             "fraction_of_roofline": max(t_link, t_hbm) / us,
