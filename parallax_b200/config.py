@@ -15,18 +15,27 @@ parameter servers):
 * ``PSConfig.protocol`` — the reference picks the PS transport
   (grpc / grpc+verbs / grpc+gdr / grpc+mpi).  Here the transport is NVLink
   peer memory; accepted values additionally include ``"nvlink"`` (default
-  behaviour for every legacy value) and ``"nccl"`` (forces the library
-  fallback, used by the baseline).
+  behaviour for every legacy value) and ``"nccl"`` — the in-engine library arm: same
+  engine, buckets and CUDA graph, but every cross-GPU byte goes through NCCL
+  (dense: ncclAllReduce + local fused optimizer; sparse: all-gather of ids and rows +
+  owner kernel; lookups: all-gather(ids) + local gather + reduce-scatter).  `bench.py`
+  reports it as ``same_engine_nccl``.
 * ``PSConfig.replicate_variables`` — True: owners *push* updated dense
   values into every GPU's mirror right after the update; False: workers
   *pull* owner values at the start of the next step.
 * ``PSConfig.local_aggregation`` — dedup/sum duplicate indices on the sender
-  before shipping (SMEM hash); False ships every (index,row) pair.
-* ``boundary_among_servers`` / ``boundary_between_workers_and_servers`` —
-  in the reference these move clip/scale/cast ops to the right side of the
-  worker↔PS wire.  Here they select whether grad post-processing
-  (scale, clip factor, down-cast to the wire dtype) is fused on the sender
-  side of the push kernel (True) or left to the owner apply kernel.
+  before shipping (shared-memory hash tables inside the push kernel); False ships
+  every (index,row) pair and the owner merges them.
+* ``boundary_among_servers`` — the reference assigns each post-aggregation op to the
+  server that owns the variable it feeds (`graph_transform_lib.py:174-327`).  Here the
+  owner of a slice / partition always runs them; the flag selects how partitions are
+  placed on owners: True = byte-greedy over all sparse variables
+  (`ps/between_graph_parallel.py:49-70`), False = round-robin.
+* ``boundary_between_workers_and_servers`` — the reference moves size-reducing ops to
+  the producer and size-increasing casts to the consumer of every worker↔server edge
+  (`graph_transform_lib.py:1315-1370`).  True: bf16 gradients cross NVLink as bf16 and
+  are widened / accumulated in fp32 by the owner, ScaleGradients runs on the sender;
+  False: the sender widens to fp32 (2x the wire bytes) and the owner scales.
 """
 from .consts import RUN_OPTIONS, RUN_OPTION_ALIASES
 

@@ -59,6 +59,8 @@ _SIGS = {
     "px_allreduce_twoshot": (c_int, [PP, c_void_p, c_void_p, c_int, c_int, c_size_t,
                                      c_int, c_float, c_void_p, c_int, c_int, c_int,
                                      c_void_p]),
+    "px_allreduce_twoshot_bulk": (c_int, [PP, c_void_p, c_void_p, c_int, c_int, c_size_t,
+                                          c_int, c_float, c_int, c_int, c_int, c_void_p]),
     "px_allreduce_oneshot": (c_int, [c_void_p, c_void_p, PP, c_size_t, c_void_p,
                                      c_void_p, c_int, c_size_t, c_int, c_float,
                                      c_void_p, c_int, c_int, c_int, c_void_p]),

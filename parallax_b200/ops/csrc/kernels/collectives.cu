@@ -80,6 +80,87 @@ px_allreduce_twoshot_kernel(PeerPtrs rot, uint32_t* const* pads, uint32_t* epoch
   px_block_barrier(pads, epoch_ctr, ch_end, rank, W);
 }
 
+
+// ---------------------------------------------------------------------------
+// TMA variant of the two-shot all-reduce (measurement for SURVEY §7.4 / the north star's
+// "TMA tiles for the dense reduction"): the reduce-scatter phase pulls every peer's slice with
+// `cp.async.bulk` (bulk async copy engine, global -> shared, mbarrier completion) into a
+// double-buffered shared-memory stage of W x PX_BULK_BYTES, the CTA sums the W tiles out of shared
+// memory in fp32 and stores the reduced tile into every peer (all-gather by store).  Same
+// barriers, same bytes over NVLink as `px_allreduce_twoshot_kernel`; only the load path differs
+// (TMA engine + SMEM instead of ld.global.v4 into registers).  Result in profiles/README.md.
+#define PX_BULK_BYTES 8192
+__device__ __forceinline__ uint32_t cvta_smem(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+template <typename T, int W>
+__global__ void __launch_bounds__(256)
+px_allreduce_twoshot_bulk_kernel(PeerPtrs rot, uint32_t* const* pads, uint32_t* epoch_ctr,
+                                 int ch_start, int ch_end, size_t n, float scale, int rank) {
+  constexpr int VN = Vec16<T>::N;
+  extern __shared__ __align__(128) uint8_t bulk_smem[];       // [2][W][PX_BULK_BYTES]
+  __shared__ __align__(8) uint64_t full[2];
+  px_block_barrier(pads, epoch_ctr, ch_start, rank, W);
+  const size_t slice_bytes = n / W * sizeof(T);               // multiple of 16
+  const size_t base_bytes = (size_t)rank * slice_bytes;
+  const size_t nchunks = (slice_bytes + PX_BULK_BYTES - 1) / PX_BULK_BYTES;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cvta_smem(&full[s])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](size_t c, int stage) {
+    const size_t off = c * PX_BULK_BYTES;
+    const uint32_t bytes = (uint32_t)min((size_t)PX_BULK_BYTES, slice_bytes - off);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::
+                 "r"(cvta_smem(&full[stage])), "r"(bytes * W) : "memory");
+#pragma unroll
+    for (int p = 0; p < W; ++p)
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+          ::"r"(cvta_smem(bulk_smem + ((size_t)stage * W + p) * PX_BULK_BYTES)),
+            "l"(reinterpret_cast<const char*>(rot.p[p]) + base_bytes + off), "r"(bytes),
+            "r"(cvta_smem(&full[stage])) : "memory");
+  };
+  size_t it = 0;
+  if (threadIdx.x == 0 && (size_t)blockIdx.x < nchunks) issue(blockIdx.x, 0);
+  for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+    const int stage = (int)(it & 1);
+    const size_t cn = c + gridDim.x;
+    if (threadIdx.x == 0 && cn < nchunks) issue(cn, stage ^ 1);   // consumed two trips ago
+    const uint32_t parity = (uint32_t)((it >> 1) & 1);
+    asm volatile(
+        "{\n.reg .pred p;\nBW_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra BD_%=;\nbra BW_%=;\nBD_%=:\n}\n" ::"r"(cvta_smem(&full[stage])), "r"(parity)
+        : "memory");
+    const size_t off = c * PX_BULK_BYTES;
+    const int nv = (int)(min((size_t)PX_BULK_BYTES, slice_bytes - off) / 16);
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+      float acc[VN];
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int p = 0; p < W; ++p) {
+        float f[VN];
+        Vec16<T>::unpack(*reinterpret_cast<const uint4*>(
+                             bulk_smem + ((size_t)stage * W + p) * PX_BULK_BYTES + (size_t)v * 16), f);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) acc[i] += f[i];
+      }
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc[i] *= scale;
+      const uint4 out = Vec16<T>::pack(acc);
+#pragma unroll
+      for (int p = 0; p < W; ++p)
+        st_v4_stream(reinterpret_cast<char*>(rot.p[p]) + base_bytes + off + (size_t)v * 16, out);
+    }
+    __syncthreads();            // the stage may be refilled by the async proxy from here on
+  }
+  px_block_barrier(pads, epoch_ctr, ch_end, rank, W);
+}
+
 // ---------------------------------------------------------------------------
 // One-shot for latency-bound sizes: copy my input into my double-buffered
 // symmetric staging area, barrier, then every rank reads every peer's staging
@@ -190,6 +271,31 @@ int px_allreduce_twoshot(const void* const* bufs, void* pads_dev, void* epoch_ct
   px_allreduce_twoshot_kernel<T, W, (W <= 4 ? 4 : 2)><<<blocks, threads, 0, stream>>>(       \
       R, (uint32_t* const*)pads_dev, (uint32_t*)epoch_ctr, ch_start, ch_end, n, scale,     \
       sumsq_out, rank)
+  if (dtype == 0) { PX_DISPATCH_WORLD(world, LAUNCH, float); }
+  else { PX_DISPATCH_WORLD(world, LAUNCH, __nv_bfloat16); }
+#undef LAUNCH
+  return (int)cudaGetLastError();
+}
+
+int px_allreduce_twoshot_bulk(const void* const* bufs, void* pads_dev, void* epoch_ctr,
+                              int ch_start, int ch_end, size_t n, int dtype, float scale, int rank,
+                              int world, int max_blocks, cudaStream_t stream) {
+  if (world < 1 || world > 8) return -3;
+  const PeerPtrs R = px_rotate(bufs, rank, world);
+  const int vn = dtype == 0 ? 4 : 8;
+  if (n % ((size_t)world * vn) != 0) return -1;
+  const size_t es = dtype == 0 ? 4 : 2;
+  const size_t chunks = (n / world * es + PX_BULK_BYTES - 1) / PX_BULK_BYTES;
+  int blocks = (int)(chunks < 1 ? 1 : (chunks > (size_t)max_blocks ? (size_t)max_blocks : chunks));
+  if (blocks > PX_MAX_BLOCKS) blocks = PX_MAX_BLOCKS;
+  const size_t smem = (size_t)2 * world * PX_BULK_BYTES;
+#define LAUNCH(T, W)                                                                          \
+  do {                                                                                        \
+    cudaFuncSetAttribute(px_allreduce_twoshot_bulk_kernel<T, W>,                              \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8 * PX_BULK_BYTES); \
+    px_allreduce_twoshot_bulk_kernel<T, W><<<blocks, 256, smem, stream>>>(                    \
+        R, (uint32_t* const*)pads_dev, (uint32_t*)epoch_ctr, ch_start, ch_end, n, scale, rank); \
+  } while (0)
   if (dtype == 0) { PX_DISPATCH_WORLD(world, LAUNCH, float); }
   else { PX_DISPATCH_WORLD(world, LAUNCH, __nv_bfloat16); }
 #undef LAUNCH

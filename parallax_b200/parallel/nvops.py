@@ -41,6 +41,17 @@ def allreduce_twoshot(heap, buf_cptrs, n, dtype, scale, channels, sumsq=None,
         _s(stream)), "allreduce_twoshot")
 
 
+def allreduce_twoshot_bulk(heap, buf_cptrs, n, dtype, scale, channels, max_blocks=128,
+                           stream=None):
+    """TMA (cp.async.bulk) variant of the two-shot all-reduce — kept for the measurement in
+    profiles/README.md; the engine uses the ld.global / multimem kernels."""
+    L = ops.lib()
+    _count()
+    ops.check(L.px_allreduce_twoshot_bulk(
+        buf_cptrs, _p(heap.pads_dev()), _p(heap.epoch), channels[0], channels[1], n, DT[dtype],
+        scale, heap.rank, heap.world, max_blocks, _s(stream)), "allreduce_twoshot_bulk")
+
+
 def allreduce_oneshot(heap, src, dst, stage_buf, n, dtype, scale, channel,
                       sumsq=None, max_blocks=8, stream=None):
     L = ops.lib()

@@ -46,6 +46,38 @@ def test_allreduce_twoshot(world, dtype):
         f.close()
 
 
+@pytest.mark.parametrize("world,dtype", [(2, torch.bfloat16), (4, torch.float32),
+                                         (8, torch.bfloat16)])
+def test_allreduce_twoshot_bulk_tma_variant(world, dtype):
+    """cp.async.bulk (TMA engine -> shared memory) variant of the reduce-scatter phase: same
+    result as the register variant, several chunks per CTA so both stages are re-used."""
+    from parallax_b200.parallel import nvops
+    from parallax_b200.parallel.symmetric import CH_COMM
+    fabs = _setup(world)
+    es = 4 if dtype == torch.float32 else 2
+    n = world * (8192 // es) * 5 + world * 8 * 3            # 5 full chunks + a partial one
+    bufs = [f.heap.alloc(n * 4, "x") for f in fabs]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    xs = []
+    for b in bufs:
+        t = b.tensor(dtype, n)
+        t.copy_(torch.randn(n, device="cuda", generator=g))
+        xs.append(t.float().clone())
+    ref = torch.stack(xs).sum(0) / world
+    torch.cuda.synchronize()
+    for r, f in enumerate(fabs):
+        nvops.allreduce_twoshot_bulk(f.heap, bufs[r].c_ptrs(), n, dtype, 1.0 / world, CH_COMM,
+                                     max_blocks=2, stream=f.comm_stream)
+    torch.cuda.synchronize()
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    for b in bufs:
+        torch.testing.assert_close(b.tensor(dtype, n).float(), ref, rtol=tol, atol=tol)
+    for b in bufs[1:]:
+        assert torch.equal(b.tensor(dtype, n), bufs[0].tensor(dtype, n))
+    for f in fabs:
+        f.close()
+
+
 @pytest.mark.parametrize("world", [2, 8])
 def test_allreduce_oneshot_repeated(world):
     from parallax_b200.parallel import nvops

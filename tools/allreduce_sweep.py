@@ -86,6 +86,11 @@ while size <= args.max_bytes:
                                                        1.0, CH_USER, max_blocks=args.blocks),
                        args.iters)
         algo = "twoshot"
+    t_bulk = None
+    if size > args.oneshot_max:
+        t_bulk = timed(lambda: nvops.allreduce_twoshot_bulk(heap, sbuf.c_ptrs(), npad,
+                                                            torch.bfloat16, 1.0, CH_USER,
+                                                            max_blocks=args.blocks), args.iters)
     t_nvls = None
     if mcbuf is not None and size >= 65536:
         mx = mcbuf.tensor(torch.bfloat16, npad)
@@ -104,6 +109,8 @@ while size <= args.max_bytes:
     f = 2.0 * (W - 1) / W
     row = {"bytes": size, "algo": algo, "ours_us": t_ours * 1e6, "nccl_us": t_nccl * 1e6,
            "nvls_us": None if t_nvls is None else t_nvls * 1e6,
+           "tma_bulk_us": None if t_bulk is None else t_bulk * 1e6,
+           "tma_bulk_busbw_GBs": None if t_bulk is None else size / t_bulk * f / 1e9,
            "nvls_busbw_GBs": None if t_nvls is None else size / t_nvls * f / 1e9,
            "ours_busbw_GBs": size / t_ours * f / 1e9, "nccl_busbw_GBs": size / t_nccl * f / 1e9,
            "speedup": t_nccl / t_ours, "n_gpus": W}
@@ -113,7 +120,9 @@ while size <= args.max_bytes:
               % (size, algo, row["ours_us"], row["ours_busbw_GBs"], row["nccl_us"],
                  row["nccl_busbw_GBs"], row["speedup"]) +
               ("" if t_nvls is None else "   nvls %9.1f us (%7.1f GB/s bus)" %
-               (row["nvls_us"], row["nvls_busbw_GBs"])), flush=True)
+               (row["nvls_us"], row["nvls_busbw_GBs"])) +
+              ("" if t_bulk is None else "   tma-bulk %9.1f us (%7.1f GB/s bus)" %
+               (row["tma_bulk_us"], row["tma_bulk_busbw_GBs"])), flush=True)
     size *= 4
 if rank == 0 and args.out:
     os.makedirs(os.path.dirname(args.out), exist_ok=True)

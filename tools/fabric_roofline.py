@@ -107,9 +107,19 @@ def dense(use_mc):
     phases = {"start_wait_us": (st_[1] - st_[0]) / 1e3, "loop_cta0_us": (st_[2] - st_[1]) / 1e3,
               "to_last_cta_fenced_us": (st_[3] - st_[2]) / 1e3,
               "end_wait_us": (st_[4] - st_[3]) / 1e3}
-    link_in = (W - 1) / W * sl * 2 if not use_mc else sl * 2      # bytes pulled per rank
-    link_out = (W - 1) * sl * 2 if not use_mc else sl * 2         # parameter stores leaving
-    hbm = sl * (2 + 8 + 8 + 8 + 2) + (0 if use_mc else 0)
+    # NVLink bytes per GPU and direction.  P2P: I pull my slice from W-1 peers (in) and the
+    # peers pull theirs from me (out), then I store my updated slice into W-1 peers (out) and
+    # receive theirs (in).  NVLS: the switch still fetches every GPU's whole gradient (out)
+    # but returns only my reduced slice (in); parameters leave once (multimem.st) and arrive
+    # replicated by the switch (in).
+    rs = (W - 1) * sl * 2                       # bytes of one phase in the busier direction
+    if use_mc:
+        link_in = sl * 2 + rs
+        link_out = rs + sl * 2
+    else:
+        link_in = rs + rs
+        link_out = rs + rs
+    hbm = sl * (2 + 8 + 8 + 8 + 2) + (W - 1) * sl * 2 * 2      # own slice + serving the peers
     t_link = max(link_in, link_out) / (NVLINK * 1e3)              # us
     t_hbm = hbm / (HBM * 1e3)
     return {"us": us, "phases_last_launch": phases, "n_params": n, "nvlink_bytes_in": link_in, "nvlink_bytes_out": link_out,
