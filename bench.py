@@ -401,7 +401,7 @@ def main():
     if extras:
         from parallax_b200.utils import selfcheck as sc_
         try:
-            r = sc_.check(world, rank, "HYBRID", "adagrad", steps=4)
+            r = sc_.check(world, rank, "HYBRID", "adagrad", steps=4, resource="localhost:0")
             oks = comm.all_gather_object((r["ok"], r["max_abs_err"]))
             selfcheck = {"ok": all(o for o, _ in oks), "max_abs_err": max(e for _, e in oks),
                          "what": "MLP+embedding, HYBRID/adagrad, 4 steps vs single-device "

@@ -66,7 +66,8 @@ def oracle(world, steps, opt, sparse_scale=1.0):
 
 
 def train(world, rank, run_option="HYBRID", opt_name="adagrad", steps=4, average=True,
-          sync=True, sess_config=None, ps=None, nparts=5, ckpt_dir=None, save=False):
+          sync=True, sess_config=None, ps=None, nparts=5, ckpt_dir=None, save=False,
+          resource="localhost"):
     """Run the probe model through the public API; returns (losses, {name: weight},
     backend).  With `ckpt_dir` an existing checkpoint is restored first (training resumes
     at its global step) and `save=True` writes one after the last step."""
@@ -80,7 +81,9 @@ def train(world, rank, run_option="HYBRID", opt_name="adagrad", steps=4, average
         cfg.communication_config = parallax.CommunicationConfig(ps)
     if ckpt_dir:
         cfg.ckpt_config = parallax.CheckPointConfig(ckpt_dir=ckpt_dir)
-    sess, nw, wid, _ = parallax.parallel_run(g, "localhost", sync=sync, parallax_config=cfg)
+    # under torchrun the process is a worker whatever `resource` says; a stand-alone process
+    # must name ONE GPU ("localhost:0"), or the launcher would start a worker per visible GPU
+    sess, nw, wid, _ = parallax.parallel_run(g, resource, sync=sync, parallax_config=cfg)
     losses = []
     for s in range(sess.engine.global_step, steps):
         ids, labels = make_batch(s, world, rank)
@@ -97,10 +100,10 @@ def train(world, rank, run_option="HYBRID", opt_name="adagrad", steps=4, average
 
 
 def check(world, rank, run_option="HYBRID", opt_name="adagrad", steps=4, average=True,
-          sess_config=None, ps=None, rtol=2e-4, atol=2e-5):
+          sess_config=None, ps=None, rtol=2e-4, atol=2e-5, resource="localhost"):
     """-> {"ok", "max_abs_err", "backend"} for this rank."""
     _, w, backend = train(world, rank, run_option, opt_name, steps, average,
-                          sess_config=sess_config, ps=ps)
+                          sess_config=sess_config, ps=ps, resource=resource)
     _, ref = oracle(world, steps, make_opt(opt_name), 1.0 if average else float(world))
     err, ok = 0.0, True
     for n, r in ref.items():
