@@ -106,7 +106,17 @@ struct GemmArgs {
   int k_per_split;             // multiple of BK
 };
 
-template <int BN, int STAGES>
+// CLUSTER = true: the K-splits of one output tile form a thread-block cluster (1,1,splits) and
+// reduce their fp32 partial tiles through distributed shared memory — each CTA parks its tile in
+// its own SMEM (the drained pipeline stages), cluster barrier, then every CTA sums 1/splits of
+// the rows straight out of its peers' SMEM (`ld.shared::cluster`), adds the addend and stores
+// bf16.  No L2 `red.add`, no ticket, no read-back pass, no workspace.
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int BN, int STAGES, bool CLUSTER>
 __global__ void __launch_bounds__(256, 1)
 px_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b, GemmArgs g) {
@@ -192,7 +202,14 @@ px_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, r);
       const size_t off = (size_t)row * g.N + (size_t)n_tile * BN + c0;
-      if (row < g.M) {
+      if (CLUSTER) {
+        // park the fp32 partial in shared memory (row stride BN+4 floats)
+        float4* dst = reinterpret_cast<float4*>(smem) + ((size_t)(wq * 32 + lane) * (BN + 4) + c0) / 4;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          dst[i / 4] = make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                   __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+      } else if (row < g.M) {
         if (splitk) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
@@ -223,6 +240,42 @@ px_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)BN) : "memory");
+  }
+  if (CLUSTER) {
+    uint32_t crank, csize;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    cluster_sync_all();                               // every split's partial is in its SMEM
+    const int rows_per = BM / (int)csize;             // csize divides 128
+    const int nvec = rows_per * BN / 4;               // float4 groups this CTA reduces
+    const uint32_t my_base = smem_u32(smem);
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+      const int rr = (int)crank * rows_per + (v * 4) / BN, cc = (v * 4) % BN;
+      const uint32_t off_b = (uint32_t)(((size_t)rr * (BN + 4) + cc) * 4);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (uint32_t p = 0; p < csize; ++p) {
+        uint32_t raddr;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(my_base + off_b), "r"(p));
+        float4 x;
+        asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(raddr) : "memory");
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+      }
+      const int row = m_tile * BM + rr;
+      if (row < g.M) {
+        const size_t off = (size_t)row * g.N + (size_t)n_tile * BN + cc;
+        if (g.addend) {
+          const uint2 a2 = *reinterpret_cast<const uint2*>(g.addend + off);
+          acc.x += __uint_as_float(a2.x << 16); acc.y += __uint_as_float(a2.x & 0xffff0000u);
+          acc.z += __uint_as_float(a2.y << 16); acc.w += __uint_as_float(a2.y & 0xffff0000u);
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+        *reinterpret_cast<uint2*>(g.C + off) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
+    }
+    cluster_sync_all();                               // nobody exits while a peer reads its SMEM
+    return;
   }
   if (gridDim.z > 1) {
     // last-arriving split for this tile finalises: ws (+addend) -> bf16 C, ws := 0
@@ -459,13 +512,16 @@ extern "C" {
 
 // C[M,N] = A[M,K] · B[N,K]^T (+ addend).  splits > 1 needs ws (fp32 [M,N], zero)
 // and tickets (uint32 [tiles], zero).  Returns 0 or a negative error.
+// cluster != 0: the splits of a tile reduce through DSMEM in a (1,1,splits) cluster (splits must
+// divide 128 and be <= 16; 16 needs the non-portable cluster size); ws / tickets unused.
 int px_gemm_tc(const void* A, const void* B, void* C, const void* addend, float* ws,
-               unsigned int* tickets, int M, int N, int K, int splits, int bn,
+               unsigned int* tickets, int M, int N, int K, int splits, int bn, int cluster,
                cudaStream_t stream) {
   using namespace tc;
   if (M % BM || K % BK || (bn != 64 && bn != 128) || N % bn) return -1;
   if (splits < 1 || K % (splits * BK)) return -2;
-  if (splits > 1 && (!ws || !tickets)) return -3;
+  if (cluster && (splits < 2 || splits > 16 || (BM % splits) != 0)) return -4;
+  if (splits > 1 && !cluster && (!ws || !tickets)) return -3;
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, A, M, K, BM);
   if (rc) return rc;
@@ -476,24 +532,59 @@ int px_gemm_tc(const void* A, const void* B, void* C, const void* addend, float*
   g.tickets = tickets; g.M = M; g.N = N; g.K = K; g.k_per_split = K / splits;
   dim3 grid(N / bn, M / BM, splits);
   constexpr int STAGES = 4;
+  if (cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = splits;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e;
+    if (bn == 128) {
+      constexpr int SMEM = STAGES * (BM * BK * 2 + 128 * BK * 2) + 1024 + 256;
+      static bool setc128 = false;
+      if (!setc128) {
+        cudaFuncSetAttribute(px_gemm_tc_kernel<128, STAGES, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaFuncSetAttribute(px_gemm_tc_kernel<128, STAGES, true>,
+                             cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        setc128 = true;
+      }
+      cfg.dynamicSmemBytes = SMEM;
+      e = cudaLaunchKernelEx(&cfg, px_gemm_tc_kernel<128, STAGES, true>, ta, tb, g);
+    } else {
+      constexpr int SMEM = STAGES * (BM * BK * 2 + 64 * BK * 2) + 1024 + 256;
+      static bool setc64 = false;
+      if (!setc64) {
+        cudaFuncSetAttribute(px_gemm_tc_kernel<64, STAGES, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        cudaFuncSetAttribute(px_gemm_tc_kernel<64, STAGES, true>,
+                             cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        setc64 = true;
+      }
+      cfg.dynamicSmemBytes = SMEM;
+      e = cudaLaunchKernelEx(&cfg, px_gemm_tc_kernel<64, STAGES, true>, ta, tb, g);
+    }
+    return e == cudaSuccess ? (int)cudaGetLastError() : (int)e;
+  }
   if (bn == 128) {
     constexpr int SMEM = STAGES * (BM * BK * 2 + 128 * BK * 2) + 1024 + 256;
     static bool set128 = false;
     if (!set128) {
-      cudaFuncSetAttribute(px_gemm_tc_kernel<128, STAGES>,
+      cudaFuncSetAttribute(px_gemm_tc_kernel<128, STAGES, false>,
                            cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
       set128 = true;
     }
-    px_gemm_tc_kernel<128, STAGES><<<grid, 256, SMEM, stream>>>(ta, tb, g);
+    px_gemm_tc_kernel<128, STAGES, false><<<grid, 256, SMEM, stream>>>(ta, tb, g);
   } else {
     constexpr int SMEM = STAGES * (BM * BK * 2 + 64 * BK * 2) + 1024 + 256;
     static bool set64 = false;
     if (!set64) {
-      cudaFuncSetAttribute(px_gemm_tc_kernel<64, STAGES>,
+      cudaFuncSetAttribute(px_gemm_tc_kernel<64, STAGES, false>,
                            cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
       set64 = true;
     }
-    px_gemm_tc_kernel<64, STAGES><<<grid, 256, SMEM, stream>>>(ta, tb, g);
+    px_gemm_tc_kernel<64, STAGES, false><<<grid, 256, SMEM, stream>>>(ta, tb, g);
   }
   return (int)cudaGetLastError();
 }

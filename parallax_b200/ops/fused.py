@@ -213,6 +213,9 @@ class _LSTMLayerFn(torch.autograd.Function):
         from . import gemm as _gemm
         use_tc = (dt == torch.bfloat16 and Bsz % 128 == 0 and P % 64 == 0 and
                   (4 * S) % 1024 == 0 and Wh.is_contiguous())
+        # K-splits of the dh product: 8 CTAs per tile reducing through DSMEM in a cluster
+        # (8.7 us at the LM1B shape) or 16 through the L2 workspace (11.5 us)
+        ksp = 8 if _gemm.cluster_default() else 16
         WhT = None if use_tc else Wh.t().contiguous()
         st = _stream()
 
@@ -301,7 +304,7 @@ class _LSTMLayerFn(torch.autograd.Function):
                         dh_chunk(t, pending_hi)
                     wgrad(t, pending_hi)
                     pending_hi = t
-            dh_rec = _gemm.gemm_tn(dgates[0], Wh, splits=16, bn=64) if use_tc \
+            dh_rec = _gemm.gemm_tn(dgates[0], Wh, splits=ksp, bn=64) if use_tc \
                 else torch.mm(dgates[0], WhT_v)
             ws.wait_stream(cur)
             with torch.cuda.stream(ws):
@@ -316,12 +319,12 @@ class _LSTMLayerFn(torch.autograd.Function):
                                           1 if tc else 0, st), "lstm_cell_bwd")
                 if t > 0:
                     if use_tc:
-                        _gemm.gemm_tn(dgates[t], Wh, addend=dH[t - 1], splits=16, bn=64,
+                        _gemm.gemm_tn(dgates[t], Wh, addend=dH[t - 1], splits=ksp, bn=64,
                                       out=dh_tot[t - 1])
                     else:
                         torch.addmm(dH[t - 1], dgates[t], WhT, out=dh_tot[t - 1])
                 else:
-                    dh_rec = _gemm.gemm_tn(dgates[0], Wh, splits=16, bn=64) if use_tc \
+                    dh_rec = _gemm.gemm_tn(dgates[0], Wh, splits=ksp, bn=64) if use_tc \
                         else torch.mm(dgates[0], WhT)
                 if t in bounds[1:-1]:
                     wgrad(t, pending_hi)

@@ -14,7 +14,7 @@ from . import lib as _lib, check as _check, register_signatures
 
 _vp, _i = ctypes.c_void_p, ctypes.c_int
 register_signatures({
-    "px_gemm_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "px_gemm_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
 })
 
 _ws_cache = {}
@@ -46,7 +46,14 @@ def supported(A, Bt):
             A.data_ptr() % 16 == 0 and Bt.data_ptr() % 16 == 0)
 
 
-def gemm_tn(A, Bt, addend=None, splits=None, out=None, bn=None):
+def cluster_default():
+    """Split-K reduction through distributed shared memory (thread-block cluster of the K-splits)
+    instead of L2 atomics + ticket + read-back; `PARALLAX_GEMM_CLUSTER=0` selects the latter."""
+    import os
+    return os.environ.get("PARALLAX_GEMM_CLUSTER", "1") != "0"
+
+
+def gemm_tn(A, Bt, addend=None, splits=None, out=None, bn=None, cluster=None):
     M, K = A.shape
     N = Bt.shape[0]
     assert Bt.shape[1] == K
@@ -56,8 +63,11 @@ def gemm_tn(A, Bt, addend=None, splits=None, out=None, bn=None):
         splits = pick_splits(M, N, K, bn)
     if out is None:
         out = torch.empty(M, N, dtype=torch.bfloat16, device=A.device)
+    if cluster is None:
+        cluster = cluster_default()
+    cluster = bool(cluster) and 2 <= splits <= 16 and 128 % splits == 0
     ws = tk = None
-    if splits > 1:
+    if splits > 1 and not cluster:
         ws, tk = _workspace(M, N, A.device)
     from ..parallel import nvops
     nvops.launches["n"] += 1
@@ -66,6 +76,6 @@ def gemm_tn(A, Bt, addend=None, splits=None, out=None, bn=None):
         _vp(addend.data_ptr()) if addend is not None else _vp(0),
         _vp(ws.data_ptr()) if ws is not None else _vp(0),
         _vp(tk.data_ptr()) if tk is not None else _vp(0), M, N, K, splits, bn,
-        _vp(torch.cuda.current_stream().cuda_stream))
+        1 if cluster else 0, _vp(torch.cuda.current_stream().cuda_stream))
     _check(rc, "gemm_tc")
     return out

@@ -54,8 +54,12 @@ def a_today():
 
 timed("A  mm(128x512x2048) + tc splitK16 (128x8192x512)+addend", a_today)
 timed("A1 mm(128x512x2048) cuBLAS alone", lambda: torch.mm(dh, WPT, out=dm))
-timed("A2 tc splitK16 128x8192->512 alone",
-      lambda: G.gemm_tn(dg, Wh, addend=dH, splits=16, bn=64, out=out_h))
+timed("A2 tc splitK16 128x8192->512 alone (L2 red.add + ticket + read-back)",
+      lambda: G.gemm_tn(dg, Wh, addend=dH, splits=16, bn=64, out=out_h, cluster=False))
+timed("A3 tc splitK16, 16-CTA cluster DSMEM reduction",
+      lambda: G.gemm_tn(dg, Wh, addend=dH, splits=16, bn=64, out=out_h, cluster=True))
+timed("A4 tc splitK8, 8-CTA cluster DSMEM reduction",
+      lambda: G.gemm_tn(dg, Wh, addend=dH, splits=8, bn=64, out=out_h, cluster=True))
 WcT = Wc.t()
 timed("B  cuBLAS addmm(DMH, dg[128x8192], Wc^T[8192x2048])",
       lambda: torch.addmm(DMH, dg, WcT, out=dm))
@@ -77,3 +81,9 @@ timed("F  today fwd: addmm(xw, h[128x512], Wh) + mm(m[128x2048], W_P)",
       lambda: (torch.addmm(xw, h, Wh, out=gp), torch.mm(m, W_P, out=h2)))
 timed("F' fused W fwd: addmm(xw, m[128x2048], W'[2048x8192])",
       lambda: torch.addmm(xw, m, Wf, out=gp))
+# forward projection h = m @ W_P on the cluster split-K kernel (needs W_P^T, K-contiguous)
+WPt = W_P.t().contiguous()
+timed("F1 cuBLAS mm(m[128x2048], W_P[2048x512])", lambda: torch.mm(m, W_P, out=h2))
+for sp in (2, 4, 8):
+    timed("F2 tc cluster splitK%d 128x2048->512" % sp,
+          lambda: G.gemm_tn(m, WPt, splits=sp, bn=64, out=h2, cluster=True))
