@@ -227,6 +227,19 @@ class TrainEngine(object):
             # NCCL — for jobs spanning several NVLink domains
             dev = torch.device("cpu") if self.backend == "host" else comm.device
             self._lib_device = dev
+            # byte-greedy placement of every sparse variable's partitions on the owners — the
+            # same rule as the NVLink fabric (`ps/between_graph_parallel.py:49-70`)
+            from .layout import assign_owners
+            from .. import optim as _optim
+            nsl = _optim.NUM_SLOTS[g.sparse_optimizer.kind] if g.sparse_optimizer else 0
+            items = []
+            for path, mod in sorted(self.analysis.sparse_modules.items()):
+                info = self.analysis.variables[path + ".weight" if path else "weight"]
+                rows = (int(mod.weight.shape[0]) + info.partitions - 1) // info.partitions
+                items.append((path, info.partitions,
+                              rows * ((int(mod.weight.shape[1]) + 3) // 4 * 16) * (1 + nsl)))
+            placed = assign_owners(items, comm.world) \
+                if bool(cfg.communication_config.ps_config.boundary_among_servers) else {}
             for path, mod in self.analysis.sparse_modules.items():
                 pname = path + ".weight" if path else "weight"
                 info = self.analysis.variables[pname]
@@ -236,7 +249,8 @@ class TrainEngine(object):
                     part.strategy if part is not None else "mod",
                     g.sparse_optimizer, comm, self.route, g, cfg,
                     init={"seed": getattr(mod, "init_seed", 1234),
-                          "scale": getattr(mod, "init_scale", 0.05)}, device=dev)
+                          "scale": getattr(mod, "init_scale", 0.05)}, device=dev,
+                    owners=placed.get(path))
                 adapter = _HostTableAdapter(t)
                 self.tables[pname] = adapter
                 _set_submodule(self.model, path, ShardedEmbedding(adapter))

@@ -151,7 +151,7 @@ class HostSparseTable(object):
     """One sparse variable (embedding table) on the host fabric."""
 
     def __init__(self, name, weight, num_partitions, strategy, optimizer, comm,
-                 route, graph, config, init=None, device=None):
+                 route, graph, config, init=None, device=None, owners=None):
         self.name = name
         self.device = torch.device("cpu") if device is None else torch.device(device)
         self.comm = comm
@@ -160,7 +160,7 @@ class HostSparseTable(object):
         self.V, self.D = int(weight.shape[0]), int(weight.shape[1])
         self.replicated = route.sparse == modes.SPARSE_ALLGATHER
         self.layout = TableLayout(self.V, num_partitions, comm.world, strategy,
-                                  replicated=self.replicated)
+                                  replicated=self.replicated, owners=owners)
         self.average = bool(config.average_sparse)
         self.local_aggregation = bool(
             config.communication_config.ps_config.local_aggregation)

@@ -488,3 +488,61 @@ def test_horovod_environment_names_are_honoured():
     assert env["PARALLAX_TIMELINE"] == "/tmp/t.json" and env["PARALLAX_CACHE_CAPACITY"] == "64"
     assert env["PARALLAX_STALL_CHECK_TIME_SECONDS"] == "9"        # an explicit setting wins
     assert sorted(adopted) == ["PARALLAX_CACHE_CAPACITY", "PARALLAX_TIMELINE"]
+
+
+def test_byte_greedy_placement_and_owner_chunks():
+    """`layout.assign_owners` = the reference's GreedyLoadBalancingStrategy over ALL sparse
+    variables; `TableLayout` with an explicit owner map enumerates exactly the same rows chunk
+    by chunk (`owner_chunks`) as all at once, for both partition strategies."""
+    from parallax_b200.parallel.layout import TableLayout, assign_owners
+    placed = assign_owners([("big", 5, 100), ("small", 5, 10), ("tiny", 3, 1)], 2)
+    load = [0, 0]
+    for key, nbytes in (("big", 100), ("small", 10), ("tiny", 1)):
+        for o in placed[key]:
+            load[o] += nbytes
+    assert placed["big"] == [0, 1, 0, 1, 0]            # equal sizes: round-robin
+    assert abs(load[0] - load[1]) <= 100               # the small tables fill the lighter owner
+    assert placed["small"].count(1) > placed["small"].count(0)
+    for strategy in ("mod", "div"):
+        for V, P, W in ((1003, 8, 3), (17, 32, 8), (64, 5, 2)):
+            owners = assign_owners([("a", P, 7), ("b", P, 3)], W)["b"]
+            L = TableLayout(V, P, W, strategy, owners=owners)
+            seen = 0
+            for o in range(W):
+                g, l = L.global_ids_of_owner(o)
+                gs, ls = [], []
+                for g2, l2 in L.owner_chunks(o, chunk=13):
+                    gs.append(g2)
+                    ls.append(l2)
+                g3 = torch.cat(gs) if gs else torch.zeros(0, dtype=torch.int64)
+                l3 = torch.cat(ls) if ls else torch.zeros(0, dtype=torch.int64)
+                assert sorted(zip(g.tolist(), l.tolist())) == sorted(zip(g3.tolist(), l3.tolist()))
+                assert bool((L.owner_of(g3) == o).all()) and (l3.numel() == 0 or
+                                                              int(l3.max()) < L.rows_local)
+                seen += g3.numel()
+            assert seen == V
+    with pytest.raises(ValueError):
+        TableLayout(10, 4, 2, owners=[0, 1, 2, 0])      # owner out of range
+
+
+def test_placement_planner_cli(capsys):
+    from parallax_b200.tools import launch_ps
+    rc = launch_ps.main(["--owners", "3", "a:1000:64:5:1", "w:793470:512:32:1+b:793470:1:32:1"])
+    out = capsys.readouterr().out
+    assert rc == 0 and "byte-greedy" in out and "owner 2:" in out and "w+b" in out
+    assert launch_ps.main(["--owners", "2", "a:100:8:4+b:100:8:5"]) == 2      # group mismatch
+
+
+def test_lookup_many_defer_on_plain_modules():
+    """Without an engine (plain torch modules / host fabric) `lookup_many` is the sequence of
+    lookups; `defer=True` returns a handle with the same rows and gradients still flow."""
+    import parallax_b200 as parallax
+    a = parallax.nn.Embedding(10, 4)
+    b = parallax.nn.Embedding(10, 1)
+    ids = torch.tensor([1, 3, 3])
+    ra, rb = parallax.nn.lookup_many([a, b], ids)
+    h = parallax.nn.lookup_many([a, b], ids, defer=True)
+    ra2, rb2 = h.rows()
+    assert torch.equal(ra, ra2) and torch.equal(rb, rb2)
+    (ra2.sum() + rb2.sum()).backward()
+    assert a.weight.grad is not None and b.weight.grad is not None
