@@ -66,7 +66,8 @@ def save_sharded(engine, path, is_chief):
     if is_chief:
         os.makedirs(path, exist_ok=True)
     comm.barrier()
-    torch.cuda.synchronize(comm.device)
+    if comm.is_cuda:
+        torch.cuda.synchronize(comm.device)
     manifest = {"format": 2, "global_step": engine.global_step, "world": comm.world,
                 "run_option": engine.run_option, "sparse": {}}
     for name, t in sorted(engine.tables.items()):

@@ -546,3 +546,81 @@ def test_lookup_many_defer_on_plain_modules():
     assert torch.equal(ra, ra2) and torch.equal(rb, rb2)
     (ra2.sum() + rb2.sum()).backward()
     assert a.weight.grad is not None and b.weight.grad is not None
+
+
+def test_sharded_checkpoint_resharding_logic(tmp_path):
+    """`checkpoint.save_sharded` / `load_sharded` with stand-in tables: one shard file per owner,
+    manifest with the placement, own-file fast path when the placement is unchanged and a full
+    re-scatter into a different partitioning otherwise."""
+    from parallax_b200 import checkpoint as ckpt
+    from parallax_b200.parallel.layout import TableLayout
+
+    class _Comm(object):
+        distributed, is_cuda, device = False, False, torch.device("cpu")
+
+        def __init__(self, rank, world):
+            self.rank, self.world = rank, world
+
+        def barrier(self):
+            pass
+
+    class _Table(object):
+        def __init__(self, V, D, P, W, rank, full=None, slot=None):
+            self.V, self.D, self.nslots, self.replicated, self.rank = V, D, 1, False, rank
+            self.layout = TableLayout(V, P, W, "mod")
+            self.w = torch.zeros(self.layout.rows_local, D)
+            self.s = torch.zeros(self.layout.rows_local, D)
+            if full is not None:
+                for g, l in self.layout.owner_chunks(rank):
+                    self.w[l] = full[g]
+                    self.s[l] = slot[g]
+
+        def local_rows(self, what="weight"):
+            src = self.w if what == "weight" else self.s
+            gs, rows = [], []
+            for g, l in self.layout.owner_chunks(self.rank):
+                gs.append(g)
+                rows.append(src[l])
+            return torch.cat(gs), torch.cat(rows)
+
+        def load_rows(self, ids, rows, what="weight"):
+            own = self.layout.owner_of(ids) == self.rank
+            dst = self.w if what == "weight" else self.s
+            dst[self.layout.local_row_of(ids[own])] = rows[own]
+
+    class _Engine(object):
+        dense, global_step, run_option = None, 7, "HYBRID"
+
+        def __init__(self, comm, table):
+            self.comm, self.tables = comm, {"emb.weight": table}
+            self.model = torch.nn.Linear(1, 1)
+
+    V, D = 101, 3
+    full, slot = torch.randn(V, D), torch.rand(V, D)
+    d = str(tmp_path / "model.ckpt-7")
+    os.makedirs(d)
+    for r in range(2):                                   # two ranks save, one after the other
+        ckpt.save_sharded(_Engine(_Comm(r, 2), _Table(V, D, 4, 2, r, full, slot)), d, r == 0)
+    files = sorted(os.listdir(d))
+    assert files == ["dense.pt", "manifest.json", "sparse-emb.weight-rank0.pt",
+                     "sparse-emb.weight-rank1.pt"]
+    assert ckpt.latest_checkpoint(str(tmp_path)) == d
+    # same placement: every rank needs only its own shard
+    t0 = _Table(V, D, 4, 2, 1)
+    os.rename(os.path.join(d, files[2]), os.path.join(d, files[2] + ".away"))
+    ckpt.load_sharded(_Engine(_Comm(1, 2), t0), d)
+    g, l = t0.layout.global_ids_of_owner(1)
+    torch.testing.assert_close(t0.w[l], full[g])
+    torch.testing.assert_close(t0.s[l], slot[g])
+    os.rename(os.path.join(d, files[2] + ".away"), os.path.join(d, files[2]))
+    # different world size and partition count: rows are re-scattered to their new owners
+    got_w, got_s = torch.zeros(V, D), torch.zeros(V, D)
+    for r in range(3):
+        t = _Table(V, D, 5, 3, r)
+        eng = _Engine(_Comm(r, 3), t)
+        ckpt.load_sharded(eng, d)
+        assert eng.global_step == 7
+        g, l = t.layout.global_ids_of_owner(r)
+        got_w[g], got_s[g] = t.w[l], t.s[l]
+    torch.testing.assert_close(got_w, full)
+    torch.testing.assert_close(got_s, slot)
