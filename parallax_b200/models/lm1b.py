@@ -108,57 +108,64 @@ class LM1B(nn.Module):
             -math.sqrt(3.0 / state_size), math.sqrt(3.0 / state_size)))
 
     def lstm(self, x, c, h):
-        """x: [B, T, E] -> outputs [B*T, P] (rows ordered like y.reshape(-1)),
-        final c, h.  One fused autograd node (`ops.fused.lstm_layer`)."""
+        """x: [T, B, E] (time-major) -> outputs [T*B, P] (rows ordered (t, b), a view of
+        the layer's output), final c, h.  One fused autograd node
+        (`ops.fused.lstm_layer`)."""
         from ..ops.fused import lstm_layer_stacked
-        Bsz, T, E = x.shape
-        H, c, h = lstm_layer_stacked(x.transpose(0, 1), self.W, self.B, self.W_P, c, h,
-                                     forget_bias=1.0)
-        out = H.transpose(0, 1)                      # [B, T, P]
+        T, Bsz, E = x.shape
+        out, c, h = lstm_layer_stacked(x, self.W, self.B, self.W_P, c, h, forget_bias=1.0)
         if self.training and self.keep_prob < 1.0:
             out = F.dropout(out, 1.0 - self.keep_prob)
-        return out.reshape(Bsz * T, -1), c, h
+        return out.reshape(T * Bsz, -1), c, h
 
     def forward(self, x, y, w=None, initial_state_c=None, initial_state_h=None):
         Bsz, T = x.shape
         dev = self.W.device
         dt = self.W.dtype
-        e = self.emb(x)
+        # Everything below is time-major (rows ordered (t, b)): the LSTM node consumes and
+        # produces [T, B, ·] and the loss is a mean over all rows, so transposing the
+        # [B, T] *ids* once replaces transposed copies of the [B, T, 512] activations and
+        # of their gradients.
+        e = self.emb(x.t())
         if e.dtype != dt:
             e = e.to(dt)
         if self.training and self.keep_prob < 1.0:
             e = F.dropout(e, 1.0 - self.keep_prob)
-        c = initial_state_c if initial_state_c is not None else \
-            torch.zeros(Bsz, self.state_size, device=dev, dtype=dt)
-        h = initial_state_h if initial_state_h is not None else \
+        c = initial_state_c.float() if initial_state_c is not None else \
+            torch.zeros(Bsz, self.state_size, device=dev, dtype=torch.float32)
+        h = initial_state_h.to(dt) if initial_state_h is not None else \
             torch.zeros(Bsz, self.projected_size, device=dev, dtype=dt)
-        targets = y.reshape(-1)
         sampled_mode = self.training and self.num_sampled > 0
         # the sampler and the softmax-table lookups do not depend on the LSTM: issue them
         # on a side stream so they run underneath the (latency-bound) recurrent chain
-        pre = self.prefetch_softmax(targets) if sampled_mode else None
-        inputs, c, h = self.lstm(e, c.float(), h.to(dt))
+        pre = self.prefetch_softmax(y) if sampled_mode else None
+        inputs, c, h = self.lstm(e, c, h)
+        row_w = None if w is None else w.t().reshape(-1)
         if sampled_mode:
-            loss = self.sampled_softmax_loss(inputs, targets, pre)
+            loss = self.sampled_softmax_loss(inputs, pre, row_w)
         else:
-            loss = self.full_softmax_loss(inputs, targets)
-        if w is not None:
-            loss = loss * w.reshape(-1).to(loss.dtype)
-        return {"loss": loss.mean(), "final_state_c": c.detach(),
-                "final_state_h": h.detach()}
+            loss = self.full_softmax_loss(inputs, y.t().reshape(-1))
+            if row_w is not None:
+                loss = loss * row_w.to(loss.dtype)
+            loss = loss.mean()
+        return {"loss": loss, "final_state_c": c.detach(), "final_state_h": h.detach()}
 
-    def prefetch_softmax(self, targets):
-        """Negative sampling + one fused lookup of (softmax_w, softmax_b) rows for
-        targets ∪ samples; on CUDA it runs on the side stream."""
-        N, S, V = targets.numel(), self.num_sampled, self.vocab_size
+    def prefetch_softmax(self, y):
+        """Time-major targets, negative sampling, one fused lookup of (softmax_w, softmax_b)
+        rows for targets ∪ samples and the ``bias - log Q`` correction; on CUDA all of it
+        runs on the side stream."""
+        S, V = self.num_sampled, self.vocab_size
         dev = self.W.device
 
         def work():
+            targets = y.t().reshape(-1).to(torch.int64)
             sampled, tries = log_uniform_sample_unique(S, V, dev)
-            ids = torch.cat([targets.to(torch.int64), sampled])
+            ids = torch.cat([targets, sampled])
             rows = pnn.lookup_many([self.softmax_w, self.softmax_b], ids, defer=True)
             logq = log_uniform_logq_unique(ids, tries, V)
-            return sampled, rows, logq
+            with torch.no_grad():
+                adj = rows._rows[1].detach().reshape(-1).float() - logq
+            return targets, sampled, rows, logq, adj
         if dev.type != "cuda":
             return work() + (None,)
         from ..ops import sinks
@@ -169,22 +176,21 @@ class LM1B(nn.Module):
             out = work()
         return out + (side,)
 
-    def sampled_softmax_loss(self, inputs, targets, pre=None):
-        from ..ops.fused import sampled_softmax_loss
-        N = targets.numel()
-        sampled, rows, logq, side = pre if pre is not None \
-            else self.prefetch_softmax(targets)
+    def sampled_softmax_loss(self, inputs, pre, row_w=None):
+        """mean sampled-softmax loss of `inputs` [T*B, P] (one fused node,
+        `ops.fused.sampled_softmax_head`)."""
+        from ..ops.fused import sampled_softmax_head
+        targets, sampled, rows, logq, adj, side = pre
         if side is not None:
             cur = torch.cuda.current_stream(inputs.device)
             cur.wait_stream(side)
-            for t in [sampled, logq] + list(rows._rows):
+            for t in [targets, sampled, logq, adj] + list(rows._rows):
                 t.record_stream(cur)
         # the rows enter the autograd graph HERE (late), so their gradients are handed to
         # the sparse group first thing in the backward pass, underneath the LSTM backward
         w_all, b_all = rows.rows()
-        b_all = b_all.squeeze(-1)
-        return sampled_softmax_loss(inputs, w_all[:N], w_all[N:], b_all[:N], b_all[N:],
-                                    logq[:N], logq[N:], targets, sampled)
+        return sampled_softmax_head(inputs, w_all, b_all, logq, targets, sampled,
+                                    row_w=row_w, adj=adj)
 
     def full_softmax_loss(self, inputs, targets):
         ids = torch.arange(self.vocab_size, device=inputs.device)

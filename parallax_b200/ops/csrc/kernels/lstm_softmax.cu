@@ -87,20 +87,39 @@ px_lstm_cell_bwd_kernel(const T* __restrict__ dm, float* __restrict__ dc,
 // One CTA per row.  logits[N,S] (in: h·w_s ; out: p_ij = softmax prob of the
 // sampled class j among {true, sampled}).  Row is held in registers
 // (ITEMS × 256 threads ≥ S).
-template <typename T, int ITEMS>
+// DOT: the true-class logit h_row · w_true_row (P elements) is computed here as well
+// (one launch instead of two casts, a multiply and a row reduction before this kernel).
+template <typename T, int ITEMS, bool DOT>
 __global__ void __launch_bounds__(256)
 px_sampled_softmax_kernel(T* __restrict__ logits, const float* __restrict__ true_dot,
                           const float* __restrict__ adj_true,   // b_true - logq_true  [N]
                           const float* __restrict__ adj_samp,   // b_samp - logq_samp  [S]
                           const long long* __restrict__ targets, const long long* __restrict__ sampled,
-                          float* __restrict__ loss, float* __restrict__ dtrue, int N, int S) {
+                          float* __restrict__ loss, float* __restrict__ dtrue, int N, int S,
+                          const T* __restrict__ h, const T* __restrict__ w_true, int P) {
   const int row = blockIdx.x;
   if (row >= N) return;
   __shared__ float s_red[8];
   __shared__ float s_bcast;
   T* x = logits + (size_t)row * S;
   const long long tgt = targets[row];
-  const float tl = true_dot[row] + adj_true[row];
+  float tl;
+  if (DOT) {
+    __shared__ float s_dot[8];
+    const T* hr = h + (size_t)row * P;
+    const T* wr = w_true + (size_t)row * P;
+    float part = 0.f;
+    for (int k = threadIdx.x; k < P; k += 256) part += to_f(hr[k]) * to_f(wr[k]);
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) s_dot[threadIdx.x >> 5] = part;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s_dot[k];          // same order in every thread
+    tl = t + adj_true[row];
+  } else {
+    tl = true_dot[row] + adj_true[row];
+  }
   float v[ITEMS];
   float mx = tl;
 #pragma unroll
@@ -151,6 +170,81 @@ px_sampled_softmax_kernel(T* __restrict__ logits, const float* __restrict__ true
   }
 }
 
+// 16-byte vectors of T (4 floats / 8 bf16)
+template <typename T> struct PxVec16;
+template <> struct PxVec16<float> {
+  static constexpr int N = 4;
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct PxVec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  float v[8];
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const unsigned w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const {
+    unsigned w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const unsigned*>(&b);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+px_ssm_bwd_kernel(T* __restrict__ G, const T* __restrict__ inputs, const T* __restrict__ w_true,
+                  const float* __restrict__ g, int g_stride, const float* __restrict__ row_w,
+                  const float* __restrict__ dtrue, float inv_n, T* __restrict__ gi,
+                  T* __restrict__ d_w_true, void* __restrict__ d_b_true, int db_bf16,
+                  T* __restrict__ grow_out, int N, int P) {
+  constexpr int V = PxVec16<T>::N;
+  const int per_row = P / V;
+  const long long total = (long long)N * per_row;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / per_row);
+    const int col = (int)(idx - (long long)row * per_row);
+    float grow = g[(size_t)row * g_stride] * inv_n;
+    if (row_w != nullptr) grow *= row_w[row];
+    const float gt = grow * dtrue[row];
+    const size_t off = (size_t)row * P + (size_t)col * V;
+    PxVec16<T> a, x, w, o;
+    a.load(G + off);
+    x.load(inputs + off);
+    w.load(w_true + off);
+#pragma unroll
+    for (int i = 0; i < V; ++i) o.v[i] = a.v[i] * grow + gt * w.v[i];
+    o.store(G + off);
+#pragma unroll
+    for (int i = 0; i < V; ++i) o.v[i] = x.v[i] * grow;
+    o.store(gi + off);
+#pragma unroll
+    for (int i = 0; i < V; ++i) o.v[i] = x.v[i] * gt;
+    o.store(d_w_true + off);
+    if (col == 0) {
+      if (db_bf16) reinterpret_cast<__nv_bfloat16*>(d_b_true)[row] = __float2bfloat16_rn(gt);
+      else reinterpret_cast<float*>(d_b_true)[row] = gt;
+      grow_out[row] = from_f<T>(grow);
+    }
+  }
+}
+
 extern "C" {
 
 int px_lstm_cell_fwd(const void* gates, const float* c_prev, void* act, float* c_new, void* m,
@@ -188,15 +282,62 @@ int px_sampled_softmax(void* logits, const float* true_dot, const float* adj_tru
                        float* loss, float* dtrue, int N, int S, int dtype, cudaStream_t stream) {
   if (S > 256 * 64) return -2;
 #define SS(T, I)                                                                          \
-  px_sampled_softmax_kernel<T, I><<<N, 256, 0, stream>>>((T*)logits, true_dot, adj_true,  \
-                                                         adj_samp, targets, sampled, loss, \
-                                                         dtrue, N, S)
+  px_sampled_softmax_kernel<T, I, false><<<N, 256, 0, stream>>>(                          \
+      (T*)logits, true_dot, adj_true, adj_samp, targets, sampled, loss, dtrue, N, S,      \
+      (const T*)nullptr, (const T*)nullptr, 0)
 #define SSD(T)                                                      \
   if (S <= 256 * 4) SS(T, 4); else if (S <= 256 * 8) SS(T, 8);      \
   else if (S <= 256 * 16) SS(T, 16); else if (S <= 256 * 32) SS(T, 32); else SS(T, 64)
   if (dtype == 0) { SSD(float); } else { SSD(__nv_bfloat16); }
 #undef SSD
 #undef SS
+  return (int)cudaGetLastError();
+}
+
+// Same, with the true-class dot product h[n]·w_true[n] computed in the kernel.
+int px_sampled_softmax_dot(void* logits, const void* h, const void* w_true, int P,
+                           const float* adj_true, const float* adj_samp,
+                           const long long* targets, const long long* sampled, float* loss,
+                           float* dtrue, int N, int S, int dtype, cudaStream_t stream) {
+  if (S > 256 * 64) return -2;
+#define SS(T, I)                                                                          \
+  px_sampled_softmax_kernel<T, I, true><<<N, 256, 0, stream>>>(                           \
+      (T*)logits, nullptr, adj_true, adj_samp, targets, sampled, loss, dtrue, N, S,       \
+      (const T*)h, (const T*)w_true, P)
+#define SSD(T)                                                      \
+  if (S <= 256 * 4) SS(T, 4); else if (S <= 256 * 8) SS(T, 8);      \
+  else if (S <= 256 * 16) SS(T, 16); else if (S <= 256 * 32) SS(T, 32); else SS(T, 64)
+  if (dtype == 0) { SSD(float); } else { SSD(__nv_bfloat16); }
+#undef SSD
+#undef SS
+  return (int)cudaGetLastError();
+}
+
+// Backward glue of the sampled-softmax head in one pass (was ~13 elementwise launches):
+//   grow[n] = g[n*g_stride] * inv_n * (row_w ? row_w[n] : 1)       per-row upstream gradient
+//   G (in: probs @ w_samp) -> d_inputs = G*grow + (grow*dtrue) * w_true
+//   gi = inputs * grow              (operand of d_w_samp = probs^T @ gi)
+//   d_w_true = (grow*dtrue) * inputs
+//   d_b_true[n] = grow*dtrue ;  grow_out[n] = grow   (operand of d_b_samp = probs^T @ grow)
+int px_ssm_bwd(void* G, const void* inputs, const void* w_true, const float* g, int g_stride,
+               const float* row_w, const float* dtrue, float inv_n, void* gi, void* d_w_true,
+               void* d_b_true, int db_bf16, void* grow_out, int N, int P, int dtype,
+               cudaStream_t stream) {
+  const int vec = dtype == 0 ? 4 : 8;
+  if (P % vec) return -2;
+  const long long total = (long long)N * (P / vec);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  if (dtype == 0)
+    px_ssm_bwd_kernel<float><<<blocks, 256, 0, stream>>>(
+        (float*)G, (const float*)inputs, (const float*)w_true, g, g_stride, row_w, dtrue, inv_n,
+        (float*)gi, (float*)d_w_true, d_b_true, db_bf16, (float*)grow_out, N, P);
+  else
+    px_ssm_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(
+        (__nv_bfloat16*)G, (const __nv_bfloat16*)inputs, (const __nv_bfloat16*)w_true, g,
+        g_stride, row_w, dtrue, inv_n, (__nv_bfloat16*)gi, (__nv_bfloat16*)d_w_true, d_b_true,
+        db_bf16, (__nv_bfloat16*)grow_out, N, P);
   return (int)cudaGetLastError();
 }
 

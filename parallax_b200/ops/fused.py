@@ -25,6 +25,10 @@ register_signatures({
     "px_lstm_cell_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "px_lstm_gates_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "px_sampled_softmax": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "px_sampled_softmax_dot": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i,
+                                    _vp]),
+    "px_ssm_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _i, _vp, _i, _i, _i,
+                        _vp]),
 })
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
@@ -104,6 +108,19 @@ def _bwd_fused_w():
     return os.environ.get("PARALLAX_LSTM_BWD_FUSEDW", "0")
 
 
+def _wpt_side():
+    """PARALLAX_LSTM_WPT_SIDE=0: transpose W_P at the head of the backward pass instead."""
+    import os
+    return os.environ.get("PARALLAX_LSTM_WPT_SIDE", "1") != "0"
+
+
+def _dbias_stream():
+    """PARALLAX_LSTM_DBIAS_STREAM=1: the bias gradient (a bandwidth-bound column sum over
+    dgates) runs on a second side stream, next to the compute-bound weight-gradient GEMMs."""
+    import os
+    return os.environ.get("PARALLAX_LSTM_DBIAS_STREAM", "1") != "0"
+
+
 def _wgrad_chunks(T):
     """How many pieces the weight-gradient GEMMs are cut into along time so that the
     earlier pieces run on the side stream underneath the (latency-bound) recurrent
@@ -146,6 +163,20 @@ class _LSTMLayerFn(torch.autograd.Function):
             bias_l = bias.index_select(0, perm)
         else:
             Wx_l, Wh_l, bias_l, WhT = Wx, Wh, bias, None
+        # W_P^T for the backward chain (dm_t = dh_t W_P^T as a plain NN GEMM): a 2 MB true
+        # transpose, 17 us of uncoalesced copy — done here on the side stream, underneath
+        # the forward chain, instead of at the head of the backward pass
+        ctx.WPT = None
+        if dev.type == "cuda" and any(ctx.needs_input_grad) and _wpt_side():
+            from . import sinks
+            cur = torch.cuda.current_stream(dev)
+            ws = sinks.side_stream(dev)
+            ws.wait_stream(cur)
+            with torch.cuda.stream(ws):
+                ctx.WPT = W_P.detach().t().contiguous()
+                ctx.WPT_ev = torch.cuda.Event()
+                ctx.WPT_ev.record(ws)
+            ctx.WPT.record_stream(cur)
         xw = torch.addmm(bias_l, x.view(T * Bsz, E), Wx_l).view(T, Bsz, 4 * S)
         act = torch.empty(T, Bsz, 4 * S, dtype=dt, device=dev)
         c_all = torch.empty(T + 1, Bsz, S, dtype=torch.float32, device=dev)
@@ -206,7 +237,11 @@ class _LSTMLayerFn(torch.autograd.Function):
         dh_rec = None if dhT is None else dhT.to(dt)
         dm = torch.empty(Bsz, S, dtype=dt, device=dev)
         # dm_t = dh_t @ W_P^T runs as a plain NN GEMM on a materialised W_P^T.
-        WPT = W_P.t().contiguous()
+        if ctx.WPT is not None:
+            torch.cuda.current_stream(dev).wait_event(ctx.WPT_ev)
+            WPT = ctx.WPT
+        else:
+            WPT = W_P.t().contiguous()
         # dh_{t-1} = dH_{t-1} + dgates_t @ Wh^T : Wh [P, 4S] is already the
         # K-contiguous "B^T" operand, so this skinny product (M=B, N=P, K=4S)
         # goes to our tcgen05 split-K kernel with the +dH addend fused in.
@@ -241,6 +276,7 @@ class _LSTMLayerFn(torch.autograd.Function):
         nchunks = _wgrad_chunks(T)
         bounds = [round(i * T / nchunks) for i in range(nchunks + 1)]   # over t, ascending
         state = {"first": True}
+        ws2 = sinks.side_stream(dev, 1) if (nchunks == 1 and _dbias_stream()) else None
 
         def wgrad(lo, hi):
             """accumulate the contribution of steps [lo, hi) (their dgates / dh_tot are final)"""
@@ -254,7 +290,8 @@ class _LSTMLayerFn(torch.autograd.Function):
                 if state["first"]:
                     torch.mm(hT, dg, out=dWh_o)
                     torch.mm(xT, dg, out=dWx_o)
-                    torch.sum(dg, 0, out=dbias_o)
+                    if ws2 is None:
+                        torch.sum(dg, 0, out=dbias_o)
                     torch.mm(mT, dh2, out=dWP_o)
                     state["first"] = False
                 else:
@@ -333,25 +370,40 @@ class _LSTMLayerFn(torch.autograd.Function):
         dg2 = dgates.view(T * Bsz, 4 * S)
         # dx first: the embedding gradient is what the rest of backward (and the sparse
         # push) is waiting for; the last weight-gradient chunk goes to the side stream
+        ev_b = None
+        if ws2 is not None:
+            # bandwidth-bound column sum: runs next to the compute-bound GEMMs below
+            ws2.wait_stream(cur)
+            with torch.cuda.stream(ws2):
+                torch.sum(dg2, 0, out=dbias_o)
+            ev_b = torch.cuda.Event()
+            ev_b.record(ws2)
+            dgates.record_stream(ws2)
+            dbias_o.record_stream(ws2)
         dx = (dg2 @ Wx.t()).view(T, Bsz, E)
         wgrad(0, pending_hi)
         ev = torch.cuda.Event()
         ev.record(ws)
+        if ev_b is None:
+            ev_b = ev
         for t_ in (dgates, dh_tot, x, h_all, m_all, dWh_o, dWx_o, dbias_o, dWP_o):
             t_.record_stream(ws)
         outs, plain = [], False
-        for ref, o, sunk in ((W_ref, dW if stacked else dWx_o, w_sunk),
-                             (bias_ref, dbias_o, b_sunk), (WP_ref, dWP_o, p_sunk)):
+        for ref, o, sunk, e_ in ((W_ref, dW if stacked else dWx_o, w_sunk, ev),
+                                 (bias_ref, dbias_o, b_sunk, ev_b), (WP_ref, dWP_o, p_sunk, ev)):
             if sunk:
                 # in the bucket already: hand it to the dense group directly (its fused
-                # reduce/update kernel waits for `ev`), nothing goes through AccumulateGrad
-                sinks.deliver(ref, ev)
+                # reduce/update kernel waits for the event), nothing goes through
+                # AccumulateGrad
+                sinks.deliver(ref, e_)
                 outs.append(None)
             else:
                 outs.append(o)
                 plain = True
         if plain or not stacked:
             cur.wait_event(ev)        # plain tensors are consumed on the current stream
+            if ev_b is not ev:
+                cur.wait_event(ev_b)
         dW_out, dbias, dW_P = outs
         dWh = None if stacked else dWh_o
         if tc:          # back to the caller's (plain) gate-column order
@@ -441,3 +493,137 @@ def sampled_softmax_loss(inputs, true_w, samp_w, true_b, samp_b, logq_true, logq
                                        logq_true, logq_samp, targets, sampled)
     return sampled_softmax_reference(inputs, true_w, samp_w, true_b, samp_b, logq_true,
                                      logq_samp, targets, sampled)
+
+
+# ---------------------------------------------------------------------------
+# the whole loss head as one node
+# ---------------------------------------------------------------------------
+def _head_enabled():
+    """PARALLAX_SSM_HEAD=0 falls back to `sampled_softmax_loss` + PyTorch glue."""
+    import os
+    return os.environ.get("PARALLAX_SSM_HEAD", "1") != "0"
+
+
+def _head_forward(inputs, w_all, adj, targets, sampled):
+    """-> (probs [N,S] in inputs.dtype, loss [N] fp32, dtrue [N] fp32).  `w_all` holds the
+    N true-class rows followed by the S sampled rows; `adj` = bias - log Q for the same
+    N + S positions."""
+    N, S = inputs.shape[0], w_all.shape[0] - inputs.shape[0]
+    P = inputs.shape[1]
+    logits = inputs @ w_all[N:].t()                                # [N, S]
+    if inputs.is_cuda:
+        loss = torch.empty(N, dtype=torch.float32, device=inputs.device)
+        dtrue = torch.empty(N, dtype=torch.float32, device=inputs.device)
+        _check(_lib().px_sampled_softmax_dot(
+            _p(logits), _p(inputs), _p(w_all), P, _p(adj), _vp(adj.data_ptr() + 4 * N),
+            _p(targets), _p(sampled), _p(loss), _p(dtrue), N, S, _DT[inputs.dtype], _stream()),
+            "sampled_softmax_dot")
+        _count(1)
+        return logits, loss, dtrue
+    # same math in PyTorch (host fabric / CPU tests of the node's algebra)
+    tl = (inputs.float() * w_all[:N].float()).sum(-1) + adj[:N]
+    a = logits.float() + adj[N:]
+    a = a.masked_fill(targets.unsqueeze(1) == sampled.unsqueeze(0), float("-inf"))
+    mx = torch.maximum(a.max(1).values, tl)
+    e, et = torch.exp(a - mx.unsqueeze(1)), torch.exp(tl - mx)
+    denom = e.sum(1) + et
+    return (e / denom.unsqueeze(1)).to(inputs.dtype), mx + torch.log(denom) - tl, et / denom - 1.0
+
+
+def _head_backward(G, inputs, w_all, g, row_w, dtrue, gi, d_w_all, db, grow):
+    """in place: G -> d_inputs; fills gi, d_w_all[:N], db[:N], grow (see `px_ssm_bwd`)."""
+    N, P = inputs.shape
+    if inputs.is_cuda:
+        _check(_lib().px_ssm_bwd(
+            _p(G), _p(inputs), _p(w_all), _p(g), 0 if g.numel() == 1 else 1,
+            _p(row_w) if row_w is not None else None, _p(dtrue), 1.0 / N, _p(gi), _p(d_w_all),
+            _p(db), 1 if db.dtype == torch.bfloat16 else 0, _p(grow), N, P, _DT[inputs.dtype],
+            _stream()), "ssm_bwd")
+        _count(1)
+        return
+    gr = g.reshape(-1).float() * (1.0 / N)
+    gr = gr.expand(N) if gr.numel() == 1 else gr
+    if row_w is not None:
+        gr = gr * row_w
+    gt = gr * dtrue
+    x, wt = inputs.float(), w_all[:N].float()
+    G.copy_(G.float() * gr.unsqueeze(1) + gt.unsqueeze(1) * wt)
+    gi.copy_(x * gr.unsqueeze(1))
+    d_w_all[:N].copy_(x * gt.unsqueeze(1))
+    db[:N].copy_(gt)
+    grow.copy_(gr)
+
+
+class _SampledSoftmaxHeadFn(torch.autograd.Function):
+    """mean (optionally row-weighted) sampled-softmax loss of `inputs` [N, P] against the
+    rows `w_all` / `b_all` of (targets ++ sampled).  Forward: logits GEMM + one kernel
+    (true-class dot product, bias - log Q, accidental hits, log-sum-exp, loss, softmax
+    probabilities in place).  Backward: two GEMMs, one GEMV and ONE glue kernel; the
+    gradients of the looked-up rows come out as single [N+S, ·] tensors in lookup order —
+    exactly what the co-lookup group's push kernel consumes (no slice / cat / cast
+    launches in between).  Reference: tf.nn.sampled_softmax_loss as used by
+    `examples/lm1b/language_model.py:96-107`."""
+
+    @staticmethod
+    def forward(ctx, inputs, w_all, b_all, adj, targets, sampled, row_w):
+        probs, loss, dtrue = _head_forward(inputs, w_all, adj, targets, sampled)
+        ctx.save_for_backward(inputs, w_all, probs, dtrue)
+        ctx.row_w = row_w
+        ctx.b_meta = (tuple(b_all.shape), b_all.dtype)
+        if row_w is not None:
+            loss = loss * row_w
+        return loss.mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        inputs, w_all, probs, dtrue = ctx.saved_tensors
+        N, P = inputs.shape
+        S = w_all.shape[0] - N
+        dt, dev = inputs.dtype, inputs.device
+        b_shape, b_dt = ctx.b_meta
+        g = g.float().contiguous()
+        G = probs @ w_all[N:]                                      # [N, P] -> d_inputs
+        d_w_all = torch.empty(N + S, P, dtype=dt, device=dev)
+        db = torch.empty(N + S, dtype=b_dt if b_dt in _DT else torch.float32, device=dev)
+        gi = torch.empty(N, P, dtype=dt, device=dev)
+        grow = torch.empty(N, dtype=dt, device=dev)
+        _head_backward(G, inputs, w_all, g, ctx.row_w, dtrue, gi, d_w_all, db, grow)
+        torch.mm(probs.t(), gi, out=d_w_all[N:])                   # d w_sampled
+        if db.dtype == dt:
+            torch.mm(probs.t(), grow.view(N, 1), out=db[N:].view(S, 1))
+        else:
+            db[N:].copy_((probs.t() @ grow.view(N, 1)).view(S))    # d b_sampled
+        db = db.view(b_shape)
+        if db.dtype != b_dt:
+            db = db.to(b_dt)
+        return G, d_w_all, db, None, None, None, None
+
+
+def sampled_softmax_head(inputs, w_all, b_all, logq, targets, sampled, row_w=None, adj=None):
+    """Scalar mean sampled-softmax loss.  `w_all` [N+S, P], `b_all` [N+S] or [N+S, 1] and
+    `logq` [N+S] are ordered (targets ++ sampled); `adj` may carry a precomputed
+    ``b - log Q`` (fp32, no gradient — the bias gradient is produced from `b_all`)."""
+    N, P = inputs.shape
+    S = w_all.shape[0] - N
+    dt = inputs.dtype
+    vec = 4 if dt == torch.float32 else 8
+    fused = (inputs.is_cuda and _head_enabled() and dt in _DT and w_all.dtype == dt and
+             0 < S <= 256 * 64 and P % vec == 0 and b_all.numel() == N + S)
+    if fused:
+        inputs = inputs.contiguous()
+        w_all = w_all.contiguous()
+        fused = inputs.data_ptr() % 16 == 0 and w_all.data_ptr() % 16 == 0
+    if not fused:
+        b = b_all.reshape(-1)
+        loss = sampled_softmax_loss(inputs, w_all[:N], w_all[N:], b[:N], b[N:], logq[:N],
+                                    logq[N:], targets, sampled)
+        if row_w is not None:
+            loss = loss * row_w.to(loss.dtype)
+        return loss.mean()
+    if adj is None:
+        adj = b_all.detach().reshape(-1).float() - logq
+    adj = adj.float().contiguous()
+    tg = targets.to(torch.int64).contiguous()
+    sm = sampled.to(torch.int64).contiguous()
+    rw = None if row_w is None else row_w.detach().float().contiguous()
+    return _SampledSoftmaxHeadFn.apply(inputs, w_all, b_all, adj, tg, sm, rw)

@@ -47,8 +47,10 @@ def deliver(param, event=None):
     _SINKS[param.data_ptr()][1](event)
 
 
-def side_stream(device):
-    key = torch.device(device).index or 0
+def side_stream(device, which=0):
+    """The device's side stream number `which` (0: weight-gradient GEMMs / prefetches,
+    1: bandwidth-bound reductions that overlap those GEMMs)."""
+    key = (torch.device(device).index or 0, int(which))
     s = _SIDE.get(key)
     if s is None:
         s = _SIDE[key] = torch.cuda.Stream(device)

@@ -88,3 +88,89 @@ def test_sampled_softmax_matches_reference(dtype, tol, S):
     for r, g in zip(ref, got):
         scale = float(r.abs().max()) + 1e-6
         assert float((r - g).abs().max()) <= tol * scale + tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 4e-2)])
+@pytest.mark.parametrize("S,weighted,b_dtype", [(100, False, torch.float32),
+                                               (1024, True, torch.bfloat16),
+                                               (8192, False, torch.bfloat16)])
+def test_sampled_softmax_head_matches_reference(dtype, tol, S, weighted, b_dtype):
+    """The loss head as ONE node (true-class dot product inside the softmax kernel, one
+    glue kernel in the backward pass, gradients of the looked-up rows as single [N+S, ·]
+    tensors) against the fp32 PyTorch composition."""
+    from parallax_b200.ops import fused
+    torch.manual_seed(2)
+    N, P, V = 96, 64, 5000
+    dev = "cuda"
+    inputs = torch.randn(N, P, device=dev) * 0.5
+    w_all = torch.randn(N + S, P, device=dev) * 0.5
+    b_all = torch.randn(N + S, 1, device=dev)
+    logq = torch.randn(N + S, device=dev)
+    targets = torch.randint(0, V, (N,), device=dev)
+    sampled = torch.randint(0, V, (S,), device=dev)
+    sampled[:5] = targets[:5]                      # accidental hits
+    rw = torch.rand(N, device=dev) if weighted else None
+    if dtype == torch.float32:
+        b_dtype = torch.float32
+
+    def run(head, dt, bdt):
+        a = [t.clone().to(dt).requires_grad_(True) for t in (inputs, w_all)]
+        b = b_all.clone().to(bdt).requires_grad_(True)
+        if head:
+            loss = fused.sampled_softmax_head(a[0], a[1], b, logq, targets, sampled, row_w=rw)
+            assert loss.grad_fn.name().startswith("_SampledSoftmaxHeadFn"), loss.grad_fn
+        else:
+            bb = b.reshape(-1)
+            loss = fused.sampled_softmax_reference(a[0], a[1][:N], a[1][N:], bb[:N], bb[N:],
+                                                   logq[:N], logq[N:], targets, sampled)
+            loss = (loss * rw if rw is not None else loss).mean()
+        (loss.float() * 7.0).backward()
+        return [loss.detach().float().reshape(1)] + [t.grad.float() for t in a] + \
+            [b.grad.float()]
+    ref = run(False, torch.float32, torch.float32)
+    got = run(True, dtype, b_dtype)
+    for r, g in zip(ref, got):
+        assert r.shape == g.shape
+        scale = float(r.abs().max()) + 1e-6
+        assert float((r - g).abs().max()) <= tol * scale + tol, \
+            (float((r - g).abs().max()), scale)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_lm1b_model_fused_paths_match_plain_pytorch(weighted, monkeypatch):
+    """LM1B forward + backward on the device (time-major rows, fused LSTM node, W_P^T on
+    the side stream, fused loss head) against the same model evaluated by the PyTorch
+    reference compositions on the CPU in fp32 — same weights, same negative samples."""
+    from parallax_b200.models import lm1b as L
+    torch.manual_seed(3)
+    B, T, V = 16, 5, 400
+    kw = dict(vocab_size=V, emb_size=32, state_size=64, projected_size=32, num_sampled=64,
+              num_steps=T, num_shards=1, keep_prob=1.0)
+    ref = L.LM1B(**kw)
+    dev_m = L.LM1B(**kw)
+    dev_m.load_state_dict(ref.state_dict())
+    dev_m.cuda()
+    x, y = torch.randint(0, V, (B, T)), torch.randint(0, V, (B, T))
+    w = torch.rand(B, T) if weighted else None
+    fixed = {}
+
+    def sampler(S, Vv, device, oversample=3):
+        if "s" not in fixed:
+            fixed["s"] = (torch.randperm(Vv)[:S], torch.tensor(float(S + 5)))
+        s, tries = fixed["s"]
+        return s.to(device), tries.to(device)
+    monkeypatch.setattr(L, "log_uniform_sample_unique", sampler)
+    out_r = ref(x, y, w)
+    out_r["loss"].backward()
+    out_d = dev_m(x.cuda(), y.cuda(), None if w is None else w.cuda())
+    assert out_d["loss"].grad_fn.name().startswith("_SampledSoftmaxHeadFn")
+    out_d["loss"].backward()
+    torch.cuda.synchronize()
+    assert abs(float(out_r["loss"]) - float(out_d["loss"])) < 1e-3
+    for k in ("final_state_c", "final_state_h"):
+        assert torch.allclose(out_r[k], out_d[k].cpu().float(), atol=1e-4)
+    for (n, p), (_, q) in zip(ref.named_parameters(), dev_m.named_parameters()):
+        g_r = p.grad.to_dense() if p.grad.is_sparse else p.grad
+        g_d = q.grad.to_dense() if q.grad.is_sparse else q.grad
+        scale = float(g_r.abs().max()) + 1e-6
+        assert float((g_r - g_d.cpu().float()).abs().max()) <= 2e-4 * scale + 1e-5, n
