@@ -589,10 +589,10 @@ class _SampledSoftmaxHeadFn(torch.autograd.Function):
         grow = torch.empty(N, dtype=dt, device=dev)
         _head_backward(G, inputs, w_all, g, ctx.row_w, dtrue, gi, d_w_all, db, grow)
         torch.mm(probs.t(), gi, out=d_w_all[N:])                   # d w_sampled
-        if db.dtype == dt:
+        if db.dtype == dt:                                         # d b_sampled
             torch.mm(probs.t(), grow.view(N, 1), out=db[N:].view(S, 1))
         else:
-            db[N:].copy_((probs.t() @ grow.view(N, 1)).view(S))    # d b_sampled
+            db[N:].copy_((probs.t() @ grow.view(N, 1)).view(S))
         db = db.view(b_shape)
         if db.dtype != b_dt:
             db = db.to(b_dt)
