@@ -85,6 +85,11 @@ def init(comm=None, workspace_bytes=64 << 20, oneshot_bytes=256 << 10):
     _state = _State(comm, workspace_bytes, oneshot_bytes)
     import os
     _registry_lib().px_registry_reset(int(os.environ.get("PARALLAX_CACHE_CAPACITY", 1024)))
+    if comm.rank == 0:
+        from . import consts
+        from .log import parallax_log
+        for name, why in consts.inert_horovod_env().items():
+            parallax_log.info("%s is set but has no effect: %s", name, why)
 
 
 def shutdown():

@@ -54,6 +54,19 @@ HOROVOD_ENV_ALIASES = {
     "HOROVOD_AUTOTUNE_LOG": PARALLAX_AUTOTUNE_LOG,
     "HOROVOD_CACHE_CAPACITY": "PARALLAX_CACHE_CAPACITY",
     "HOROVOD_LOG_LEVEL": PARALLAX_LOG_LEVEL,
+    "HOROVOD_TIMELINE_MARK_CYCLES": "PARALLAX_TIMELINE_MARK_CYCLES",
+}
+
+# Knobs of Horovod's background loop that have no counterpart in a design with a static
+# schedule (no 5 ms negotiation tick, no MPI, one NVSwitch domain): accepted, reported once.
+HOROVOD_INERT_ENV = {
+    "HOROVOD_CYCLE_TIME": "there is no negotiation cycle: collectives are launched from a "
+                          "static per-step schedule",
+    "HOROVOD_HIERARCHICAL_ALLREDUCE": "one NVSwitch domain per node: every GPU reaches every "
+                                      "peer at full bandwidth, there is no intra/inter level",
+    "HOROVOD_HIERARCHICAL_ALLGATHER": "one NVSwitch domain per node (see "
+                                      "HOROVOD_HIERARCHICAL_ALLREDUCE)",
+    "HOROVOD_MPI_THREADS_DISABLE": "no MPI in the process",
 }
 
 
@@ -67,6 +80,13 @@ def adopt_horovod_env(environ=None):
             env[dst] = env[src]
             adopted.append(dst)
     return adopted
+
+
+def inert_horovod_env(environ=None):
+    """{name: why it changes nothing here} for the Horovod knobs that are set but have no
+    effect in this design (logged once by `collectives.init` / the engine)."""
+    env = os.environ if environ is None else environ
+    return {k: why for k, why in HOROVOD_INERT_ENV.items() if k in env}
 
 
 def _user():

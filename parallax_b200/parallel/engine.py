@@ -273,6 +273,9 @@ class TrainEngine(object):
         self.timeline = timeline
         self.watchdog = None
         self.autotuner = None
+        if self.comm.rank == 0:
+            for name, why in consts.inert_horovod_env().items():
+                parallax_log.info("%s is set but has no effect: %s", name, why)
         try:
             timeline.start_from_env(self.comm.rank)
         except Exception as e:  # pragma: no cover
@@ -393,7 +396,10 @@ class TrainEngine(object):
         if tuning:
             self.autotuner.step_begin()
         if tl:
-            self.timeline.instant("CYCLE_START", args="step %d" % step)
+            # a training step is this design's "cycle" (HOROVOD_TIMELINE_MARK_CYCLES,
+            # `horovod/common/operations.cc:1286-1289`); marks are on unless set to 0
+            if os.environ.get("PARALLAX_TIMELINE_MARK_CYCLES", "1") != "0":
+                self.timeline.instant("CYCLE_START", args="step %d" % step)
             self.timeline.begin("step", "STEP", "global_step %d" % step)
         self._begin_step(step)
         # traced steps run eagerly (CUDA-event ranges cannot live inside a captured graph);

@@ -488,6 +488,11 @@ def test_horovod_environment_names_are_honoured():
     assert env["PARALLAX_TIMELINE"] == "/tmp/t.json" and env["PARALLAX_CACHE_CAPACITY"] == "64"
     assert env["PARALLAX_STALL_CHECK_TIME_SECONDS"] == "9"        # an explicit setting wins
     assert sorted(adopted) == ["PARALLAX_CACHE_CAPACITY", "PARALLAX_TIMELINE"]
+    # knobs of Horovod's negotiation loop are accepted and reported as having no effect
+    inert = consts.inert_horovod_env({"HOROVOD_CYCLE_TIME": "3.5", "HOROVOD_TIMELINE": "x",
+                                      "HOROVOD_HIERARCHICAL_ALLREDUCE": "1"})
+    assert sorted(inert) == ["HOROVOD_CYCLE_TIME", "HOROVOD_HIERARCHICAL_ALLREDUCE"]
+    assert "no negotiation cycle" in inert["HOROVOD_CYCLE_TIME"]
 
 
 def test_byte_greedy_placement_and_owner_chunks():
