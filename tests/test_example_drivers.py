@@ -87,3 +87,26 @@ def test_horovod_style_examples_under_run_cli(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     assert "Total img/sec on 2 worker(s)" in r.stdout
+
+
+@pytest.mark.parametrize("extra", [[], ["--sparse-as-dense"]])
+def test_horovod_style_word2vec_sparse_gradients(tmp_path, extra):
+    """Row-sparse embedding gradients through `DistributedOptimizer`: all-gather of (indices,
+    values) — Horovod's IndexedSlices path — or a dense all-reduce; replicas stay identical."""
+    env = {k: v for k, v in os.environ.items()
+           if not k.startswith("PARALLAX_") and k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env.update(CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "parallax_b200.run", "-np", "2",
+                        os.path.join(ROOT, "examples/horovod/pytorch_word2vec.py"),
+                        "--steps", "120", "--no-cuda"] + extra, env=env, cwd=ROOT,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    last = [l for l in r.stdout.splitlines() if "neighbour score" in l][-1]
+    first_loss, last_loss = (float(x) for x in
+                             last.split("loss ")[1].split(";")[0].split(" -> "))
+    assert last_loss < 0.3 * first_loss
+    nb, rnd = float(last.split("neighbour score ")[1].split()[0]), \
+        float(last.split("vs random ")[1].split(";")[0])
+    assert nb > rnd + 1.0
+    assert float(last.split("replica spread ")[1].split(";")[0]) < 1e-6
+    assert ("dense all-reduce" if extra else "all-gather of (indices, values)") in last
