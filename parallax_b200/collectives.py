@@ -704,6 +704,32 @@ def mpi_threads_supported():
     return True
 
 
+def mpi_built():
+    """Horovod scripts branch on this to pick a launcher; nothing here links MPI."""
+    return False
+
+
+def mpi_enabled():
+    return False
+
+
+def gloo_built():
+    """the host fabric (CPU tensors, bootstrap) runs over torch.distributed's gloo backend"""
+    import torch.distributed as dist
+    return bool(dist.is_available() and dist.is_gloo_available())
+
+
+def nccl_built():
+    """NCCL is reachable (`protocol="nccl"`, int / fp64 reductions, the bench's same-engine
+    arm); the default data path is the hand-written NVLink fabric, not NCCL."""
+    import torch.distributed as dist
+    return bool(dist.is_available() and dist.is_nccl_available())
+
+
+def cuda_built():
+    return bool(torch.cuda.is_available())
+
+
 def broadcast_object(obj, root_rank=0):
     """pickle-able python object from `root_rank` to everyone"""
     return _st().comm.broadcast_object(obj, root_rank)

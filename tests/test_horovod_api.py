@@ -15,6 +15,8 @@ def _worker(rank, world):
     hvd.init()
     out = {}
     assert hvd.mpi_threads_supported() and hvd.broadcast_object({"r": rank}, 1) == {"r": 1}
+    assert not hvd.mpi_built() and not hvd.mpi_enabled() and hvd.gloo_built()
+    assert isinstance(hvd.nccl_built(), bool) and hvd.cuda_built() == torch.cuda.is_available()
 
     # ---- DistributedOptimizer: gradient accumulation + fp16 compression ------------
     torch.manual_seed(0)
