@@ -95,6 +95,7 @@ def main():
     check("bf16 + graph trains (bf16 wire, bf16 shadow lookups)", trains(losses))
     variable_rows(comm, check)
     sharded_checkpoint(comm, check)
+    lm1b_flagship(comm, check)
 
     # public collectives vs NCCL
     from parallax_b200 import collectives as hvd
@@ -183,6 +184,34 @@ def variable_rows(comm, check):
             good = good and torch.allclose(sd["dense"]["master"][n], p.detach(),
                                            rtol=2e-4, atol=2e-5)
     check("variable rows per rank/step: rings re-negotiated (cap %d)" % grp.cap, good and grew)
+
+
+def lm1b_flagship(comm, check):
+    """The flagship step on N ranks (the smoke() shape: tcgen05 recurrent product, fused LSTM
+    and loss-head nodes, co-lookup group, gradient sinks, CUDA graph, bf16): finite losses and
+    bit-identical parameter replicas on every rank after 8 steps of different data per rank."""
+    from parallax_b200.models.lm1b import LM1B, lm1b_graph
+    world, rank = comm.world, comm.rank
+    torch.manual_seed(0)
+    B, T, V = 128, 4, 4096
+    model = LM1B(vocab_size=V, emb_size=64, state_size=256, projected_size=64, num_sampled=128,
+                 num_steps=T, num_shards=8)
+    cfg = parallax.Config(run_option="HYBRID", search_partitions=False,
+                          sess_config={"compute_dtype": "bf16", "cuda_graph": True})
+    sess, *_ = parallax.parallel_run(lm1b_graph(model, batch_size=B), "localhost", sync=True,
+                                     parallax_config=cfg)
+    g = torch.Generator().manual_seed(7 + rank)
+    losses = []
+    for _ in range(8):
+        x, y = torch.randint(0, V, (B, T), generator=g), torch.randint(0, V, (B, T), generator=g)
+        losses.append(float(sess.run(["loss", "train_op"], {"x": [x], "y": [y]})[0][0]))
+    m = sess.engine.model
+    digest = [float(p.detach().double().abs().sum()) for p in (m.W, m.B, m.W_P)]
+    sess.close()
+    every = comm.all_gather_object(digest)
+    same = all(d == every[0] for d in every)
+    check("LM1B flagship step (bf16, graph): finite, replicas identical (|W| %.6g)" % digest[0],
+          bool(np.isfinite(losses).all()) and same and losses[-1] < 2 * np.log(V))
 
 
 def sharded_checkpoint(comm, check):
