@@ -8,9 +8,8 @@ mkdir -p gpurun_out
 timeout 200 python -m pytest tests/test_gpu_fused.py -x -q > gpurun_out/t_fused.log 2>&1; echo "fused_rc=$?"
 tail -3 gpurun_out/t_fused.log
 STEPS=${STEPS:-300}
-ARMS=("default:" "ssm_rowcta:PARALLAX_SSM_MODE=0" \
-      "nodbias:PARALLAX_LSTM_DBIAS_STREAM=0" \
-      "default2:")
+ARMS=("default:" "head_unfused:PARALLAX_SSM_HEAD=0" "wpt_main:PARALLAX_LSTM_WPT_SIDE=0" \
+      "nodbias:PARALLAX_LSTM_DBIAS_STREAM=0" "default2:")
 for arm in "${ARMS[@]}"; do
   name=${arm%%:*}; envs=${arm#*:}
   env $envs timeout 90 python bench.py --no-extras --no-e2e --steps $STEPS --warmup 20 \
