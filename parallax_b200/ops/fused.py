@@ -567,8 +567,7 @@ class _SampledSoftmaxHeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inputs, w_all, b_all, adj, targets, sampled, row_w):
         probs, loss, dtrue = _head_forward(inputs, w_all, adj, targets, sampled)
-        ctx.save_for_backward(inputs, w_all, probs, dtrue)
-        ctx.row_w = row_w
+        ctx.save_for_backward(inputs, w_all, probs, dtrue, row_w)
         ctx.b_meta = (tuple(b_all.shape), b_all.dtype)
         if row_w is not None:
             loss = loss * row_w
@@ -576,7 +575,7 @@ class _SampledSoftmaxHeadFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        inputs, w_all, probs, dtrue = ctx.saved_tensors
+        inputs, w_all, probs, dtrue, row_w = ctx.saved_tensors
         N, P = inputs.shape
         S = w_all.shape[0] - N
         dt, dev = inputs.dtype, inputs.device
@@ -587,7 +586,7 @@ class _SampledSoftmaxHeadFn(torch.autograd.Function):
         db = torch.empty(N + S, dtype=b_dt if b_dt in _DT else torch.float32, device=dev)
         gi = torch.empty(N, P, dtype=dt, device=dev)
         grow = torch.empty(N, dtype=dt, device=dev)
-        _head_backward(G, inputs, w_all, g, ctx.row_w, dtrue, gi, d_w_all, db, grow)
+        _head_backward(G, inputs, w_all, g, row_w, dtrue, gi, d_w_all, db, grow)
         torch.mm(probs.t(), gi, out=d_w_all[N:])                   # d w_sampled
         if db.dtype == dt:                                         # d b_sampled
             torch.mm(probs.t(), grow.view(N, 1), out=db[N:].view(S, 1))
