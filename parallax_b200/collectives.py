@@ -613,9 +613,13 @@ class DistributedOptimizer(object):
     """Wrap a ``torch.optim.Optimizer``: gradients are averaged across ranks
     before `step()` (`horovod/torch/__init__.py:44-177`: per-parameter hooks
     fire `allreduce_async_` during backward, `synchronize()` waits).  Here the
-    hooks fuse gradients per dtype in reverse-registration order and reduce
-    them with the fabric kernels; sparse gradients are all-gathered unless
-    `sparse_as_dense` (`horovod/tensorflow/__init__.py:189-192`)."""
+    per-parameter hooks only count backward passes; `synchronize()` — called by
+    `step()` — reduces all dense gradients of one dtype as ONE fused group
+    (`grouped_allreduce`) on the fabric kernels, i.e. after the backward pass,
+    not underneath it (the `parallel_run` engine is the path that launches
+    bucket kernels from autograd hooks on a comm stream while backward still
+    runs).  Sparse gradients are all-gathered unless `sparse_as_dense`
+    (`horovod/tensorflow/__init__.py:189-192`)."""
 
     def __init__(self, optimizer, named_parameters=None, sparse_as_dense=False,
                  compression=None, backward_passes_per_step=1):
