@@ -141,6 +141,76 @@ def load_sharded(engine, path):
     return manifest
 
 
+def is_sharded(path):
+    return os.path.isdir(path) and os.path.exists(os.path.join(path, MANIFEST))
+
+
+def list_checkpoints(ckpt_dir):
+    """[(global_step, path)] of every checkpoint in `ckpt_dir`, either format, oldest first"""
+    out = []
+    for f in os.listdir(ckpt_dir):
+        if not f.startswith(PREFIX):
+            continue
+        path = os.path.join(ckpt_dir, f)
+        m = re.match(r"^(\d+)(\.pt)?$", f[len(PREFIX):])
+        if m and (f.endswith(".pt") or is_sharded(path)):
+            out.append((int(m.group(1)), path))
+    return sorted(out)
+
+
+def load_logical(path, max_table_bytes=None):
+    """The logical (layout-independent) state dict of a checkpoint in either format — what
+    offline consumers (evaluation scripts, checkpoint averaging, the inspection tool) read."""
+    if is_sharded(path):
+        return assemble_sharded(path, max_table_bytes)
+    return torch.load(path, map_location="cpu", weights_only=False)
+
+
+def read_manifest(path):
+    with open(os.path.join(path, MANIFEST)) as f:
+        return json.load(f)
+
+
+def assemble_table(path, name, manifest=None):
+    """One sparse variable of a sharded checkpoint as full logical tensors
+    ``{"weight": [V, D], "slots": [[V, D], ...]}`` — no engine, no GPU: what an offline tool
+    (`tools/inspect_checkpoint`, an evaluation script on another machine) needs."""
+    man = manifest or read_manifest(path)
+    ent = man["sparse"][name]
+    V, D, ns = int(ent["V"]), int(ent["D"]), int(ent["nslots"])
+    w, slots, seen = None, None, 0
+    for fn in ent["files"]:
+        sh = torch.load(os.path.join(path, fn), map_location="cpu", weights_only=False)
+        if w is None:
+            w = torch.zeros(V, D, dtype=sh["weight"].dtype)
+            slots = [torch.zeros(V, D, dtype=s_.dtype) for s_ in sh["slots"][:ns]]
+        w[sh["ids"]] = sh["weight"]
+        for dst, src in zip(slots, sh["slots"]):
+            dst[sh["ids"]] = src
+        seen += int(sh["ids"].numel())
+    if seen != V:
+        raise RuntimeError("sharded checkpoint %s: variable %r has %d of %d rows in its shards"
+                           % (path, name, seen, V))
+    return {"weight": w, "slots": slots}
+
+
+def assemble_sharded(path, max_table_bytes=None):
+    """A sharded checkpoint directory as the single-file logical state dict
+    (``global_step`` / ``dense`` / ``buffers`` / ``sparse``).  Tables whose assembled size
+    would exceed `max_table_bytes` are left out and listed under ``"skipped"``."""
+    man = read_manifest(path)
+    d = torch.load(os.path.join(path, "dense.pt"), map_location="cpu", weights_only=False)
+    sd = {"global_step": int(d["global_step"]), "dense": d.get("dense"),
+          "buffers": d.get("buffers", {}), "sparse": {}, "skipped": []}
+    for name, ent in sorted(man["sparse"].items()):
+        nbytes = int(ent["V"]) * int(ent["D"]) * 4 * (1 + int(ent["nslots"]))
+        if max_table_bytes is not None and nbytes > max_table_bytes:
+            sd["skipped"].append(name)
+            continue
+        sd["sparse"][name] = assemble_table(path, name, man)
+    return sd
+
+
 class CheckpointSaver(object):
     """`CheckpointSaverHook` analogue: `after_step` is called by the session
     after every training step on *all* workers."""

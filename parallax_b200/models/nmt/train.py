@@ -56,16 +56,13 @@ def avg_checkpoints(ckpt_dir, num_last_checkpoints, out_dir=None):
     """Average the dense/sparse weights of the last N checkpoints
     (`model_helper.py:473-536`); optimizer slots and the step are taken from the
     newest.  Returns the path written (``<ckpt_dir>/avg_checkpoints`` by default)."""
-    names = [f for f in os.listdir(ckpt_dir)
-             if f.startswith(_ckpt.PREFIX) and f.endswith(".pt")]
-    names.sort(key=lambda f: int(f[len(_ckpt.PREFIX):-3]))
-    names = names[-int(num_last_checkpoints):]
-    if len(names) < num_last_checkpoints:
-        log.info("skipping averaging: only %d checkpoints", len(names))
+    found = _ckpt.list_checkpoints(ckpt_dir)[-int(num_last_checkpoints):]   # either format
+    if len(found) < num_last_checkpoints:
+        log.info("skipping averaging: only %d checkpoints", len(found))
         return None
-    states = [torch.load(os.path.join(ckpt_dir, n), map_location="cpu", weights_only=False)
-              for n in names]
+    states = [_ckpt.load_logical(path) for _, path in found]
     avg = states[-1]
+    avg.pop("skipped", None)
 
     def mean_into(dst, srcs):
         for k, v in dst.items():

@@ -208,7 +208,7 @@ def main(argv=None):          # pragma: no cover - thin CLI
         if ck:
             from ... import checkpoint as _ckpt
             path = _ckpt.latest_checkpoint(ck) if os.path.isdir(ck) else ck
-            state = torch.load(path, map_location="cpu", weights_only=False)
+            state = _ckpt.load_logical(path)
             mgr.load_model(configuration.model_config(bidirectional_encoder=bidi),
                            getattr(a, kind + "_vocab_file"),
                            getattr(a, kind + "_embeddings_file"), state)

@@ -42,7 +42,7 @@ def run_once(model_config, checkpoint_dir, num_eval_examples=50000, min_global_s
     if path is None:
         log.info("Skipping evaluation. No checkpoint found in: %s", checkpoint_dir)
         return None
-    state = torch.load(path, map_location="cpu", weights_only=False)
+    state = _ckpt.load_logical(path)          # single file or the NVLink fabric's sharded directory
     step = int(state["global_step"])
     if step < min_global_step or step == last_step:
         log.info("Skipping evaluation. Global step = %d (min %d, last %s)", step,

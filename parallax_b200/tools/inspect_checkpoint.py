@@ -1,6 +1,6 @@
 """Inspect / convert Parallax checkpoints.
 
-    python -m parallax_b200.tools.inspect_checkpoint <ckpt_dir | model.ckpt-N.pt>
+    python -m parallax_b200.tools.inspect_checkpoint <ckpt_dir | model.ckpt-N.pt | model.ckpt-N/>
     python -m parallax_b200.tools.inspect_checkpoint <ckpt> --tensor W_P
     python -m parallax_b200.tools.inspect_checkpoint <ckpt> --to_state_dict out.pt [--ema]
 
@@ -9,7 +9,9 @@ The counterpart of TensorFlow's `inspect_checkpoint` for the reference's
 (dense master weights, optimizer slots, EMA shadows, sparse tables and their
 slots) with shape / dtype / bytes, prints one tensor, or writes a plain
 ``name → tensor`` state_dict loadable into the single-device model
-(`--ema` substitutes the EMA shadows, like `lm1b_eval.py:96-104`).
+(`--ema` substitutes the EMA shadows, like `lm1b_eval.py:96-104`).  Sharded
+checkpoints of the NVLink fabric (a directory with a manifest and one file per
+owner) are assembled offline, without an engine or a GPU.
 """
 import argparse
 import os
@@ -20,13 +22,20 @@ import torch
 from .. import checkpoint as _ckpt
 
 
-def load(path):
-    if os.path.isdir(path):
+_is_sharded = _ckpt.is_sharded
+
+
+def load(path, max_table_bytes=None):
+    """(resolved path, logical state dict).  `path`: a checkpoint directory (its latest
+    checkpoint is taken), a single-file checkpoint, or a sharded checkpoint directory
+    (`model.ckpt-N/` with a manifest and one shard file per owner), which is assembled
+    offline — tables larger than `max_table_bytes` are only listed."""
+    if os.path.isdir(path) and not _is_sharded(path):
         found = _ckpt.latest_checkpoint(path)
         if found is None:
             raise FileNotFoundError("no checkpoint in %s" % path)
         path = found
-    return path, torch.load(path, map_location="cpu", weights_only=False)
+    return path, _ckpt.load_logical(path, max_table_bytes)
 
 
 def entries(sd):
@@ -76,6 +85,8 @@ def summarize(sd, out=sys.stdout):
             kind, name, "x".join(map(str, t.shape)) or "scalar",
             str(t.dtype).replace("torch.", ""), nbytes))
     out.write("total: %.2f MiB in %d tensors\n" % (total / 2 ** 20, len(entries(sd))))
+    for name in sd.get("skipped", []):
+        out.write("not assembled (larger than --max_table_gib): %s\n" % name)
     return total
 
 
@@ -85,9 +96,12 @@ def main(argv=None):
     ap.add_argument("--tensor", default=None, help="print this variable's values")
     ap.add_argument("--to_state_dict", default=None, help="write a plain state_dict here")
     ap.add_argument("--ema", action="store_true", help="use EMA shadows where they exist")
+    ap.add_argument("--max_table_gib", type=float, default=8.0,
+                    help="sharded checkpoints: do not assemble tables larger than this")
     a = ap.parse_args(argv)
-    path, sd = load(a.checkpoint)
-    print("checkpoint:", path)
+    path, sd = load(a.checkpoint, int(a.max_table_gib * 2 ** 30))
+    print("checkpoint:", path + (" (sharded: %d sparse variable(s) assembled from their owners' "
+                                 "files)" % len(sd["sparse"]) if _is_sharded(path) else ""))
     if a.tensor:
         hits = [(k, n, t) for k, n, t in entries(sd) if n == a.tensor]
         if not hits:

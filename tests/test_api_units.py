@@ -629,3 +629,41 @@ def test_sharded_checkpoint_resharding_logic(tmp_path):
         got_w[g], got_s[g] = t.w[l], t.s[l]
     torch.testing.assert_close(got_w, full)
     torch.testing.assert_close(got_s, slot)
+    # offline: the inspection tool assembles the shards without an engine
+    import io
+    from parallax_b200.tools import inspect_checkpoint as ic
+    for target in (d, str(tmp_path)):                    # the checkpoint itself / its directory
+        path, sd = ic.load(target)
+        assert path == d and sd["global_step"] == 7 and sd["skipped"] == []
+        torch.testing.assert_close(sd["sparse"]["emb.weight"]["weight"], full)
+        torch.testing.assert_close(sd["sparse"]["emb.weight"]["slots"][0], slot)
+    buf = io.StringIO()
+    ic.summarize(sd, buf)
+    assert "sparse-slot0" in buf.getvalue() and "101x3" in buf.getvalue()
+    torch.testing.assert_close(ic.to_state_dict(sd)["emb.weight"], full)
+    _, small = ic.load(d, max_table_bytes=100)           # too large to assemble: only listed
+    assert small["sparse"] == {} and small["skipped"] == ["emb.weight"]
+    out = str(tmp_path / "plain.pt")
+    assert ic.main([d, "--to_state_dict", out]) == 0
+    torch.testing.assert_close(torch.load(out)["emb.weight"], full)
+    # offline consumers read either format: a second (sharded) checkpoint, then the average
+    full2 = full + 2.0
+    d2 = str(tmp_path / "model.ckpt-9")
+    os.makedirs(d2)
+    for r in range(2):
+        e = _Engine(_Comm(r, 2), _Table(V, D, 4, 2, r, full2, slot))
+        e.global_step = 9
+        ckpt.save_sharded(e, d2, r == 0)
+    torch.save({"global_step": 3, "dense": None, "buffers": {},
+                "sparse": {"emb.weight": {"weight": full - 2.0, "slots": [slot]}}},
+               str(tmp_path / "model.ckpt-3.pt"))           # and an older single-file one
+    assert [st for st, _ in ckpt.list_checkpoints(str(tmp_path))] == [3, 7, 9]
+    assert ckpt.load_logical(str(tmp_path / "model.ckpt-3.pt"))["global_step"] == 3
+    from parallax_b200.models.nmt.train import avg_checkpoints
+    avg_path = avg_checkpoints(str(tmp_path), 3)
+    avg = torch.load(avg_path, weights_only=False)
+    assert avg["global_step"] == 9
+    torch.testing.assert_close(avg["sparse"]["emb.weight"]["weight"], full)     # mean of -2, 0, +2
+    os.remove(os.path.join(d, files[3]))                 # a missing shard is an error, not zeros
+    with pytest.raises((RuntimeError, FileNotFoundError)):
+        ckpt.assemble_table(d, "emb.weight")
