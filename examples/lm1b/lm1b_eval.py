@@ -49,9 +49,11 @@ def main():
     sess, *_ = parallax.parallel_run(graph, "localhost", parallax_config=cfg)   # restores on start
     eng = sess.engine
     if FLAGS.use_ema and eng.dense is not None:
-        sd = eng.state_dict()
-        sd["dense"]["master"].update(sd["dense"]["ema"])
-        eng.load_state_dict(sd)
+        # evaluate with the EMA shadows of the LSTM variables (`lm1b_eval.py:96-104`); only
+        # the dense group is touched — the sparse tables stay where they are
+        d = eng.dense.state_dict()
+        d["master"].update(d["ema"])
+        eng.dense.load_state_dict(d)
     eng.model.eval()                       # full softmax, no dropout
     V = model.vocab_size
     if FLAGS.use_synthetic or not FLAGS.datadir:

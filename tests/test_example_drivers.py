@@ -110,3 +110,30 @@ def test_horovod_style_word2vec_sparse_gradients(tmp_path, extra):
     assert nb > rnd + 1.0
     assert float(last.split("replica spread ")[1].split(";")[0]) < 1e-6
     assert ("dense all-reduce" if extra else "all-gather of (indices, values)") in last
+
+
+def test_lm1b_train_checkpoint_then_eval_with_and_without_ema(tmp_path):
+    """`lm1b_distributed_driver.py` writes checkpoints, `lm1b_eval.py` restores the latest one and
+    reports the perplexity of the full softmax — with the raw weights and with the EMA shadows of
+    the LSTM variables (`examples/lm1b/lm1b_eval.py:96-104` of the reference)."""
+    env = {k: v for k, v in os.environ.items()
+           if not k.startswith("PARALLAX_") and k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env.update(PARALLAX_FABRIC="host", CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="2")
+    ck = str(tmp_path / "ck")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "examples/lm1b/lm1b_distributed_driver.py"),
+                        "--use_synthetic", "--tiny", "--max_steps", "12", "--ckpt_dir", ck,
+                        "--save_ckpt_steps", "6", "--logdir", str(tmp_path / "log")],
+                       env=env, cwd=str(tmp_path), capture_output=True, text=True, timeout=400)
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert os.path.exists(os.path.join(ck, "model.ckpt-12.pt"))
+    ppl = {}
+    for extra in ([], ["--use_ema"]):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "examples/lm1b/lm1b_eval.py"),
+                            "--use_synthetic", "--tiny", "--ckpt_dir", ck, "--max_batches", "3"]
+                           + extra, env=env, cwd=str(tmp_path), capture_output=True, text=True,
+                           timeout=400)
+        assert r.returncode == 0, r.stderr[-1500:]
+        assert "global_step 12" in r.stderr + r.stdout
+        ppl[bool(extra)] = float(r.stdout.strip().splitlines()[-1].split()[1])
+    assert all(1000.0 < v < 1e6 for v in ppl.values())       # ~ vocabulary size on random ids
+    assert ppl[True] != ppl[False]                            # the EMA shadows were used
