@@ -101,5 +101,13 @@ loss = fused.sampled_softmax_loss(inp, tw, sw, torch.zeros(N, device=dev),
                                   torch.randint(0, V, (N,), device=dev),
                                   torch.randint(0, V, (Sn,), device=dev))
 loss.sum().backward()
+# ---- the loss head as one node (dot product inside the softmax kernel, one backward glue
+# kernel) at the LM1B shape
+w_all = torch.randn(N + Sn, P, device=dev).bfloat16().requires_grad_(True)
+b_all = torch.zeros(N + Sn, 1, device=dev).bfloat16().requires_grad_(True)
+head = fused.sampled_softmax_head(inp, w_all, b_all, torch.zeros(N + Sn, device=dev),
+                                  torch.randint(0, V, (N,), device=dev),
+                                  torch.randint(0, V, (Sn,), device=dev))
+head.backward()
 torch.cuda.synchronize()
 print("ncu targets done")
