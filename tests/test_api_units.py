@@ -667,3 +667,59 @@ def test_sharded_checkpoint_resharding_logic(tmp_path):
     os.remove(os.path.join(d, files[3]))                 # a missing shard is an error, not zeros
     with pytest.raises((RuntimeError, FileNotFoundError)):
         ckpt.assemble_table(d, "emb.weight")
+
+
+def test_sharded_checkpoint_restores_on_the_host_fabric(tmp_path):
+    """A checkpoint directory as GPU owners write it (manifest + one shard file per owner) restores
+    into a host-fabric engine with another partition count — train on the NVLink fabric, evaluate
+    anywhere — and `CheckpointSaver.restore_if_present` picks it up from the checkpoint directory."""
+    import json
+    from parallax_b200 import checkpoint as ckpt
+    from parallax_b200.models.simple import MLPWithEmbedding
+    from parallax_b200.utils import selfcheck as sc
+
+    def make(nparts, ckpt_dir=None):
+        torch.manual_seed(0)
+        model = MLPWithEmbedding(sc.VOCAB, partitioner=parallax.get_partitioner(nparts))
+        g = parallax.Graph(model, optimizer=optim.Adagrad(0.2, initial_accumulator_value=1.0))
+        cfg = parallax.Config(run_option="HYBRID", search_partitions=False,
+                              sess_config={"fabric": "host"})
+        if ckpt_dir:
+            cfg.ckpt_config = parallax.CheckPointConfig(ckpt_dir=ckpt_dir)
+        sess, *_ = parallax.parallel_run(g, "localhost", sync=True, parallax_config=cfg)
+        return sess
+
+    s1 = make(5)
+    for s in range(3):
+        ids, labels = sc.make_batch(s, 1, 0)
+        s1.run(["loss", "train_op"], {"ids": [ids], "labels": [labels]})
+    sd = s1.engine.state_dict()
+    s1.close()
+    d = str(tmp_path / "model.ckpt-3")
+    os.makedirs(d)
+    man = {"format": 2, "global_step": 3, "world": 2, "run_option": "HYBRID", "sparse": {}}
+    for name, ent in sd["sparse"].items():
+        V, D = ent["weight"].shape
+        files = []
+        for r in range(2):                                   # two owners, rows dealt round-robin
+            rows = torch.arange(r, V, 2)
+            fn = "sparse-%s-rank%d.pt" % (name, r)
+            torch.save({"ids": rows, "weight": ent["weight"][rows],
+                        "slots": [s_[rows] for s_ in ent["slots"]]}, os.path.join(d, fn))
+            files.append(fn)
+        man["sparse"][name] = {"V": V, "D": D, "nslots": len(ent["slots"]), "files": files,
+                               "placement": [2, "mod", 2, [0, 1], False]}
+    torch.save({"global_step": 3, "dense": sd["dense"], "buffers": sd["buffers"]},
+               os.path.join(d, "dense.pt"))
+    with open(os.path.join(d, "manifest.json"), "w") as f:
+        json.dump(man, f)
+    s2 = make(3, ckpt_dir=str(tmp_path))                     # restore-on-start finds the directory
+    sd2 = s2.engine.state_dict()
+    s2.close()
+    assert sd2["global_step"] == 3
+    for name in sd["sparse"]:
+        assert torch.equal(sd2["sparse"][name]["weight"], sd["sparse"][name]["weight"])
+        for a, b in zip(sd2["sparse"][name]["slots"], sd["sparse"][name]["slots"]):
+            assert torch.equal(a, b)
+    for n, v in sd["dense"]["master"].items():
+        assert torch.equal(sd2["dense"]["master"][n], v)
